@@ -1,0 +1,122 @@
+/* zb200.h -- C-ABI extensions of the zb200 engine (additive to zlib.h).
+ *
+ * zlib.h's calls take one host buffer at a time and 32-bit lengths
+ * (h/zlib.h:84,88,1285 in the reference).  The work a B200 is good at is the
+ * same arithmetic over device-resident data and over many independent streams
+ * at once.  These entry points expose exactly that, with plain pointers and
+ * sizes only, so that a maintainer of the reference can bind them from C (or
+ * cgo / JNI / ctypes) without any CUDA or torch type.  Each one names the
+ * reference routine whose arithmetic it performs.
+ *
+ * Conventions
+ *   - Every buffer argument may be host memory (pageable or pinned) or device
+ *     memory of the current device; the library detects which.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = CUDA's default stream 0,
+ *     as everywhere in CUDA).  Calls whose results land in host variables synchronise that
+ *     stream before returning; the *_dev variants never synchronise.
+ *   - Return value: Z_OK (0) or a negative zlib error code; text of the last
+ *     failure on this thread is available from zb200_last_error().
+ *   - There is no CPU implementation behind any of these.
+ */
+#ifndef ZB200_H
+#define ZB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZB200_WRAP_RAW   0      /* windowBits < 0      (qcsrc/deflate.c:255-258) */
+#define ZB200_WRAP_ZLIB  1      /* windowBits 8..15    RFC 1950 */
+#define ZB200_WRAP_GZIP  2      /* windowBits + 16     RFC 1952 (qcsrc/deflate.c:259-264) */
+
+#define ZB200_CHUNK      131072u /* input bytes per independently parsed chunk */
+
+/* ---- lifetime ---------------------------------------------------------- */
+int         zb200_init(int device);          /* device < 0: keep the current device */
+int         zb200_device_count(void);
+const char *zb200_last_error(void);
+const char *zb200_build_info(void);          /* "sm_100a, nvcc x.y, ..." */
+
+/* Pinned host memory and device memory without CUDA headers. */
+void *zb200_alloc_pinned(size_t bytes);
+void  zb200_free_pinned(void *p);
+void *zb200_alloc_device(size_t bytes);
+void  zb200_free_device(void *p);
+int   zb200_copy(void *dst, const void *src, size_t bytes, void *stream);   /* any direction, synchronous */
+int   zb200_sync(void *stream);
+
+/* ---- checksums: crc32() + adler32() in one pass (qcsrc/crc32.c:219, adler32.c:57) ----
+ * Computes crc32(0, buf, len) and adler32(1, buf, len); either result pointer may
+ * be NULL.  len is 64-bit (the reference's uInt len forces callers to slice). */
+int zb200_checksum(const void *buf, size_t len, uint32_t *crc, uint32_t *adler, void *stream);
+
+/* Device-resident form: out2[0] = crc32, out2[1] = adler32, written by the GPU. */
+int zb200_checksum_dev(const void *d_buf, size_t len, uint32_t *d_out2, void *stream);
+
+/* n independent buffers in one launch sequence (per-file CRCs of a ZIP archive,
+ * per-slice checksums ahead of a _combine tree).  offsets has n+1 entries. */
+int zb200_checksum_batch(const void *base, const uint64_t *offsets, size_t n,
+                         uint32_t *crc, uint32_t *adler, void *stream);
+
+/* ---- deflate: whole buffer -> one stream (qcsrc/compress.c:22 compress2) ----
+ * Input is cut into ZB200_CHUNK-byte chunks, each parsed with the previous
+ * 32 KiB as its dictionary, each ending byte-aligned; the result is one valid
+ * raw / zlib / gzip stream.  level 0..9 or -1.  *dst_len: in = capacity,
+ * out = bytes written.  Z_BUF_ERROR if the capacity is too small. */
+int zb200_deflate(const void *src, size_t src_len, void *dst, size_t *dst_len,
+                  int level, int wrap, void *stream);
+
+/* As above, also returning what a multi-GPU assembler needs: the checksums of
+ * the UNCOMPRESSED input (for crc32_combine / adler32_combine across ranks).
+ * flags: bit0 = this shard is not the last one (do not set BFINAL, end on a
+ *        byte boundary with an empty stored block instead);
+ *        bit1 = omit the stream header; bit2 = omit the trailer.
+ * dict/dict_len: up to 32 KiB that precedes src in the logical stream (the tail
+ * of the previous rank's shard), or NULL. */
+#define ZB200_DEFLATE_NOT_LAST   1
+#define ZB200_DEFLATE_NO_HEADER  2
+#define ZB200_DEFLATE_NO_TRAILER 4
+int zb200_deflate_shard(const void *src, size_t src_len, const void *dict, size_t dict_len,
+                        void *dst, size_t *dst_len, int level, int wrap, int flags,
+                        uint32_t *crc, uint32_t *adler, void *stream);
+
+/* n independent inputs -> n independent streams (minizip-style per-file streams).
+ * src/dst are single arenas; src_off and dst_off have n+1 entries (dst_off gives
+ * each stream's slot, which must hold compressBound of its input). */
+int zb200_deflate_batch(const void *src, const uint64_t *src_off, size_t n,
+                        void *dst, const uint64_t *dst_off, uint64_t *dst_len,
+                        uint32_t *crc, uint32_t *adler, int32_t *status,
+                        int level, int wrap, void *stream);
+
+/* ---- inflate: n independent streams (qcsrc/uncompr.c:26 uncompress, batched) ----
+ * Stream i occupies src[src_off[i] .. src_off[i+1]) and is decoded into
+ * dst[dst_off[i] .. dst_off[i+1]).  Per stream: dst_len[i] = bytes produced,
+ * status[i] = Z_OK / Z_DATA_ERROR / Z_BUF_ERROR with uncompress()'s mapping
+ * (qcsrc/uncompr.c:53-55).  Returns Z_OK if the batch ran, whatever the per-stream
+ * statuses are. */
+int zb200_inflate_batch(const void *src, const uint64_t *src_off, size_t n,
+                        void *dst, const uint64_t *dst_off, uint64_t *dst_len,
+                        int32_t *status, int wrap, void *stream);
+
+/* Fully device-resident form: every pointer is device memory, nothing is copied,
+ * nothing synchronises. */
+int zb200_inflate_batch_dev(const void *d_src, const uint64_t *d_src_off, size_t n,
+                            void *d_dst, const uint64_t *d_dst_off, uint64_t *d_dst_len,
+                            int32_t *d_status, int wrap, void *stream);
+
+/* ---- instrumentation -------------------------------------------------- */
+/* Number of kernels this library has launched since load (all threads). */
+uint64_t zb200_kernel_launches(void);
+
+/* Synthetic corpora of SURVEY.md section 8(d): kind 0 = text (T), 1 = mixed (M),
+ * 2 = xorshift64* noise.  Deterministic in (kind, seed, offset); host memory only.
+ * Workload generator for benchmarks and tests, not part of the codec. */
+void zb200_synth(void *host_dst, size_t len, int kind, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZB200_H */

@@ -1,0 +1,224 @@
+"""ctypes binding of libzb200.so: every symbol of include/zlib.h and include/zb200.h.
+
+Mirrors the reference's C interface one to one (same names, argument order and
+return codes as h/zlib.h in ChrisHird/ZLIB), so tests read like the reference's
+example.c.  Loading is RTLD_LOCAL|RTLD_DEEPBIND: the library exports the same
+names as the system libz that CPython itself links, and must never interpose.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple, Union
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libzb200.so")
+
+Z_OK, Z_STREAM_END, Z_NEED_DICT = 0, 1, 2
+Z_ERRNO, Z_STREAM_ERROR, Z_DATA_ERROR, Z_MEM_ERROR, Z_BUF_ERROR, Z_VERSION_ERROR = -1, -2, -3, -4, -5, -6
+Z_NO_FLUSH, Z_PARTIAL_FLUSH, Z_SYNC_FLUSH, Z_FULL_FLUSH, Z_FINISH, Z_BLOCK = 0, 1, 2, 3, 4, 5
+Z_DEFLATED = 8
+WRAP_RAW, WRAP_ZLIB, WRAP_GZIP = 0, 1, 2
+ZLIB_VERSION = b"1.2.3"
+
+
+class z_stream(C.Structure):
+    """h/zlib.h:82-101 (112 bytes on LP64)."""
+    _fields_ = [
+        ("next_in", C.c_void_p), ("avail_in", C.c_uint), ("total_in", C.c_ulong),
+        ("next_out", C.c_void_p), ("avail_out", C.c_uint), ("total_out", C.c_ulong),
+        ("msg", C.c_char_p), ("state", C.c_void_p),
+        ("zalloc", C.c_void_p), ("zfree", C.c_void_p), ("opaque", C.c_void_p),
+        ("data_type", C.c_int), ("adler", C.c_ulong), ("reserved", C.c_ulong),
+    ]
+
+
+Buf = Union[bytes, bytearray, memoryview, int, "C.Array"]
+
+
+def _ptr(buf) -> Tuple[C.c_void_p, Optional[object]]:
+    """(pointer, keep-alive) for bytes-like objects, numpy arrays or raw addresses."""
+    if buf is None:
+        return C.c_void_p(0), None
+    if isinstance(buf, int):
+        return C.c_void_p(buf), None
+    if isinstance(buf, bytes):
+        return C.cast(C.c_char_p(buf), C.c_void_p), buf
+    if hasattr(buf, "ctypes") and hasattr(buf, "nbytes"):        # numpy
+        return C.c_void_p(buf.ctypes.data), buf
+    if hasattr(buf, "data_ptr"):                                  # torch tensor
+        return C.c_void_p(buf.data_ptr()), buf
+    if isinstance(buf, C.Array):
+        return C.cast(buf, C.c_void_p), buf
+    mv = memoryview(buf)
+    arr = (C.c_char * mv.nbytes).from_buffer(mv.obj if not mv.readonly else bytearray(mv))
+    return C.cast(arr, C.c_void_p), arr
+
+
+def _stream(stream) -> C.c_void_p:
+    if stream is None:
+        return C.c_void_p(0)
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(stream.cuda_stream)                         # torch.cuda.Stream
+
+
+class Lib:
+    """One loaded copy of libzb200.so."""
+
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(zlib_b200 has no fallback implementation)")
+        self.path = path
+        self.dll = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_DEEPBIND)
+        d = self.dll
+        ul, ui, vp, sz = C.c_ulong, C.c_uint, C.c_void_p, C.c_size_t
+        u32p, u64p, i32p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
+        zsp = C.POINTER(z_stream)
+        sig = {
+            # zlib.h
+            "zlibVersion": (C.c_char_p, []), "zlibCompileFlags": (ul, []), "zError": (C.c_char_p, [C.c_int]),
+            "get_crc_table": (C.POINTER(ul), []), "inflateSyncPoint": (C.c_int, [zsp]),
+            "deflate": (C.c_int, [zsp, C.c_int]), "deflateEnd": (C.c_int, [zsp]),
+            "deflateSetDictionary": (C.c_int, [zsp, vp, ui]), "deflateCopy": (C.c_int, [zsp, zsp]),
+            "deflateReset": (C.c_int, [zsp]), "deflateParams": (C.c_int, [zsp, C.c_int, C.c_int]),
+            "deflateTune": (C.c_int, [zsp, C.c_int, C.c_int, C.c_int, C.c_int]),
+            "deflateBound": (ul, [zsp, ul]), "deflatePrime": (C.c_int, [zsp, C.c_int, C.c_int]),
+            "deflateSetHeader": (C.c_int, [zsp, vp]),
+            "inflate": (C.c_int, [zsp, C.c_int]), "inflateEnd": (C.c_int, [zsp]),
+            "inflateSetDictionary": (C.c_int, [zsp, vp, ui]), "inflateSync": (C.c_int, [zsp]),
+            "inflateCopy": (C.c_int, [zsp, zsp]), "inflateReset": (C.c_int, [zsp]),
+            "inflatePrime": (C.c_int, [zsp, C.c_int, C.c_int]), "inflateGetHeader": (C.c_int, [zsp, vp]),
+            "compress": (C.c_int, [vp, C.POINTER(ul), vp, ul]),
+            "compress2": (C.c_int, [vp, C.POINTER(ul), vp, ul, C.c_int]),
+            "compressBound": (ul, [ul]), "uncompress": (C.c_int, [vp, C.POINTER(ul), vp, ul]),
+            "adler32": (ul, [ul, vp, ui]), "adler32_combine": (ul, [ul, ul, C.c_long]),
+            "crc32": (ul, [ul, vp, ui]), "crc32_combine": (ul, [ul, ul, C.c_long]),
+            "deflateInit_": (C.c_int, [zsp, C.c_int, C.c_char_p, C.c_int]),
+            "inflateInit_": (C.c_int, [zsp, C.c_char_p, C.c_int]),
+            "deflateInit2_": (C.c_int, [zsp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]),
+            "inflateInit2_": (C.c_int, [zsp, C.c_int, C.c_char_p, C.c_int]),
+            # zb200.h
+            "zb200_init": (C.c_int, [C.c_int]), "zb200_device_count": (C.c_int, []),
+            "zb200_last_error": (C.c_char_p, []), "zb200_build_info": (C.c_char_p, []),
+            "zb200_alloc_pinned": (vp, [sz]), "zb200_free_pinned": (None, [vp]),
+            "zb200_alloc_device": (vp, [sz]), "zb200_free_device": (None, [vp]),
+            "zb200_copy": (C.c_int, [vp, vp, sz, vp]), "zb200_sync": (C.c_int, [vp]),
+            "zb200_checksum": (C.c_int, [vp, sz, u32p, u32p, vp]),
+            "zb200_checksum_dev": (C.c_int, [vp, sz, vp, vp]),
+            "zb200_checksum_batch": (C.c_int, [vp, vp, sz, vp, vp, vp]),
+            "zb200_deflate": (C.c_int, [vp, sz, vp, C.POINTER(sz), C.c_int, C.c_int, vp]),
+            "zb200_deflate_shard": (C.c_int, [vp, sz, vp, sz, vp, C.POINTER(sz), C.c_int, C.c_int, C.c_int, u32p, u32p, vp]),
+            "zb200_deflate_batch": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
+            "zb200_inflate_batch": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
+            "zb200_inflate_batch_dev": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
+            "zb200_kernel_launches": (C.c_uint64, []),
+            "zb200_synth": (None, [vp, sz, C.c_int, C.c_uint64]),
+        }
+        self.missing = []
+        for name, (res, args) in sig.items():
+            try:
+                f = getattr(d, name)
+            except AttributeError:
+                self.missing.append(name)
+                continue
+            f.restype, f.argtypes = res, args
+        self.signatures = sig
+
+    # ---- errors ---------------------------------------------------------
+    def last_error(self) -> str:
+        return (self.dll.zb200_last_error() or b"").decode()
+
+    def _check(self, rc: int, what: str):
+        if rc != Z_OK:
+            raise RuntimeError(f"{what} -> {rc}: {self.last_error()}")
+
+    # ---- checksums ------------------------------------------------------
+    def crc32(self, data: Buf, value: int = 0, length: Optional[int] = None) -> int:
+        p, keep = _ptr(data)
+        n = len(data) if length is None else length
+        return self.dll.crc32(value, p, n)
+
+    def adler32(self, data: Buf, value: int = 1, length: Optional[int] = None) -> int:
+        p, keep = _ptr(data)
+        n = len(data) if length is None else length
+        return self.dll.adler32(value, p, n)
+
+    def crc32_combine(self, c1: int, c2: int, len2: int) -> int:
+        return self.dll.crc32_combine(c1, c2, len2)
+
+    def adler32_combine(self, a1: int, a2: int, len2: int) -> int:
+        return self.dll.adler32_combine(a1, a2, len2)
+
+    def checksum(self, data: Buf, length: Optional[int] = None, stream=None) -> Tuple[int, int]:
+        """(crc32(0,data), adler32(1,data)) in one GPU pass; data may be a device pointer."""
+        p, keep = _ptr(data)
+        n = len(data) if length is None else length
+        crc, adl = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.dll.zb200_checksum(p, n, C.byref(crc), C.byref(adl), _stream(stream)), "zb200_checksum")
+        return crc.value, adl.value
+
+    def checksum_dev(self, d_ptr: int, length: int, d_out2: int, stream=None) -> None:
+        self._check(self.dll.zb200_checksum_dev(C.c_void_p(d_ptr), length, C.c_void_p(d_out2), _stream(stream)),
+                    "zb200_checksum_dev")
+
+    # ---- one-shot codec ---------------------------------------------------
+    def compress_bound(self, n: int) -> int:
+        return self.dll.compressBound(n)
+
+    def compress2(self, data: Buf, level: int = -1, cap: Optional[int] = None) -> Tuple[int, bytes]:
+        n = len(data)
+        cap = self.compress_bound(n) if cap is None else cap
+        out = C.create_string_buffer(max(cap, 1))
+        ol = C.c_ulong(cap)
+        p, keep = _ptr(data)
+        rc = self.dll.compress2(out, C.byref(ol), p, n, level)
+        return rc, (out.raw[:ol.value] if rc == Z_OK else b"")
+
+    def uncompress(self, data: Buf, cap: int) -> Tuple[int, bytes]:
+        out = C.create_string_buffer(max(cap, 1))
+        ol = C.c_ulong(cap)
+        p, keep = _ptr(data)
+        rc = self.dll.uncompress(out, C.byref(ol), p, len(data))
+        return rc, (out.raw[:ol.value] if rc == Z_OK else b"")
+
+    def deflate(self, src: Buf, src_len: int, dst: Buf, dst_cap: int, level: int = 6, wrap: int = WRAP_ZLIB,
+                stream=None) -> int:
+        """zb200_deflate on host or device buffers; returns the compressed length."""
+        ps, k1 = _ptr(src)
+        pd, k2 = _ptr(dst)
+        ol = C.c_size_t(dst_cap)
+        self._check(self.dll.zb200_deflate(ps, src_len, pd, C.byref(ol), level, wrap, _stream(stream)), "zb200_deflate")
+        return ol.value
+
+    def deflate_shard(self, src: Buf, src_len: int, dict_: Buf, dict_len: int, dst: Buf, dst_cap: int, level: int,
+                      wrap: int, flags: int, stream=None) -> Tuple[int, int, int]:
+        ps, k1 = _ptr(src)
+        pk, k3 = _ptr(dict_)
+        pd, k2 = _ptr(dst)
+        ol = C.c_size_t(dst_cap)
+        crc, adl = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.dll.zb200_deflate_shard(ps, src_len, pk, dict_len, pd, C.byref(ol), level, wrap, flags,
+                                                 C.byref(crc), C.byref(adl), _stream(stream)), "zb200_deflate_shard")
+        return ol.value, crc.value, adl.value
+
+    def synth(self, n: int, kind: int = 1, seed: int = 1):
+        """numpy uint8 array of synthetic corpus bytes."""
+        import numpy as np
+        a = np.empty(n, dtype=np.uint8)
+        self.dll.zb200_synth(C.c_void_p(a.ctypes.data), n, kind, seed)
+        return a
+
+    def kernel_launches(self) -> int:
+        return self.dll.zb200_kernel_launches()
+
+
+_default: Optional[Lib] = None
+
+
+def load(path: str = LIB_PATH) -> Lib:
+    global _default
+    if _default is None or _default.path != path:
+        _default = Lib(path)
+    return _default

@@ -1,0 +1,355 @@
+// zb_checksum.cu -- K5/K6: CRC-32 and Adler-32 in one pass over device memory.
+//
+// Replaces the reference's crc32()/crc32_little() (qcsrc/crc32.c:219,262) and adler32()
+// (qcsrc/adler32.c:57) plus the GF(2) / modular merges of crc32_combine (crc32.c:370) and
+// adler32_combine (adler32.c:128), which here run as an on-device combine tree.
+//
+// CRC formulation.  Write the raw CRC register (no pre/post inversion) of a message M as
+// R(M) = M(x) * x^32 mod P.  R is linear over GF(2), so R(M) is the XOR over all 32-bit
+// words W at byte offset o of  W * x^(8*(len-o)) mod P.  A warp owns a contiguous segment
+// and reads it 512 bytes at a time (one coalesced 16-byte load per lane); each lane keeps
+// FOUR independent registers, one per word of its uint4, advanced by Horner's rule with the
+// fixed stride of 512 bytes:      c <- c * x^(8*512) mod P  xor  W.
+// Multiplying by the constant x^(8*512) is four byte-indexed table lookups (the same shape
+// as the reference's slicing-by-4 step, but for a 512-byte jump).  The four tables live in
+// shared memory replicated once per bank (entry v of table t for lane l at word
+// (t*256+v)*32 + l), so a warp's 32 lookups always hit 32 distinct banks: one lookup per
+// input byte at the full shared-memory rate, no bank conflicts, and no staging of the data
+// itself -- it goes global -> registers exactly once.
+// At the end of a segment each lane register is moved to the segment end with a modular
+// multiply by a per-lane constant, lanes are XOR-reduced, and one partial record per warp
+// goes to global memory.  A final one-block kernel moves every partial to the end of the
+// buffer (multiply by x^(8*suffix) assembled from precomputed x^(8*2^k)), folds in the
+// unaligned head/tail bytes and the 0xffffffff pre/post conditioning.
+//
+// Adler-32 rides along: per 16 bytes three dp4a-fed accumulators give the plain sum, the
+// iteration-weighted sum and the in-piece weighted sum, from which s1/s2 partials follow in
+// closed form (the deferred-modulo idea of adler32.c:97-106, with the bound set by u32).
+//
+// Roofline: HBM.  Algorithmic bytes = len (read once), 8 bytes written.
+#include "zb_common.cuh"
+
+namespace zb {
+
+constexpr int kStride = 512;               // bytes a warp consumes per iteration
+constexpr int kMainThreads = 1024;
+constexpr int kMainWarps = kMainThreads / 32;
+constexpr uint32_t kMaxIters = 1024;       // keeps the u32 Adler accumulators exact (see below)
+constexpr size_t kMainSmem = 4 * 256 * 32 * sizeof(uint32_t);   // 128 KiB of replicated tables
+constexpr size_t kMainThreshold = 1u << 20;                      // below this the stripe kernel runs alone
+constexpr int kStripeThreads = 256;
+constexpr uint32_t kMaxStripe = 4096;      // u32 bound for the serial s2 accumulation
+
+struct Partial {
+    uint32_t reg;                          // raw CRC register contribution at `end`
+    uint32_t a, b;                         // Adler sums (mod 65521) of the covered bytes, relative to `end`
+    uint32_t pad;
+    uint64_t end;                          // byte offset one past the covered range; 0 = unused record
+};
+
+__device__ uint32_t g_tab_stride[4][256];  // v<<(8t) times x^(8*512)
+__device__ uint32_t g_tab_byte[256];       // the classic byte table (crc32.h table 0)
+__device__ uint32_t g_lane_mul[128];       // x^(8*(512 - 16*lane - 4*k))
+__constant__ uint32_t c_pow8[64];          // x^(8*2^k) mod P
+
+static unsigned long h_crc_table[256];
+const unsigned long* host_crc_table() { return h_crc_table; }
+
+// ---- GF(2) helpers: reflected representation, bit 31 = x^0, right shift = times x ----
+__host__ __device__ inline uint32_t gf2_mul(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+#pragma unroll 4
+    for (int i = 31; i >= 0; --i) {
+        r ^= a & (0u - ((b >> i) & 1u));
+        a = (a >> 1) ^ (kCrcPoly & (0u - (a & 1u)));
+    }
+    return r;
+}
+
+__device__ inline uint32_t pow8(uint64_t nbytes)          // x^(8*nbytes) mod P
+{
+    uint32_t acc = 0x80000000u;
+    bool first = true;
+    for (int k = 0; nbytes; ++k, nbytes >>= 1)
+        if (nbytes & 1) {
+            acc = first ? c_pow8[k] : gf2_mul(acc, c_pow8[k]);
+            first = false;
+        }
+    return acc;
+}
+
+static uint32_t host_pow8(uint64_t nbytes)
+{
+    uint32_t acc = 0x80000000u, p = 0x00800000u;          // x^0, x^8
+    for (; nbytes; nbytes >>= 1) {
+        if (nbytes & 1) acc = gf2_mul(acc, p);
+        p = gf2_mul(p, p);
+    }
+    return acc;
+}
+
+int checksum_setup()
+{
+    uint32_t tab0[256], tabs[4][256], lane_mul[128], pw[64];
+    for (uint32_t n = 0; n < 256; n++) {
+        uint32_t c = n;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ kCrcPoly : c >> 1;
+        tab0[n] = c;
+        h_crc_table[n] = c;
+    }
+    const uint32_t xs = host_pow8(kStride);
+    for (int t = 0; t < 4; t++)
+        for (uint32_t v = 0; v < 256; v++) tabs[t][v] = gf2_mul(v << (8 * t), xs);
+    for (int lane = 0; lane < 32; lane++)
+        for (int k = 0; k < 4; k++) lane_mul[lane * 4 + k] = host_pow8((uint64_t)(kStride - 16 * lane - 4 * k));
+    uint32_t p = 0x00800000u;
+    for (int k = 0; k < 64; k++) { pw[k] = p; p = gf2_mul(p, p); }
+    ZB_CUDA(cudaMemcpyToSymbol(g_tab_stride, tabs, sizeof(tabs)));
+    ZB_CUDA(cudaMemcpyToSymbol(g_tab_byte, tab0, sizeof(tab0)));
+    ZB_CUDA(cudaMemcpyToSymbol(g_lane_mul, lane_mul, sizeof(lane_mul)));
+    ZB_CUDA(cudaMemcpyToSymbol(c_pow8, pw, sizeof(pw)));
+    return 0;
+}
+
+// ---- main kernel: aligned bulk, one segment of `iters_per_warp` x 512 B per warp ----
+__device__ __forceinline__ uint32_t stride_step(const uint32_t* __restrict__ lane_tab, uint32_t c)
+{
+    // lane_tab points at word `lane` of the replicated tables; entry v of table t sits at
+    // lane_tab[(t*256 + v)*32].
+    return lane_tab[((c & 0xffu)) * 32] ^ lane_tab[(256 + ((c >> 8) & 0xffu)) * 32] ^
+           lane_tab[(512 + ((c >> 16) & 0xffu)) * 32] ^ lane_tab[(768 + (c >> 24)) * 32];
+}
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kMainThreads, 1)
+k_checksum_main(const uint8_t* __restrict__ base, uint64_t n_units, uint32_t iters_per_warp,
+                uint64_t base_off, Partial* __restrict__ parts)
+{
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    for (int i = threadIdx.x; i < 4 * 256 * 32; i += kMainThreads) s_tab[i] = (&g_tab_stride[0][0])[i >> 5];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * kMainWarps + (threadIdx.x >> 5);
+    const uint64_t u0 = warp * iters_per_warp;
+    if (u0 >= n_units) {
+        if (lane == 0) parts[warp] = Partial{0, 0, 0, 0, 0};
+        return;
+    }
+    const uint32_t iters = (uint32_t)min((uint64_t)iters_per_warp, n_units - u0);
+    const uint4* p = reinterpret_cast<const uint4*>(base + u0 * kStride) + lane;
+    const uint32_t* lane_tab = s_tab + lane;
+
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    uint32_t s_a = 0, s_j = 0, s_b = 0;    // sum, iteration-weighted sum, in-piece weighted sum
+
+    uint32_t j = 0;
+    // two loads in flight per lane
+    for (; j + 2 <= iters; j += 2) {
+        uint4 w0 = ld_stream(p + (size_t)j * 32);
+        uint4 w1 = ld_stream(p + (size_t)(j + 1) * 32);
+        c0 = stride_step(lane_tab, c0) ^ w0.x; c1 = stride_step(lane_tab, c1) ^ w0.y;
+        c2 = stride_step(lane_tab, c2) ^ w0.z; c3 = stride_step(lane_tab, c3) ^ w0.w;
+        uint32_t sum0 = __dp4a(w0.x, 0x01010101u, __dp4a(w0.y, 0x01010101u, __dp4a(w0.z, 0x01010101u, __dp4a(w0.w, 0x01010101u, 0u))));
+        s_b = __dp4a(w0.x, 0x0d0e0f10u, __dp4a(w0.y, 0x090a0b0cu, __dp4a(w0.z, 0x05060708u, __dp4a(w0.w, 0x01020304u, s_b))));
+        s_a += sum0; s_j += j * sum0;
+        c0 = stride_step(lane_tab, c0) ^ w1.x; c1 = stride_step(lane_tab, c1) ^ w1.y;
+        c2 = stride_step(lane_tab, c2) ^ w1.z; c3 = stride_step(lane_tab, c3) ^ w1.w;
+        uint32_t sum1 = __dp4a(w1.x, 0x01010101u, __dp4a(w1.y, 0x01010101u, __dp4a(w1.z, 0x01010101u, __dp4a(w1.w, 0x01010101u, 0u))));
+        s_b = __dp4a(w1.x, 0x0d0e0f10u, __dp4a(w1.y, 0x090a0b0cu, __dp4a(w1.z, 0x05060708u, __dp4a(w1.w, 0x01020304u, s_b))));
+        s_a += sum1; s_j += (j + 1) * sum1;
+    }
+    for (; j < iters; ++j) {
+        uint4 w0 = ld_stream(p + (size_t)j * 32);
+        c0 = stride_step(lane_tab, c0) ^ w0.x; c1 = stride_step(lane_tab, c1) ^ w0.y;
+        c2 = stride_step(lane_tab, c2) ^ w0.z; c3 = stride_step(lane_tab, c3) ^ w0.w;
+        uint32_t sum0 = __dp4a(w0.x, 0x01010101u, __dp4a(w0.y, 0x01010101u, __dp4a(w0.z, 0x01010101u, __dp4a(w0.w, 0x01010101u, 0u))));
+        s_b = __dp4a(w0.x, 0x0d0e0f10u, __dp4a(w0.y, 0x090a0b0cu, __dp4a(w0.z, 0x05060708u, __dp4a(w0.w, 0x01020304u, s_b))));
+        s_a += sum0; s_j += j * sum0;
+    }
+
+    // Move the four lane registers to the end of the segment and reduce across the warp.
+    uint32_t reg = gf2_mul(c0, g_lane_mul[lane * 4 + 0]) ^ gf2_mul(c1, g_lane_mul[lane * 4 + 1]) ^
+                   gf2_mul(c2, g_lane_mul[lane * 4 + 2]) ^ gf2_mul(c3, g_lane_mul[lane * 4 + 3]);
+    // Adler: byte at segment offset o = 512 j + 16 lane + t weighs (L - o).
+    const uint64_t L = (uint64_t)iters * kStride;
+    uint64_t bw = (L - 16u * lane - 16u) * (uint64_t)s_a + (uint64_t)s_b - (uint64_t)kStride * s_j;
+    uint32_t a = s_a % kAdlerBase, b = (uint32_t)(bw % kAdlerBase);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) parts[warp] = Partial{reg, a % kAdlerBase, b % kAdlerBase, 0, base_off + (u0 + iters) * kStride};
+}
+
+// ---- stripe kernel: small or ragged ranges, one contiguous stripe per thread ----
+__global__ void __launch_bounds__(kStripeThreads)
+k_checksum_stripes(const uint8_t* __restrict__ buf, uint64_t len, uint32_t stripe, Partial* __restrict__ parts)
+{
+    __shared__ uint32_t s_tab[256];
+    s_tab[threadIdx.x] = g_tab_byte[threadIdx.x];
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * kStripeThreads + threadIdx.x;
+    const uint64_t beg = t * stripe;
+    if (beg >= len) { parts[t] = Partial{0, 0, 0, 0, 0}; return; }
+    const uint64_t end = min(len, beg + stripe);
+    uint32_t c = 0, a = 0, b = 0;
+    for (uint64_t i = beg; i < end; ++i) {
+        uint32_t v = buf[i];
+        c = s_tab[(c ^ v) & 0xffu] ^ (c >> 8);
+        a += v; b += a;
+    }
+    parts[t] = Partial{c, a % kAdlerBase, b % kAdlerBase, 0, end};
+}
+
+// ---- final kernel: combine tree over partial records + ragged edge bytes ----
+__global__ void __launch_bounds__(1024, 1)
+k_checksum_final(const Partial* __restrict__ parts, uint32_t n_parts, const uint8_t* __restrict__ buf,
+                 uint64_t len, uint64_t head, uint64_t tail_begin, uint32_t* __restrict__ out2)
+{
+    __shared__ uint32_t s_reg[32], s_a[32], s_b[32];
+    uint32_t reg = 0, a = 0, b = 0;
+    for (uint32_t i = threadIdx.x; i < n_parts; i += blockDim.x) {
+        Partial p = parts[i];
+        if (p.end == 0) continue;
+        uint64_t suffix = len - p.end;
+        reg ^= suffix ? gf2_mul(p.reg, pow8(suffix)) : p.reg;
+        a += p.a;
+        b = (b + p.b + (uint32_t)((suffix % kAdlerBase) * p.a % kAdlerBase)) % kAdlerBase;
+        a %= kAdlerBase;
+    }
+    const uint64_t n_edge = head + (len - tail_begin);
+    for (uint64_t e = threadIdx.x; e < n_edge; e += blockDim.x) {
+        uint64_t o = e < head ? e : tail_begin + (e - head);
+        uint32_t v = buf[o];
+        uint64_t suffix = len - o - 1;
+        uint32_t r1 = g_tab_byte[v];
+        reg ^= suffix ? gf2_mul(r1, pow8(suffix)) : r1;
+        a = (a + v) % kAdlerBase;
+        b = (b + (uint32_t)(((len - o) % kAdlerBase) * v % kAdlerBase)) % kAdlerBase;
+    }
+    if (threadIdx.x == 0) reg ^= len ? gf2_mul(0xffffffffu, pow8(len)) : 0xffffffffu;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_reg[warp] = reg; s_a[warp] = a % kAdlerBase; s_b[warp] = b % kAdlerBase; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        reg = lane < nw ? s_reg[lane] : 0; a = lane < nw ? s_a[lane] : 0; b = lane < nw ? s_b[lane] : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+            uint32_t s1 = (1u + a) % kAdlerBase;
+            uint32_t s2 = (uint32_t)((len % kAdlerBase + b) % kAdlerBase);
+            out2[0] = ~reg;
+            out2[1] = (s2 << 16) | s1;
+        }
+    }
+}
+
+int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, cudaStream_t s)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        ZB_CUDA(cudaFuncSetAttribute(k_checksum_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMainSmem));
+        attr_set = true;
+    }
+    if (len < kMainThreshold) {
+        // one stripe kernel over everything
+        uint32_t threads_wanted = (uint32_t)((len + 63) / 64);
+        uint32_t blocks = (threads_wanted + kStripeThreads - 1) / kStripeThreads;
+        if (blocks < 1) blocks = 1;
+        if (blocks > (uint32_t)kSMs) blocks = kSMs;
+        uint64_t nthreads = (uint64_t)blocks * kStripeThreads;
+        uint32_t stripe = (uint32_t)((len + nthreads - 1) / nthreads);
+        if (stripe < 16) stripe = 16;
+        int rc = c->ws[0].ensure(nthreads * sizeof(Partial));
+        if (rc) return rc;
+        ZB_LAUNCH(k_checksum_stripes, blocks, kStripeThreads, 0, s, d_buf, (uint64_t)len, stripe, c->ws[0].as<Partial>());
+        ZB_LAUNCH(k_checksum_final, 1, 1024, 0, s, c->ws[0].as<Partial>(), (uint32_t)nthreads, d_buf, (uint64_t)len,
+                  (uint64_t)0, (uint64_t)len, d_out2);
+        ZB_CHECK_LAUNCH();
+        return 0;
+    }
+    const uint64_t head = (16 - ((uintptr_t)d_buf & 15)) & 15;
+    const uint64_t n_units = (len - head) / kStride;
+    const uint64_t tail_begin = head + n_units * kStride;
+    // every resident warp gets the same number of iterations; several rounds only for huge inputs
+    uint64_t warps = (uint64_t)kSMs * kMainWarps;
+    uint64_t rounds = (n_units + warps * kMaxIters - 1) / (warps * kMaxIters);
+    uint64_t total_warps = warps * rounds;
+    uint32_t iters = (uint32_t)((n_units + total_warps - 1) / total_warps);
+    if (iters < 8) iters = 8;
+    uint64_t used_warps = (n_units + iters - 1) / iters;
+    uint32_t blocks = (uint32_t)((used_warps + kMainWarps - 1) / kMainWarps);
+    uint64_t n_parts = (uint64_t)blocks * kMainWarps;
+    int rc = c->ws[0].ensure(n_parts * sizeof(Partial));
+    if (rc) return rc;
+    ZB_LAUNCH(k_checksum_main, blocks, kMainThreads, kMainSmem, s, d_buf + head, n_units, iters, head, c->ws[0].as<Partial>());
+    ZB_LAUNCH(k_checksum_final, 1, 1024, 0, s, c->ws[0].as<Partial>(), (uint32_t)n_parts, d_buf, (uint64_t)len, head,
+              tail_begin, d_out2);
+    ZB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+ZB_API int zb200_checksum_dev(const void* d_buf, size_t len, uint32_t* d_out2, void* stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    Ctx* c = ctx_acquire((cudaStream_t)stream);
+    if (!c) return ZB_MEM_ERROR;
+    cudaStream_t s = pick_stream(c, stream);
+    rc = checksum_launch(c, static_cast<const uint8_t*>(d_buf), len, d_out2, s);
+    ctx_release(c, s);
+    return rc;
+}
+
+ZB_API int zb200_checksum(const void* buf, size_t len, uint32_t* crc, uint32_t* adler, void* stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    Ctx* c = ctx_acquire((cudaStream_t)stream);
+    if (!c) return ZB_MEM_ERROR;
+    cudaStream_t s = pick_stream(c, stream);
+    do {
+        const uint8_t* d = to_device(c, buf, len, s, &rc);
+        if (rc) break;
+        if ((rc = c->small.ensure(256)) != 0) break;
+        if ((rc = c->ensure_pinned(256)) != 0) break;
+        if ((rc = checksum_launch(c, d, len, c->small.as<uint32_t>(), s)) != 0) break;
+        if (cudaMemcpyAsync(c->pinned, c->small.p, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            set_error("checksum readback failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = ZB_STREAM_ERROR;
+            break;
+        }
+        const uint32_t* r = static_cast<const uint32_t*>(c->pinned);
+        if (crc) *crc = r[0];
+        if (adler) *adler = r[1];
+    } while (0);
+    ctx_release(c, s);
+    return rc;
+}

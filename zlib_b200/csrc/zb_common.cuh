@@ -1,0 +1,92 @@
+// zb_common.cuh -- internal declarations shared by the zb200 CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/zb200.h"
+
+#define ZB_API extern "C" __attribute__((visibility("default")))
+#define ZB_STR1(x) #x
+#define ZB_STR2(x) ZB_STR1(x)
+
+// zlib return codes (include/zlib.h)
+enum { ZB_OK = 0, ZB_STREAM_END = 1, ZB_NEED_DICT = 2, ZB_STREAM_ERROR = -2, ZB_DATA_ERROR = -3,
+       ZB_MEM_ERROR = -4, ZB_BUF_ERROR = -5 };
+
+namespace zb {
+
+constexpr int kSMs = 148;                 // B200: 2 dies x 74 SMs
+constexpr uint32_t kCrcPoly = 0xEDB88320u;
+constexpr uint32_t kAdlerBase = 65521u;
+
+extern std::atomic<uint64_t> g_launches;
+void set_error(const char* fmt, ...);
+
+// Growable device buffer owned by a context.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);              // 0 or ZB_MEM_ERROR
+    void release();
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// One execution context: a stream, scratch memory and pinned staging.  Contexts are
+// pooled; a z_stream or an extension call borrows one for the duration of a call.
+struct Ctx {
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t  idle = nullptr;           // recorded when the context is released
+    DevBuf in, out, ws[12];
+    DevBuf small;                          // few-KB result words
+    void* pinned = nullptr; size_t pinned_cap = 0;
+    int ensure_pinned(size_t bytes);
+    Ctx* next = nullptr;
+};
+
+int  ensure_init();                        // 0 or negative zlib code
+Ctx* ctx_acquire(cudaStream_t use);        // waits (on `use`) for the context's previous work
+void ctx_release(Ctx* c, cudaStream_t used);
+// NULL means CUDA's legacy default stream (stream 0), which orders with torch's default stream.
+inline cudaStream_t pick_stream(Ctx*, void* user) { return (cudaStream_t)user; }
+
+enum MemKind { kHostPageable = 0, kHostPinned = 1, kDevice = 2 };
+MemKind classify(const void* p);
+
+// Brings `len` bytes at `src` (any memory kind) to the device; returns a device pointer that
+// is either `src` itself or c->in.  Asynchronous on `s` for pinned/device sources.
+const uint8_t* to_device(Ctx* c, const void* src, size_t len, cudaStream_t s, int* err);
+
+#define ZB_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (expr);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            zb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return ZB_STREAM_ERROR;                                                     \
+        }                                                                               \
+    } while (0)
+
+#define ZB_LAUNCH(kernel, grid, block, smem, stream, ...)                               \
+    do {                                                                                \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                     \
+        zb::g_launches.fetch_add(1, std::memory_order_relaxed);                         \
+    } while (0)
+
+#define ZB_CHECK_LAUNCH()                                                               \
+    do {                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess) {                                                       \
+            zb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return ZB_STREAM_ERROR;                                                     \
+        }                                                                               \
+    } while (0)
+
+// ---- checksum engine (zb_checksum.cu) ----
+int checksum_setup();                      // uploads tables; called from ensure_init
+// crc32(0,..)/adler32(1,..) of d_buf[0..len) -> d_out2[0..1]; async on s.
+int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, cudaStream_t s);
+const unsigned long* host_crc_table();
+
+}  // namespace zb
