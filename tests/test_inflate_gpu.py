@@ -1,0 +1,129 @@
+"""GPU: K4 batch inflate through the C-ABI vs golden reference streams and the CPU oracle."""
+import base64
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import zhelpers
+from zlib_b200 import binding as zb
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(name):
+    return json.load(open(os.path.join(zhelpers.GOLDEN, name)))
+
+
+def test_kat_streams(gpu_lib):
+    """compress2 outputs of the reference quoted in SURVEY.md 8(c) decode to their inputs."""
+    k = _golden("kat.json")["compress2"]
+    streams = [bytes.fromhex(z) for _, _, z in k]
+    datas = [bytes.fromhex(d) for d, _, _ in k]
+    outs, st = gpu_lib.inflate_batch(streams, [len(d) for d in datas])
+    assert st == [0] * len(k)
+    assert outs == datas
+
+
+def test_golden_reference_streams(gpu_lib):
+    streams, datas = [], []
+    for e in _golden("streams.json"):
+        d = zhelpers.corpus(e["kind"], e["n"], e["seed"])
+        for level, z in e["z"].items():
+            streams.append(base64.b64decode(z)); datas.append(d)
+    outs, st = gpu_lib.inflate_batch(streams, [len(d) for d in datas])
+    assert st == [0] * len(streams)
+    for o, d in zip(outs, datas):
+        assert o == d
+    # generous capacity gives the same result
+    outs, st = gpu_lib.inflate_batch(streams, [len(d) + 1000 for d in datas])
+    assert st == [0] * len(streams) and outs == datas
+
+
+def test_golden_corrupt_status(gpu_lib):
+    """Same return code as the reference's uncompress() on damaged / truncated / short-output cases."""
+    es = _golden("corrupt.json")
+    streams = [base64.b64decode(e["z"]) for e in es]
+    outs, st = gpu_lib.inflate_batch(streams, [e["cap"] for e in es])
+    bad = [(i, es[i]["rc"], st[i]) for i in range(len(es)) if st[i] != es[i]["rc"]]
+    assert not bad, bad[:10]
+    for e, o in zip(es, outs):
+        if e["out_ok"]:
+            assert o == zhelpers.corpus(e["kind"], e["n"], e["seed"])
+
+
+def test_differential_vs_oracle(gpu_lib, oracle):
+    rng = random.Random(5)
+    streams, caps, want = [], [], []
+    for t in range(400):
+        kind = rng.randrange(5)
+        n = rng.choice([0, 1, 2, 3, 10, 257, 258, 259, 4000, 32768, 32769, 70000, rng.randint(0, 200000)])
+        d = zhelpers.corpus(kind, n, 1000 + t)
+        z = bytearray(oracle.deflate(d, rng.choice([0, 1, 1, 6, 6, 9])))
+        mode = rng.randrange(6)
+        if mode == 0 and len(z) > 0:
+            z[rng.randrange(len(z))] ^= 1 << rng.randrange(8)
+        elif mode == 1:
+            z = z[:rng.randrange(len(z) + 1)]
+        cap = rng.choice([n, n, n, n // 2, n + 17, 0, max(n - 1, 0)])
+        rc, out, _ = oracle.inflate(bytes(z), cap)
+        streams.append(bytes(z)); caps.append(cap); want.append((rc, out))
+    outs, st = gpu_lib.inflate_batch(streams, caps)
+    for i, (rc, out) in enumerate(want):
+        assert st[i] == rc, (i, st[i], rc, len(streams[i]), caps[i])
+        if rc == 0:
+            assert outs[i] == out, i
+
+
+def test_raw_wrap_and_unaligned(gpu_lib, oracle):
+    rng = random.Random(6)
+    streams, datas = [], []
+    for t in range(64):
+        d = zhelpers.corpus(rng.randrange(5), rng.randint(0, 50000), 2000 + t)
+        streams.append(oracle.deflate(d, 6, 0)); datas.append(d)       # odd lengths -> every alignment
+    outs, st = gpu_lib.inflate_batch(streams, [len(d) for d in datas], wrap=zb.WRAP_RAW)
+    assert st == [0] * 64 and outs == datas
+
+
+def test_hand_made_blocks(gpu_lib, oracle):
+    """Fixed-code block, stored block of length 0, multi-block streams, invalid block type."""
+    import zlib
+    cases = []
+    co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    d = b"fixed huffman block " * 50
+    cases.append((co.compress(d) + co.flush(), d))
+    co = zlib.compressobj(6)
+    parts = [b"abc" * 100, b"", b"xyz" * 1000]
+    z = b""
+    for p in parts:
+        z += co.compress(p) + co.flush(zlib.Z_FULL_FLUSH)          # empty stored blocks in the middle
+    z += co.flush()
+    cases.append((z, b"".join(parts)))
+    outs, st = gpu_lib.inflate_batch([c[0] for c in cases], [len(c[1]) for c in cases])
+    assert st == [0, 0] and outs == [c[1] for c in cases]
+    bad = b"\x78\x9c\x07"                                             # block type 3
+    outs, st = gpu_lib.inflate_batch([bad], [10])
+    assert st == [oracle.inflate(bad, 10)[0]] == [-3]
+
+
+def test_many_streams_device_resident(gpu_lib, oracle):
+    """2000 x 64 KiB slices of the mixed corpus, reference/oracle-compressed, decoded on device memory."""
+    import torch
+    n, sz = 2000, 65536
+    host = gpu_lib.synth(n * sz, kind=1, seed=21)
+    zs = [oracle.deflate(host[i * sz:(i + 1) * sz], 6) for i in range(n)]
+    src_off = np.zeros(n + 1, dtype=np.int64); src_off[1:] = np.cumsum([len(z) for z in zs])
+    dst_off = np.arange(n + 1, dtype=np.int64) * sz
+    d_src = torch.from_numpy(np.frombuffer(b"".join(zs) + b"\0" * 8, dtype=np.uint8).copy()).cuda()
+    d_so, d_do = torch.from_numpy(src_off).cuda(), torch.from_numpy(dst_off).cuda()
+    d_dst = torch.zeros(n * sz, dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(n, dtype=torch.int64, device="cuda")
+    d_st = torch.full((n,), -99, dtype=torch.int32, device="cuda")
+    gpu_lib.inflate_batch_dev(d_src.data_ptr(), d_so.data_ptr(), n, d_dst.data_ptr(), d_do.data_ptr(),
+                              d_len.data_ptr(), d_st.data_ptr(), zb.WRAP_ZLIB, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum()) == 0
+    assert bool((d_len == sz).all())
+    assert np.array_equal(d_dst.cpu().numpy(), host)

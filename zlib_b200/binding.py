@@ -203,6 +203,29 @@ class Lib:
                                                  C.byref(crc), C.byref(adl), _stream(stream)), "zb200_deflate_shard")
         return ol.value, crc.value, adl.value
 
+    def inflate_batch(self, streams, caps, wrap: int = WRAP_ZLIB, stream=None):
+        """zb200_inflate_batch over a list of bytes objects; returns (outputs, statuses)."""
+        import numpy as np
+        n = len(streams)
+        src_off = np.zeros(n + 1, dtype=np.uint64)
+        dst_off = np.zeros(n + 1, dtype=np.uint64)
+        src_off[1:] = np.cumsum([len(x) for x in streams], dtype=np.uint64)
+        dst_off[1:] = np.cumsum(caps, dtype=np.uint64)
+        src = np.frombuffer(b"".join(streams) + b"\0" * 8, dtype=np.uint8)
+        dst = np.zeros(int(dst_off[-1]) + 8, dtype=np.uint8)
+        dst_len = np.zeros(max(n, 1), dtype=np.uint64)
+        status = np.full(max(n, 1), -99, dtype=np.int32)
+        self._check(self.dll.zb200_inflate_batch(src.ctypes.data, src_off.ctypes.data, n, dst.ctypes.data,
+                                                 dst_off.ctypes.data, dst_len.ctypes.data, status.ctypes.data,
+                                                 wrap, _stream(stream)), "zb200_inflate_batch")
+        outs = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + int(dst_len[i])]) for i in range(n)]
+        return outs, [int(x) for x in status[:n]]
+
+    def inflate_batch_dev(self, d_src, d_src_off, n, d_dst, d_dst_off, d_dst_len, d_status, wrap=WRAP_ZLIB, stream=None):
+        self._check(self.dll.zb200_inflate_batch_dev(C.c_void_p(d_src), C.c_void_p(d_src_off), n, C.c_void_p(d_dst),
+                                                     C.c_void_p(d_dst_off), C.c_void_p(d_dst_len), C.c_void_p(d_status),
+                                                     wrap, _stream(stream)), "zb200_inflate_batch_dev")
+
     def synth(self, n: int, kind: int = 1, seed: int = 1):
         """numpy uint8 array of synthetic corpus bytes."""
         import numpy as np

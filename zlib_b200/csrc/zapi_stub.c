@@ -21,5 +21,3 @@ STUB(zb200_checksum_batch, (const void *b, const uint64_t *o, size_t n, uint32_t
 STUB(zb200_deflate, (const void *s, size_t sl, void *d, size_t *dl, int l, int w, void *st))
 STUB(zb200_deflate_shard, (const void *s, size_t sl, const void *dc, size_t dcl, void *d, size_t *dl, int l, int w, int f, uint32_t *c, uint32_t *a, void *st))
 STUB(zb200_deflate_batch, (const void *s, const uint64_t *so, size_t n, void *d, const uint64_t *dof, uint64_t *dl, uint32_t *c, uint32_t *a, int32_t *stt, int l, int w, void *st))
-STUB(zb200_inflate_batch, (const void *s, const uint64_t *so, size_t n, void *d, const uint64_t *dof, uint64_t *dl, int32_t *stt, int w, void *st))
-STUB(zb200_inflate_batch_dev, (const void *s, const uint64_t *so, size_t n, void *d, const uint64_t *dof, uint64_t *dl, int32_t *stt, int w, void *st))

@@ -1,0 +1,610 @@
+// zb_inflate.cu -- K4: many independent DEFLATE streams decoded in parallel, one warp each.
+//
+// Replaces the reference's inflate() state machine (qcsrc/inflate.c:554-1153), its table
+// builder inflate_table() (qcsrc/inftrees.c:32-329) and the inner loop inflate_fast()
+// (qcsrc/inffast.c:67-302) for the case the GPU is good at: a batch of complete streams
+// (uncompress() semantics, qcsrc/uncompr.c:26-61), and -- through the same code with a
+// saved state -- one z_stream fed piecewise (zapi_stream.c).
+//
+// Shape.  DEFLATE decoding is serial inside a stream (the bit position of symbol i+1 depends
+// on symbol i; copies depend on earlier output), so the parallel axis is the stream.  A warp
+// owns a stream: all 32 lanes run the same bit-level decode on warp-uniform values (no
+// divergence), and the lanes split the two things that are wide: building the Huffman tables
+// of a dynamic block and copying matches (lane i moves byte i; overlapping copies read
+// modulo the distance, so nothing depends on bytes written by the same copy).
+// Tables live in shared memory, per warp: a 10-bit primary table for literal/length codes and
+// an 8-bit primary for distances, each entry carrying {code bits, extra bits, kind, base}; codes
+// longer than the primary width (rare) fall back to canonical first-code decoding over the
+// sorted symbol list, which is also what rejects bit patterns that are not codes.
+//
+// Validity rules follow the reference: over-subscribed sets and incomplete sets (other than a
+// single one-bit code) are rejected (inftrees.c:130-138), nlen > 286 / ndist > 30
+// (inflate.c:846), stored LEN/NLEN (inflate.c:810), distance beyond the produced output
+// (inflate.c:1039), zlib header (inflate.c:589-632) and Adler-32 trailer (inflate.c:1077-1098).
+//
+// Roofline: HBM (algorithmic bytes = compressed in + plain out), but the kernel is
+// latency/issue bound by construction; see DESIGN.md.
+#include "zb_inflate.cuh"
+
+namespace zb {
+
+constexpr int kInfWarps = 4;                     // warps (= streams in flight) per CTA
+constexpr int kLitBits = 10, kDistBits = 8, kClBits = 7;
+constexpr int kLitSize = 1 << kLitBits, kDistSize = 1 << kDistBits;
+constexpr uint32_t kFull = 0xffffffffu;
+
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// entry: bits 0-3 code length (0 = not in the primary table), 4-7 extra-bit count, 8-9 kind,
+// 16-31 literal value / symbol, or base of a length or distance
+enum { kLit = 0, kBase = 1, kEob = 2, kBad = 3 };
+__device__ __forceinline__ uint32_t mk_entry(uint32_t len, uint32_t extra, uint32_t kind, uint32_t val)
+{
+    return len | (extra << 4) | (kind << 8) | (val << 16);
+}
+__device__ __forceinline__ uint32_t litlen_entry(uint32_t s, uint32_t len)
+{
+    if (s < 256) return mk_entry(len, 0, kLit, s);
+    if (s == 256) return mk_entry(len, 0, kEob, 0);
+    if (s > 285) return mk_entry(len, 0, kBad, 0);
+    uint32_t c = s - 257;
+    if (c < 8) return mk_entry(len, 0, kBase, 3 + c);
+    if (c == 28) return mk_entry(len, 0, kBase, 258);
+    uint32_t e = (c >> 2) - 1;
+    return mk_entry(len, e, kBase, 3 + ((4 + (c & 3)) << e));
+}
+__device__ __forceinline__ uint32_t dist_entry(uint32_t s, uint32_t len)
+{
+    if (s > 29) return mk_entry(len, 0, kBad, 0);
+    if (s < 4) return mk_entry(len, 0, kBase, 1 + s);
+    uint32_t e = (s >> 1) - 1;
+    return mk_entry(len, e, kBase, 1 + ((2 + (s & 1)) << e));
+}
+
+struct WarpTables {
+    uint32_t lit[kLitSize];
+    uint32_t dist[kDistSize];                    // also hosts the code-length code while a header is read
+    uint32_t lit_count[16], dist_count[16];      // symbols per code length
+    uint32_t first[16], offs[16], run[16];       // scratch while building
+    uint16_t lit_sorted[288];
+    uint16_t dist_sorted[32];
+    uint8_t  lens[320];
+    uint8_t  cl_lens[20];
+    int      lit_max, dist_max;                  // longest code present (0 = no codes at all)
+};
+
+struct Bits {
+    const uint32_t* words;                       // 4-byte aligned base covering the stream
+    uint32_t nwords, nextw;
+    uint64_t buf;
+    int cnt;
+    uint64_t used, total;                        // bits consumed so far / bits in the stream
+};
+
+__device__ __forceinline__ void refill(Bits& b)
+{
+    if (b.cnt <= 32) {
+        uint32_t w = b.nextw < b.nwords ? __ldg(b.words + b.nextw) : 0u;
+        b.nextw++;
+        b.buf |= (uint64_t)w << b.cnt;
+        b.cnt += 32;
+    }
+}
+__device__ __forceinline__ uint32_t peek(const Bits& b, int n) { return (uint32_t)b.buf & ((1u << n) - 1u); }
+__device__ __forceinline__ void drop(Bits& b, int n) { b.buf >>= n; b.cnt -= n; b.used += n; }
+__device__ __forceinline__ bool have(const Bits& b, int n) { return b.used + (uint64_t)n <= b.total; }
+
+__device__ void seek_bits(Bits& b, const uint8_t* in, uint64_t bitpos)
+{
+    const uintptr_t a = (uintptr_t)in + (bitpos >> 3);
+    const uintptr_t base = (uintptr_t)b.words;
+    const int skip = (int)(((a - base) & 3) * 8 + (bitpos & 7));
+    b.nextw = (uint32_t)((a - base) >> 2);
+    b.buf = 0; b.cnt = 0;
+    refill(b);
+    b.buf >>= skip; b.cnt -= skip;
+    refill(b);
+    b.used = bitpos;
+}
+
+// ---- table construction, all lanes of the warp cooperate (inftrees.c:32-329) ----
+// kind 0 = code-length code, 1 = literal/length, 2 = distance.  Returns 0 ok, -1 invalid set.
+__device__ int build_table(const uint8_t* lens, int n, int kind, uint32_t* tab, int tab_bits,
+                           uint16_t* sorted, uint32_t* count, WarpTables* t, int* max_out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    __syncwarp();
+    if (lane < 16) { count[lane] = 0; t->run[lane] = 0; }
+    for (int i = lane; i < (1 << tab_bits); i += 32) tab[i] = 0;
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) atomicAdd(&count[lens[s]], 1u);
+    __syncwarp();
+    int maxlen = 15;
+    while (maxlen >= 1 && count[maxlen] == 0) maxlen--;
+    if (lane == 0) *max_out = maxlen;
+    if (maxlen == 0) { __syncwarp(); return 0; }  // no codes: an error only if a symbol is needed (inftrees.c:116-124)
+    int left = 1;
+    for (int len = 1; len <= 15; len++) {
+        left = (left << 1) - (int)count[len];
+        if (left < 0) return -1;                 // over-subscribed
+    }
+    if (left > 0 && (kind == 0 || maxlen != 1)) return -1;   // incomplete
+    if (lane == 0) {
+        uint32_t code = 0, o = 0;
+        for (int len = 1; len <= 15; len++) {
+            code = (code + (len > 1 ? count[len - 1] : 0u)) << 1;
+            t->first[len] = code;
+            t->offs[len] = o;
+            o += count[len];
+        }
+    }
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        const int s = base + lane;
+        const uint32_t L = s < n ? lens[s] : 0u;
+        const uint32_t grp = __match_any_sync(kFull, L);
+        const uint32_t rank = t->run[L] + __popc(grp & lt);
+        __syncwarp();
+        if ((grp & lt) == 0) t->run[L] += __popc(grp);       // first lane of each length group
+        __syncwarp();
+        if (L != 0) {
+            if (sorted) sorted[t->offs[L] + rank] = (uint16_t)s;
+            if ((int)L <= tab_bits) {
+                const uint32_t code = t->first[L] + rank;
+                const uint32_t rc = __brev(code) >> (32 - L);
+                const uint32_t e = kind == 1 ? litlen_entry((uint32_t)s, L)
+                                 : kind == 2 ? dist_entry((uint32_t)s, L) : mk_entry(L, 0, kLit, (uint32_t)s);
+                for (uint32_t j = rc; j < (1u << tab_bits); j += 1u << L) tab[j] = e;
+            }
+        }
+    }
+    __syncwarp();
+    return 0;
+}
+
+// Canonical decode for codes that are not in the primary table.  Returns the symbol, -1 if the
+// input ends inside the code, -2 if the bits are not a code of this set.  Consumes on success.
+__device__ int slow_symbol(Bits& b, const uint32_t* count, const uint16_t* sorted, int maxlen)
+{
+    if (maxlen == 0) return have(b, 1) ? -2 : -1;
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= maxlen; len++) {
+        if (!have(b, len)) return -1;
+        code |= (int)((b.buf >> (len - 1)) & 1u);
+        const int c = (int)count[len];
+        if (code - c < first) {
+            drop(b, len);
+            return sorted[index + (code - first)];
+        }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -2;
+}
+
+__device__ __forceinline__ void store_lens(WarpTables* t, int at, int n, uint8_t v)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n; i += 32) t->lens[at + i] = v;
+}
+
+enum Stop { kRunning = 0, kDone, kShortIn, kShortOut, kError };
+
+// Output cursor: positions are relative to p; bytes at negative offsets down to -hist are history.
+struct Out { uint8_t* p; uint64_t pos, cap, hist; };
+
+__device__ __forceinline__ uint32_t copy_match(Out& o, uint32_t len, uint32_t dist)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t n = len;
+    if (o.pos + n > o.cap) n = (uint32_t)(o.cap - o.pos);
+    __syncwarp();
+    uint8_t* dst = o.p + o.pos;
+    const uint8_t* src = dst - dist;
+    if (dist >= n) {
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    } else {
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i % dist];
+    }
+    __syncwarp();
+    o.pos += n;
+    return n;
+}
+
+// Decodes symbols of the current block until end-of-block or a stop condition (the work of
+// inflate_fast, inffast.c:67-302, plus the careful tail of inflate.c:951-1076).
+__device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st, bool streaming)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        const uint64_t mark = b.used;
+        refill(b);
+        uint32_t e = t->lit[peek(b, kLitBits)];
+        const uint32_t len = e & 15u;
+        if (len != 0) {
+            if (!have(b, (int)len)) { b.used = mark; return kShortIn; }
+            drop(b, (int)len);
+        } else {
+            int s = slow_symbol(b, t->lit_count, t->lit_sorted, t->lit_max);
+            if (s == -1) { b.used = mark; return kShortIn; }
+            if (s == -2) { st->msg = kMsgBadLit; return kError; }
+            e = litlen_entry((uint32_t)s, 1);
+        }
+        const uint32_t kind = (e >> 8) & 3u;
+        if (kind == kLit) {
+            if (o.pos >= o.cap) { if (streaming) b.used = mark; return kShortOut; }
+            if (lane == 0) o.p[o.pos] = (uint8_t)(e >> 16);
+            o.pos++;
+            continue;
+        }
+        if (kind == kEob) return kDone;
+        if (kind == kBad) { st->msg = kMsgBadLit; return kError; }
+        const int xl = (int)((e >> 4) & 15u);
+        if (!have(b, xl)) { b.used = mark; return kShortIn; }
+        const uint32_t mlen = (e >> 16) + peek(b, xl);
+        drop(b, xl);
+        refill(b);
+        uint32_t de = t->dist[peek(b, kDistBits)];
+        const uint32_t dl = de & 15u;
+        if (dl != 0) {
+            if (!have(b, (int)dl)) { b.used = mark; return kShortIn; }
+            drop(b, (int)dl);
+        } else {
+            int s = slow_symbol(b, t->dist_count, t->dist_sorted, t->dist_max);
+            if (s == -1) { b.used = mark; return kShortIn; }
+            if (s == -2) { st->msg = kMsgBadDist; return kError; }
+            de = dist_entry((uint32_t)s, 1);
+        }
+        if (((de >> 8) & 3u) == kBad) { st->msg = kMsgBadDist; return kError; }
+        const int xd = (int)((de >> 4) & 15u);
+        refill(b);
+        if (!have(b, xd)) { b.used = mark; return kShortIn; }
+        const uint32_t dist = (de >> 16) + peek(b, xd);
+        drop(b, xd);
+        if ((uint64_t)dist > o.pos + o.hist) { st->msg = kMsgFar; return kError; }
+        const uint32_t done = copy_match(o, mlen, dist);
+        if (done < mlen) {
+            st->copy_len = mlen - done; st->copy_dist = dist;
+            return kShortOut;
+        }
+    }
+}
+
+// Adds out[0..n) to the running Adler-32 (s1, s2) of the stream; all lanes cooperate.
+__device__ void adler_fold(uint32_t& s1, uint32_t& s2, const uint8_t* p, uint64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    while (n) {
+        const uint32_t m = n > (1u << 20) ? (1u << 20) : (uint32_t)n;
+        uint64_t a = 0, w = 0;
+        for (uint32_t i = lane; i < m; i += 32) {
+            const uint32_t v = p[i];
+            a += v; w += (uint64_t)(m - i) * v;
+        }
+#pragma unroll
+        for (int k = 16; k; k >>= 1) {
+            a += __shfl_xor_sync(kFull, a, k);
+            w += __shfl_xor_sync(kFull, w, k);
+        }
+        s2 = (uint32_t)((s2 + (uint64_t)m % kAdlerBase * s1 + w % kAdlerBase) % kAdlerBase);
+        s1 = (uint32_t)((s1 + a) % kAdlerBase);
+        p += m; n -= m;
+    }
+}
+
+// Whole-stream driver for one warp.  `st` is this stream's state (shared memory for the batch
+// path, global memory for a z_stream, where it carries the position between calls).
+__device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, uint64_t out_cap,
+                             bool streaming, InfState* st, WarpTables* t,
+                             uint64_t* out_len_p, uint64_t* in_used_p, int32_t* status_p, int32_t* msg_p)
+{
+    const int lane = threadIdx.x & 31;
+    Bits b;
+    b.words = reinterpret_cast<const uint32_t*>((uintptr_t)in & ~(uintptr_t)3);
+    b.nwords = (uint32_t)(((((uintptr_t)in + in_len + 3) & ~(uintptr_t)3) - (uintptr_t)b.words) >> 2);
+    b.total = in_len * 8;
+    seek_bits(b, in, st->bit_off);
+    Out o{out, 0, out_cap, st->hist};
+    const int wrap = st->wrap;
+    int mode = st->mode;
+    int last = st->last;
+    uint32_t s1 = st->s1, s2 = st->s2;
+    uint64_t folded = 0;
+    Stop stop = kRunning;
+
+    if (streaming && mode == kModeCodes) {       // resume inside a compressed block: rebuild its tables
+        for (int i = lane; i < 320; i += 32) t->lens[i] = st->lens[i];
+        __syncwarp();
+        build_table(t->lens, st->nlen, 1, t->lit, kLitBits, t->lit_sorted, t->lit_count, t, &t->lit_max);
+        build_table(t->lens + st->nlen, st->ndist, 2, t->dist, kDistBits, t->dist_sorted, t->dist_count, t, &t->dist_max);
+    }
+
+    while (stop == kRunning) {
+        const uint64_t mark = b.used;
+        if (mode == kModeHead) {
+            if (wrap == ZB200_WRAP_ZLIB) {           // inflate.c:589-632
+                if (!have(b, 16)) { stop = kShortIn; continue; }
+                refill(b);
+                const uint32_t cmf = peek(b, 8); drop(b, 8);
+                const uint32_t flg = peek(b, 8); drop(b, 8);
+                if (((cmf << 8) + flg) % 31u) { st->msg = kMsgHeader; stop = kError; continue; }
+                if ((cmf & 15u) != 8u) { st->msg = kMsgMethod; stop = kError; continue; }
+                if ((cmf >> 4) + 8u > 15u) { st->msg = kMsgWindow; stop = kError; continue; }
+                if (flg & 0x20u) { st->msg = kMsgNeedDict; stop = kError; continue; }
+                s1 = 1; s2 = 0;
+            } else if (wrap != ZB200_WRAP_RAW) { st->msg = kMsgHeader; stop = kError; continue; }
+            mode = kModeBlock;
+        } else if (mode == kModeBlock) {
+            if (last) { mode = kModeTrailer; continue; }
+            if (!have(b, 3)) { stop = kShortIn; continue; }
+            refill(b);
+            const int blast = (int)peek(b, 1); drop(b, 1);
+            const uint32_t type = peek(b, 2); drop(b, 2);
+            if (type == 0) {                          // stored, inflate.c:807-836
+                const int pad = (int)((8 - (b.used & 7)) & 7);
+                if (!have(b, pad + 32)) { b.used = mark; stop = kShortIn; continue; }
+                drop(b, pad);
+                refill(b);
+                const uint32_t len = peek(b, 16); drop(b, 16);
+                refill(b);
+                const uint32_t nlen = peek(b, 16); drop(b, 16);
+                if (len != (nlen ^ 0xffffu)) { st->msg = kMsgStored; stop = kError; continue; }
+                st->stored_left = len;
+                last = blast;
+                mode = kModeStored;
+            } else if (type == 1) {                   // fixed code, inflate.c:205-246
+                store_lens(t, 0, 144, 8); store_lens(t, 144, 112, 9); store_lens(t, 256, 24, 7);
+                store_lens(t, 280, 8, 8); store_lens(t, 288, 32, 5);
+                __syncwarp();
+                build_table(t->lens, 288, 1, t->lit, kLitBits, t->lit_sorted, t->lit_count, t, &t->lit_max);
+                build_table(t->lens + 288, 32, 2, t->dist, kDistBits, t->dist_sorted, t->dist_count, t, &t->dist_max);
+                st->nlen = 288; st->ndist = 32;
+                if (streaming) { for (int i = lane; i < 320; i += 32) st->lens[i] = t->lens[i]; }
+                last = blast;
+                mode = kModeCodes;
+            } else if (type == 2) {                   // dynamic, inflate.c:837-949
+                if (!have(b, 14)) { b.used = mark; stop = kShortIn; continue; }
+                refill(b);
+                const int nlen = (int)peek(b, 5) + 257; drop(b, 5);
+                const int ndist = (int)peek(b, 5) + 1; drop(b, 5);
+                const int ncode = (int)peek(b, 4) + 4; drop(b, 4);
+                if (nlen > 286 || ndist > 30) { st->msg = kMsgTooMany; stop = kError; continue; }
+                if (lane < 20) t->cl_lens[lane] = 0;
+                __syncwarp();
+                bool shortin = false;
+                for (int i = 0; i < ncode; i++) {
+                    if (!have(b, 3)) { shortin = true; break; }
+                    refill(b);
+                    const uint32_t v = peek(b, 3); drop(b, 3);
+                    if (lane == 0) t->cl_lens[c_cl_order[i]] = (uint8_t)v;
+                }
+                if (shortin) { b.used = mark; stop = kShortIn; continue; }
+                __syncwarp();
+                int cl_max;
+                if (build_table(t->cl_lens, 19, 0, t->dist, kClBits, nullptr, t->dist_count, t, &t->dist_max)) {
+                    st->msg = kMsgCodeLens; stop = kError; continue;
+                }
+                __syncwarp();
+                cl_max = t->dist_max;
+                const int total = nlen + ndist;
+                int idx = 0, err = 0;
+                uint32_t prev = 0;
+                while (idx < total) {
+                    refill(b);
+                    uint32_t sym;
+                    if (cl_max == 0) {                // empty code-length code: the reference's marker table
+                        if (!have(b, 1)) { shortin = true; break; }   // yields symbol 0 for one bit
+                        drop(b, 1); sym = 0;
+                    } else {
+                        const uint32_t e = t->dist[peek(b, kClBits)];
+                        const int l = (int)(e & 15u);
+                        if (!have(b, l)) { shortin = true; break; }
+                        drop(b, l); sym = e >> 16;
+                    }
+                    if (sym < 16) {
+                        if (lane == 0) t->lens[idx] = (uint8_t)sym;
+                        prev = sym; idx++;
+                        continue;
+                    }
+                    uint32_t rep, val = 0;
+                    if (sym == 16) {
+                        if (!have(b, 2)) { shortin = true; break; }
+                        if (idx == 0) { err = 1; break; }
+                        val = prev; rep = 3 + peek(b, 2); drop(b, 2);
+                    } else if (sym == 17) {
+                        if (!have(b, 3)) { shortin = true; break; }
+                        rep = 3 + peek(b, 3); drop(b, 3);
+                    } else {
+                        if (!have(b, 7)) { shortin = true; break; }
+                        rep = 11 + peek(b, 7); drop(b, 7);
+                    }
+                    if (idx + (int)rep > total) { err = 1; break; }
+                    store_lens(t, idx, (int)rep, (uint8_t)val);
+                    idx += (int)rep; prev = val;
+                }
+                if (shortin) { b.used = mark; stop = kShortIn; continue; }
+                if (err) { st->msg = kMsgRepeat; stop = kError; continue; }
+                __syncwarp();
+                if (build_table(t->lens, nlen, 1, t->lit, kLitBits, t->lit_sorted, t->lit_count, t, &t->lit_max)) {
+                    st->msg = kMsgLitSet; stop = kError; continue;
+                }
+                if (build_table(t->lens + nlen, ndist, 2, t->dist, kDistBits, t->dist_sorted, t->dist_count, t, &t->dist_max)) {
+                    st->msg = kMsgDistSet; stop = kError; continue;
+                }
+                st->nlen = nlen; st->ndist = ndist;
+                if (streaming) { for (int i = lane; i < 320; i += 32) st->lens[i] = t->lens[i]; }
+                last = blast;
+                mode = kModeCodes;
+            } else { st->msg = kMsgBlockType; stop = kError; }
+        } else if (mode == kModeStored) {
+            const uint64_t bytepos = b.used >> 3;
+            const uint64_t ain = in_len - bytepos, aout = o.cap - o.pos;
+            uint64_t c = st->stored_left;
+            if (c > ain) c = ain;
+            if (c > aout) c = aout;
+            __syncwarp();
+            for (uint64_t i = lane; i < c; i += 32) o.p[o.pos + i] = in[bytepos + i];
+            __syncwarp();
+            o.pos += c; b.used += c * 8;
+            st->stored_left -= (uint32_t)c;
+            if (st->stored_left == 0) { seek_bits(b, in, b.used); mode = kModeBlock; }
+            else stop = (c == ain) ? kShortIn : kShortOut;
+        } else if (mode == kModeCodes) {
+            stop = decode_block(b, o, t, st, streaming);
+            if (stop == kDone) { stop = kRunning; mode = kModeBlock; }
+            else if (stop == kShortOut && st->copy_len) mode = kModeCopy;
+        } else if (mode == kModeCopy) {
+            const uint32_t done = copy_match(o, st->copy_len, st->copy_dist);
+            st->copy_len -= done;
+            if (st->copy_len) stop = kShortOut; else mode = kModeCodes;
+        } else if (mode == kModeTrailer) {
+            const int pad = (int)((8 - (b.used & 7)) & 7);
+            if (wrap == ZB200_WRAP_ZLIB) {            // inflate.c:1077-1098
+                if (!have(b, pad + 32)) { stop = kShortIn; continue; }
+                drop(b, pad);
+                uint32_t want = 0;
+                for (int i = 0; i < 4; i++) { refill(b); want = (want << 8) | peek(b, 8); drop(b, 8); }
+                __syncwarp();
+                adler_fold(s1, s2, o.p + folded, o.pos - folded);
+                folded = o.pos;
+                if (want != ((s2 << 16) | s1)) { st->msg = kMsgCheck; stop = kError; continue; }
+            } else {
+                if (!have(b, pad)) { stop = kShortIn; continue; }
+                drop(b, pad);
+            }
+            mode = kModeDone;
+            stop = kDone;
+        } else {
+            stop = mode == kModeDone ? kDone : kError;
+        }
+    }
+
+    if (wrap == ZB200_WRAP_ZLIB && streaming && folded < o.pos) {
+        __syncwarp();
+        adler_fold(s1, s2, o.p + folded, o.pos - folded);
+    }
+    int32_t status;
+    if (streaming) {
+        status = stop == kDone ? ZB_STREAM_END : stop == kShortIn ? kNeedInput : stop == kShortOut ? kNeedOutput
+               : (st->msg == kMsgNeedDict ? ZB_NEED_DICT : ZB_DATA_ERROR);
+        if (stop == kError) mode = kModeBad;
+    } else {
+        // uncompress() mapping, uncompr.c:53-55: out of input is a data error, out of room with input left a buffer error
+        if (stop == kDone) status = ZB_OK;
+        else if (stop == kShortOut && ((b.used + 7) >> 3) < in_len) status = ZB_BUF_ERROR;
+        else status = ZB_DATA_ERROR;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        st->mode = mode; st->last = last; st->s1 = s1; st->s2 = s2;
+        st->bit_off = (uint32_t)(b.used & 7);
+        uint64_t h = st->hist + o.pos;
+        st->hist = h > 32768 ? 32768 : h;
+        st->total_out += o.pos;
+        *out_len_p = o.pos;
+        if (in_used_p) *in_used_p = stop == kDone ? ((b.used + 7) >> 3) : (b.used >> 3);
+        *status_p = status;
+        if (msg_p) *msg_p = st->msg;
+    }
+}
+
+__global__ void __launch_bounds__(kInfWarps * 32)
+k_inflate_batch(const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_off, uint64_t n,
+                uint8_t* __restrict__ dst, const uint64_t* __restrict__ dst_off,
+                uint64_t* __restrict__ dst_len, int32_t* __restrict__ status, int wrap)
+{
+    __shared__ WarpTables s_tab[kInfWarps];
+    __shared__ InfState s_state[kInfWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t i = (uint64_t)blockIdx.x * kInfWarps + warp;
+    if (i >= n) return;
+    InfState* st = &s_state[warp];
+    for (int k = lane; k < (int)(sizeof(InfState) / 4); k += 32) reinterpret_cast<uint32_t*>(st)[k] = 0;
+    __syncwarp();
+    if (lane == 0) st->wrap = wrap;
+    __syncwarp();
+    const uint64_t a = src_off[i], e = src_off[i + 1], oa = dst_off[i], oe = dst_off[i + 1];
+    inflate_warp(src + a, e - a, dst + oa, oe - oa, false, st, &s_tab[warp], &dst_len[i], nullptr, &status[i], nullptr);
+}
+
+// One z_stream: a single warp continues from *st.
+__global__ void __launch_bounds__(32)
+k_inflate_stream(const uint8_t* __restrict__ in, uint64_t in_len, uint8_t* __restrict__ out, uint64_t out_cap,
+                 InfState* __restrict__ st, InfCallResult* __restrict__ res)
+{
+    __shared__ WarpTables s_tab;
+    inflate_warp(in, in_len, out, out_cap, true, st, &s_tab, &res->out_len, &res->in_used, &res->status, &res->msg);
+}
+
+int inflate_batch_launch(const uint8_t* d_src, const uint64_t* d_src_off, size_t n, uint8_t* d_dst,
+                         const uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status, int wrap, cudaStream_t s)
+{
+    if (n == 0) return 0;
+    if (wrap != ZB200_WRAP_RAW && wrap != ZB200_WRAP_ZLIB) { set_error("inflate batch: wrap %d not supported", wrap); return ZB_STREAM_ERROR; }
+    const unsigned blocks = (unsigned)((n + kInfWarps - 1) / kInfWarps);
+    ZB_LAUNCH(k_inflate_batch, blocks, kInfWarps * 32, 0, s, d_src, d_src_off, (uint64_t)n, d_dst, d_dst_off, d_dst_len, d_status, wrap);
+    ZB_CHECK_LAUNCH();
+    return 0;
+}
+
+int inflate_stream_launch(const uint8_t* d_in, uint64_t in_len, uint8_t* d_out, uint64_t out_cap, InfState* d_state,
+                          InfCallResult* d_res, cudaStream_t s)
+{
+    ZB_LAUNCH(k_inflate_stream, 1, 32, 0, s, d_in, in_len, d_out, out_cap, d_state, d_res);
+    ZB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace zb
+
+using namespace zb;
+
+ZB_API int zb200_inflate_batch_dev(const void* d_src, const uint64_t* d_src_off, size_t n, void* d_dst,
+                                   const uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status, int wrap,
+                                   void* stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    return inflate_batch_launch((const uint8_t*)d_src, d_src_off, n, (uint8_t*)d_dst, d_dst_off, d_dst_len, d_status,
+                                wrap, (cudaStream_t)stream);
+}
+
+ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t n, void* dst, const uint64_t* dst_off,
+                               uint64_t* dst_len, int32_t* status, int wrap, void* stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    Ctx* c = ctx_acquire((cudaStream_t)stream);
+    if (!c) return ZB_MEM_ERROR;
+    cudaStream_t s = pick_stream(c, stream);
+    do {
+        const size_t src_total = (size_t)src_off[n], dst_total = (size_t)dst_off[n];
+        const uint8_t* d_src = to_device(c, src, src_total, s, &rc);
+        if (rc) break;
+        const bool dst_on_host = classify(dst) != kDevice;
+        uint8_t* d_dst = (uint8_t*)dst;
+        if (dst_on_host) {
+            if ((rc = c->out.ensure(dst_total + 16)) != 0) break;
+            d_dst = c->out.as<uint8_t>();
+        }
+        // descriptors: [src_off n+1][dst_off n+1][dst_len n][status n]
+        const size_t desc_bytes = (size_t)(3 * n + 2) * 8 + n * 4;
+        if ((rc = c->ws[0].ensure(desc_bytes)) != 0) break;
+        uint64_t* d_src_off = c->ws[0].as<uint64_t>();
+        uint64_t* d_dst_off = d_src_off + (n + 1);
+        uint64_t* d_len = d_dst_off + (n + 1);
+        int32_t* d_status = (int32_t*)(d_len + n);
+        cudaError_t e = cudaMemcpyAsync(d_src_off, src_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst_off, dst_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { set_error("descriptor upload failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        if ((rc = inflate_batch_launch(d_src, d_src_off, n, d_dst, d_dst_off, d_len, d_status, wrap, s)) != 0) break;
+        e = cudaMemcpyAsync(dst_len, d_len, n * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && dst_on_host) e = cudaMemcpyAsync(dst, d_dst, dst_total, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("inflate batch readback failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+    } while (0);
+    ctx_release(c, s);
+    return rc;
+}
