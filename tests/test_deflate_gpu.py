@@ -1,0 +1,123 @@
+"""GPU: K1-K3 deflate through the C-ABI.  Gate (a): the oracle and the compiled reference decode the
+GPU's output to the original bytes; gate (d): size within 2 % of the reference at the same level."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import zhelpers
+from zlib_b200 import binding as zb
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 2, 3, 4, 5, 100, 257, 258, 259, 1000, 32767, 32768, 32769, 65535, 65536, 131071, 131072, 131073,
+         200000, 262144, 400000]
+
+
+def _decode_everywhere(z, data, oracle, ref=None):
+    rc, out, used = oracle.inflate(z, len(data))
+    assert rc == 0 and out == data and used == len(z)
+    assert zlib.decompress(z) == data                       # independent decoder (system zlib 1.3)
+    if ref is not None:
+        rc, out = ref.uncompress(z, len(data))
+        assert rc == 0 and out == data
+
+
+@pytest.mark.parametrize("level", [1, 6])
+def test_round_trip_sizes_and_kinds(gpu_lib, oracle, level):
+    for kind in range(5):
+        for n in SIZES:
+            data = zhelpers.corpus(kind, n, 7)
+            rc, z = gpu_lib.compress2(data, level)
+            assert rc == 0, (kind, n, rc, gpu_lib.last_error())
+            assert len(z) <= gpu_lib.compress_bound(n)
+            _decode_everywhere(z, data, oracle)
+
+
+def test_all_levels(gpu_lib, oracle):
+    data = zhelpers.corpus(1, 300000, 3) + zhelpers.corpus(3, 100000, 4) + zhelpers.corpus(0, 50000, 5)
+    sizes = {}
+    for level in range(10):
+        rc, z = gpu_lib.compress2(data, level)
+        assert rc == 0
+        _decode_everywhere(z, data, oracle)
+        sizes[level] = len(z)
+        flevel = (z[1] >> 6) & 3
+        assert flevel == (0 if level < 2 else 1 if level < 6 else 2 if level == 6 else 3)   # deflate.c:628-636
+    assert sizes[0] > len(data) and sizes[0] <= gpu_lib.compress_bound(len(data))
+    assert sizes[9] <= sizes[1]
+    rc, z = gpu_lib.compress2(data, -1)
+    assert rc == 0 and len(z) == sizes[6]
+
+
+def test_reference_decodes_gpu_output(gpu_lib, oracle, ref):
+    rng = random.Random(3)
+    for t in range(20):
+        data = zhelpers.corpus(rng.randrange(5), rng.randint(0, 500000), 50 + t)
+        for level in (1, 6):
+            rc, z = gpu_lib.compress2(data, level)
+            assert rc == 0
+            _decode_everywhere(z, data, oracle, ref)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_ratio_gate_vs_reference(gpu_lib, oracle, kind):
+    """<= 2 % larger than the reference compressing the WHOLE buffer as one stream."""
+    data = gpu_lib.synth(8 << 20, kind=kind, seed=11)
+    for level in (1, 6):
+        rc, z = gpu_lib.compress2(data, level)
+        assert rc == 0
+        want = len(oracle.deflate(data, level))
+        assert len(z) <= 1.02 * want, (kind, level, len(z), want, len(z) / want)
+        rc, out, _ = oracle.inflate(z, len(data))
+        assert rc == 0 and out == data.tobytes()
+
+
+def test_buf_error_and_bad_level(gpu_lib):
+    data = zhelpers.corpus(1, 50000, 1)
+    rc, _ = gpu_lib.compress2(data, 6, cap=100)
+    assert rc == zb.Z_BUF_ERROR
+    rc, _ = gpu_lib.compress2(data, 10)
+    assert rc == zb.Z_STREAM_ERROR
+    rc, z = gpu_lib.compress2(zhelpers.corpus(0, 70000, 2), 6, cap=gpu_lib.compress_bound(70000))
+    assert rc == 0                                              # incompressible input fits compressBound
+
+
+def test_gpu_inflate_reads_gpu_deflate(gpu_lib):
+    data = gpu_lib.synth(3 << 20, kind=1, seed=2)
+    rc, z = gpu_lib.compress2(data, 6)
+    assert rc == 0
+    rc, out = gpu_lib.uncompress(z, len(data))
+    assert rc == 0 and out == data.tobytes()
+
+
+def test_raw_gzip_and_shards(gpu_lib, oracle):
+    """Shards with a 32 KiB dictionary concatenate into one valid stream (multi-GPU assembly rule)."""
+    import ctypes as C
+    data = gpu_lib.synth((1 << 20) + 12345, kind=1, seed=4).tobytes()
+    cuts = [0, 300000, 300000 + 131072 * 3, len(data)]
+    parts, adl, crc = [], 1, 0
+    for i, (a, b) in enumerate(zip(cuts, cuts[1:])):
+        last = i == len(cuts) - 2
+        flags = (0 if last else zb.ZB200_DEFLATE_NOT_LAST) | zb.ZB200_DEFLATE_NO_HEADER | zb.ZB200_DEFLATE_NO_TRAILER
+        dict_ = data[max(0, a - 32768):a]
+        cap = gpu_lib.compress_bound(b - a) + 64
+        out = C.create_string_buffer(cap)
+        n, c1, a1 = gpu_lib.deflate_shard(data[a:b], b - a, dict_ if dict_ else None, len(dict_), out, cap, 6, zb.WRAP_RAW, flags)
+        parts.append(out.raw[:n])
+        adl = gpu_lib.adler32_combine(adl, a1, b - a)
+        crc = gpu_lib.crc32_combine(crc, c1, b - a)
+    raw = b"".join(parts)
+    assert zlib.decompress(raw, -15) == data
+    z = b"\x78\x9c" + raw + adl.to_bytes(4, "big")
+    rc, out, used = oracle.inflate(z, len(data))
+    assert rc == 0 and out == data and used == len(z)
+    assert crc == oracle.crc32(data)
+    # gzip wrapper
+    cap = gpu_lib.compress_bound(len(data)) + 32
+    out = C.create_string_buffer(cap)
+    n = gpu_lib.deflate(data, len(data), out, cap, 6, zb.WRAP_GZIP)
+    assert zlib.decompress(out.raw[:n], 31) == data
+    rc, o2, _ = oracle.inflate(out.raw[:n], len(data), 2)
+    assert rc == 0 and o2 == data

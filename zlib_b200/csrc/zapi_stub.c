@@ -11,13 +11,9 @@ STUB(deflateSetHeader, (z_streamp s, gz_headerp h)) STUB(inflate, (z_streamp s, 
 STUB(inflateSetDictionary, (z_streamp s, const Bytef *d, uInt n)) STUB(inflateSync, (z_streamp s))
 STUB(inflateCopy, (z_streamp d, z_streamp s)) STUB(inflateReset, (z_streamp s)) STUB(inflatePrime, (z_streamp s, int b, int v))
 STUB(inflateGetHeader, (z_streamp s, gz_headerp h))
-STUB(compress, (Bytef *d, uLongf *dl, const Bytef *s, uLong sl)) STUB(compress2, (Bytef *d, uLongf *dl, const Bytef *s, uLong sl, int l))
-STUB(uncompress, (Bytef *d, uLongf *dl, const Bytef *s, uLong sl))
 STUB(deflateInit_, (z_streamp s, int l, const char *v, int sz)) STUB(inflateInit_, (z_streamp s, const char *v, int sz))
 STUB(deflateInit2_, (z_streamp s, int l, int m, int w, int ml, int st, const char *v, int sz))
 STUB(inflateInit2_, (z_streamp s, int w, const char *v, int sz))
 ZAPI uLong deflateBound(z_streamp s, uLong n) { (void)s; return compressBound(n); }
 STUB(zb200_checksum_batch, (const void *b, const uint64_t *o, size_t n, uint32_t *c, uint32_t *a, void *s))
-STUB(zb200_deflate, (const void *s, size_t sl, void *d, size_t *dl, int l, int w, void *st))
-STUB(zb200_deflate_shard, (const void *s, size_t sl, const void *dc, size_t dcl, void *d, size_t *dl, int l, int w, int f, uint32_t *c, uint32_t *a, void *st))
 STUB(zb200_deflate_batch, (const void *s, const uint64_t *so, size_t n, void *d, const uint64_t *dof, uint64_t *dl, uint32_t *c, uint32_t *a, int32_t *stt, int l, int w, void *st))

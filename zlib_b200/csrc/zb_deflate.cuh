@@ -1,0 +1,53 @@
+// zb_deflate.cuh -- data layout of the deflate pipeline in HBM (shared by its kernels).
+#pragma once
+#include "zb_common.cuh"
+
+namespace zb {
+
+constexpr uint32_t kChunk = ZB200_CHUNK;         // input bytes parsed by one warp / packed by one CTA
+constexpr uint32_t kWindow = 32768;              // DEFLATE history (h/zconf.h MAX_WBITS = 15)
+constexpr uint32_t kMinMatch = 3, kMaxMatch = 258;
+constexpr uint32_t kBlockTokens = 16384;         // symbols per DEFLATE block (lit_bufsize, deflate.c:291)
+constexpr uint32_t kMaxBlocks = 10;              // block slots per chunk
+constexpr uint32_t kHdrWords = 144;              // dynamic-block header, <= 4495 bits
+constexpr uint32_t kTooFar = 4096;               // deflate.c:108-110
+
+// configuration_table of the reference (deflate.c:137-149); kind 0 stored, 1 greedy, 2 lazy
+struct LevelCfg { uint16_t good, lazy, nice, chain; int kind; };
+
+// One DEFLATE block, produced by the parse kernel, completed by the code-construction kernel.
+struct BlockMeta {
+    uint32_t tok_start;                          // index into the chunk's token array
+    uint32_t tok_count;
+    uint32_t in_start, in_len;                   // input span (relative to the chunk) the tokens cover
+    uint32_t type;                               // 0 stored, 1 fixed, 2 dynamic
+    uint32_t body_bits;                          // bits after the 3 header bits (types 1, 2)
+    uint32_t hdr_bits;                           // dynamic header length in bits (type 2)
+    uint32_t pad;
+};
+
+struct ChunkMeta {
+    uint32_t nblocks;
+    uint32_t stored;                             // 1 = whole chunk emitted as stored blocks
+    uint64_t bytes;                              // compressed size of the chunk
+    uint64_t offset;                             // byte offset in the output stream
+};
+
+// Token: literal = byte value; match = (distance << 16) | (length - 3).
+__device__ __forceinline__ uint32_t len_code(uint32_t l)       // l = length - 3; trees.c _length_code
+{
+    if (l < 8) return l;
+    if (l == 255) return 28;
+    const uint32_t e = 29 - __clz(l);                           // extra bits = msb - 2
+    return 4 * e + 4 + ((l >> e) & 3);
+}
+__device__ __forceinline__ uint32_t len_extra_bits(uint32_t code) { return (code < 8 || code == 28) ? 0 : (code >> 2) - 1; }
+__device__ __forceinline__ uint32_t dist_code(uint32_t d)      // d = distance - 1; trees.c d_code
+{
+    if (d < 4) return d;
+    const uint32_t msb = 31 - __clz(d);
+    return 2 * msb + ((d >> (msb - 1)) & 1);
+}
+__device__ __forceinline__ uint32_t dist_extra_bits(uint32_t code) { return code < 4 ? 0 : (code >> 1) - 1; }
+
+}  // namespace zb
