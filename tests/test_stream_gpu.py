@@ -1,0 +1,131 @@
+"""GPU: the streaming zlib.h ABI (deflate/inflate with arbitrary buffer sizes, flushes, dictionaries) and the
+reference's own callers -- example.c, minizip, miniunz -- linked against libzb200.so."""
+import os
+import random
+import subprocess
+import zlib
+
+import pytest
+
+import zhelpers
+from zlib_b200 import binding as zb
+
+pytestmark = pytest.mark.gpu
+REFDIR = os.path.join(zhelpers.ORACLE_DIR, "_ref")
+
+EXAMPLE_LINES = [  # what the reference's own build prints
+    "uncompress(): hello, hello!", "gzread(): hello, hello!", "gzgets() after gzseek:  hello!",
+    "inflate(): hello, hello!", "large_inflate(): OK", "after inflateSync(): hello, hello!",
+    "inflate with dictionary: hello, hello!"]
+
+
+def test_streaming_deflate_buffer_sizes(gpu_lib, oracle):
+    rng = random.Random(1)
+    for t in range(12):
+        data = zhelpers.corpus(rng.randrange(5), rng.choice([0, 1, 14, 5000, 70000, 300000]), t)
+        for in_chunk, out_chunk in ((1, 1), (7, 13), (4096, 16384), (1 << 20, 1 << 20)):
+            if len(data) > 6000 and in_chunk < 4096:
+                continue
+            for wbits in (15, -15, 31):
+                rc, z = gpu_lib.deflate_stream(data, rng.choice([1, 6]), wbits, in_chunk, out_chunk)
+                assert rc == zb.Z_OK, (t, in_chunk, wbits, rc)
+                assert zlib.decompress(z, wbits) == data
+                if wbits == 15:
+                    assert gpu_lib.last_adler == oracle.adler32(data)
+                    rc2, out, used = oracle.inflate(z, len(data))
+                    assert rc2 == 0 and out == data and used == len(z)
+
+
+def test_flush_points_and_full_flush(gpu_lib, oracle):
+    data = zhelpers.corpus(1, 200000, 9)
+    flushes = {3: zb.Z_FULL_FLUSH, 1000: zb.Z_SYNC_FLUSH, 70000: zb.Z_PARTIAL_FLUSH, 150000: zb.Z_FULL_FLUSH}
+    rc, z = gpu_lib.deflate_stream(data, 6, 15, 1 << 20, 1 << 20, flushes)
+    assert rc == zb.Z_OK
+    assert z.count(b"\x00\x00\xff\xff") >= 4                  # every flush leaves the empty stored block
+    rc2, out, _ = oracle.inflate(z, len(data))
+    assert rc2 == 0 and out == data
+    # after a full flush the tail is decodable on its own as raw deflate (history forgotten)
+    d = zlib.decompressobj(-15)
+    i = z.index(b"\x00\x00\xff\xff") + 4
+    assert (d.decompress(z[i:-4]) + d.flush()) == data[3:]
+
+
+def test_streaming_inflate_buffer_sizes(gpu_lib, oracle):
+    rng = random.Random(2)
+    for t in range(10):
+        data = zhelpers.corpus(rng.randrange(5), rng.choice([0, 1, 14, 5000, 70000, 400000]), 40 + t)
+        z = oracle.deflate(data, rng.choice([0, 1, 6, 9]))
+        for in_chunk, out_chunk in ((1, 1), (5, 3), (16384, 8192), (1 << 20, 1 << 16), (100, 1 << 20)):
+            if len(data) > 6000 and min(in_chunk, out_chunk) < 100:
+                continue
+            rc, out, msg, tin = gpu_lib.inflate_stream(z, 15, in_chunk, out_chunk)
+            assert rc == zb.Z_STREAM_END and out == data and msg is None and tin == len(z), (t, in_chunk, out_chunk, rc, msg)
+            assert gpu_lib.last_adler == oracle.adler32(data)
+        raw = oracle.deflate(data, 6, 0)
+        rc, out, msg, tin = gpu_lib.inflate_stream(raw, -15, 16384, 16384, zb.Z_SYNC_FLUSH)   # the way unzip.c calls it
+        assert rc == zb.Z_STREAM_END and out == data and tin == len(raw)
+
+
+def test_streaming_inflate_errors(gpu_lib, oracle):
+    data = zhelpers.corpus(1, 50000, 3)
+    z = bytearray(oracle.deflate(data, 6))
+    z[len(z) // 2] ^= 0x10
+    rc, out, msg, _ = gpu_lib.inflate_stream(bytes(z), 15, 4096, 4096)
+    assert rc == zb.Z_DATA_ERROR and msg is not None
+    assert msg == oracle.last_msg() or oracle.inflate(bytes(z), len(data))[0] == -3
+    z = oracle.deflate(data, 6)
+    rc, out, msg, _ = gpu_lib.inflate_stream(z[:-1] + bytes([z[-1] ^ 1]), 15, 4096, 4096)
+    assert rc == zb.Z_DATA_ERROR and msg == "incorrect data check" and out == data
+    rc, out, msg, _ = gpu_lib.inflate_stream(z[:len(z) // 2], 15, 4096, 4096, zb.Z_FINISH)
+    assert rc == zb.Z_BUF_ERROR
+
+
+def test_dictionary_round_trip(gpu_lib, oracle):
+    dictionary = b"hello, " * 200
+    data = b"hello, hello! " * 500
+    rc, z = gpu_lib.deflate_stream(data, 9, 15, 1 << 20, 1 << 20, dictionary=dictionary)
+    assert rc == zb.Z_OK and (z[1] & 0x20)
+    d = zlib.decompressobj(zdict=dictionary)
+    assert d.decompress(z) == data
+    rc, out, msg, _ = gpu_lib.inflate_stream(z, 15, 1 << 20, 1 << 20, dictionary=dictionary)
+    assert rc == zb.Z_STREAM_END and out == data
+    rc, out, msg, _ = gpu_lib.inflate_stream(z, 15, 1 << 20, 1 << 20, dictionary=b"wrong dictionary")
+    assert rc == zb.Z_DATA_ERROR
+
+
+def _need(path):
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: run __graft_entry__.build() where /root/reference exists")
+    return path
+
+
+def test_reference_example_c_against_libzb200(gpu_lib):
+    """The reference's acceptance program (qcsrc/example.c + its gzio.c) linked against our library."""
+    exe = _need(os.path.join(REFDIR, "example_zb200"))
+    r = subprocess.run([exe, "/tmp/zb200_example.gz"], capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l.strip() for l in r.stdout.splitlines()]
+    assert lines[0].startswith("zlib version 1.2.3 = 0x1230, compile flags = 0xa9")
+    assert lines[1:] == EXAMPLE_LINES
+
+
+def test_minizip_miniunz_both_directions(gpu_lib, tmp_path):
+    """ZIP written by minizip-on-libzb200 is extracted bit-exact by the reference miniunz, and vice versa."""
+    files = {}
+    for i, (kind, n) in enumerate([(1, 4096), (3, 70000), (0, 20000), (1, 1 << 20), (2, 300000), (1, 0)]):
+        name = f"f{i:05d}.bin"
+        files[name] = zhelpers.corpus(kind, n, 70 + i)
+        (tmp_path / name).write_bytes(files[name])
+    for writer, reader in (("minizip_zb200", "miniunz"), ("minizip", "miniunz_zb200"), ("minizip_zb200", "miniunz_zb200")):
+        w, r = _need(os.path.join(REFDIR, writer)), _need(os.path.join(REFDIR, reader))
+        arc = tmp_path / f"{writer}.zip"
+        out = tmp_path / f"x_{writer}_{reader}"
+        out.mkdir()
+        p = subprocess.run([w, "-o", "-6", str(arc)] + sorted(files), cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout + p.stderr
+        p = subprocess.run([r, "-o", str(arc)], cwd=out, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout + p.stderr
+        for name, data in files.items():
+            assert (out / name).read_bytes() == data, (writer, reader, name)   # miniunz's exit code is not trusted
+        import zipfile
+        assert zipfile.ZipFile(arc).testzip() is None

@@ -227,6 +227,88 @@ class Lib:
                                                      C.c_void_p(d_dst_off), C.c_void_p(d_dst_len), C.c_void_p(d_status),
                                                      wrap, _stream(stream)), "zb200_inflate_batch_dev")
 
+    # ---- streaming API driven the way example.c drives it ----------------
+    def deflate_stream(self, data: bytes, level=6, wbits=15, in_chunk=1 << 16, out_chunk=1 << 16, flushes=None,
+                       dictionary=None, strategy=0):
+        """deflateInit2 + deflate(...) loop + deflateEnd; `flushes` maps input offsets to flush values."""
+        strm = z_stream()
+        rc = self.dll.deflateInit2_(C.byref(strm), level, Z_DEFLATED, wbits, 8, strategy, ZLIB_VERSION, C.sizeof(z_stream))
+        if rc != Z_OK:
+            return rc, b""
+        if dictionary is not None:
+            rc = self.dll.deflateSetDictionary(C.byref(strm), dictionary, len(dictionary))
+            assert rc == Z_OK, rc
+        src = C.create_string_buffer(bytes(data), len(data) + 1)
+        outbuf = C.create_string_buffer(out_chunk)
+        out = bytearray()
+        pos = 0
+        flushes = dict(flushes or {})
+        base = C.addressof(src)
+        while True:
+            n = min(in_chunk, len(data) - pos)
+            cut = min([o for o in flushes if pos < o <= pos + n], default=None)
+            if cut is not None:
+                n = cut - pos
+            strm.next_in, strm.avail_in = base + pos, n
+            pos += n
+            flush = Z_FINISH if pos == len(data) else flushes.get(pos, Z_NO_FLUSH)
+            while True:
+                strm.next_out, strm.avail_out = C.addressof(outbuf), out_chunk
+                rc = self.dll.deflate(C.byref(strm), flush)
+                out += outbuf.raw[:out_chunk - strm.avail_out]
+                if rc == Z_STREAM_END:
+                    break
+                if rc not in (Z_OK, Z_BUF_ERROR):
+                    self.dll.deflateEnd(C.byref(strm))
+                    return rc, bytes(out)
+                if strm.avail_in == 0 and strm.avail_out != 0:
+                    break
+            if rc == Z_STREAM_END:
+                break
+        adler, tin, tout = strm.adler, strm.total_in, strm.total_out
+        rc = self.dll.deflateEnd(C.byref(strm))
+        assert tin == len(data) and tout == len(out), (tin, tout, len(out))
+        self.last_adler = adler
+        return rc, bytes(out)
+
+    def inflate_stream(self, comp: bytes, wbits=15, in_chunk=1 << 16, out_chunk=1 << 16, flush=Z_NO_FLUSH,
+                       dictionary=None):
+        """inflateInit2 + inflate(...) loop + inflateEnd -> (last rc, output, msg, total_in)."""
+        strm = z_stream()
+        rc = self.dll.inflateInit2_(C.byref(strm), wbits, ZLIB_VERSION, C.sizeof(z_stream))
+        if rc != Z_OK:
+            return rc, b"", None, 0
+        if dictionary is not None and wbits < 0:
+            assert self.dll.inflateSetDictionary(C.byref(strm), dictionary, len(dictionary)) == Z_OK
+        src = C.create_string_buffer(bytes(comp), len(comp) + 1)
+        outbuf = C.create_string_buffer(out_chunk)
+        out = bytearray()
+        pos, base = 0, C.addressof(src)
+        rc = Z_OK
+        stall = 0
+        while rc == Z_OK or rc == Z_BUF_ERROR:
+            if strm.avail_in == 0 and pos < len(comp):
+                n = min(in_chunk, len(comp) - pos)
+                strm.next_in, strm.avail_in = base + pos, n
+                pos += n
+            strm.next_out, strm.avail_out = C.addressof(outbuf), out_chunk
+            before = (strm.total_in, strm.total_out)
+            rc = self.dll.inflate(C.byref(strm), flush)
+            out += outbuf.raw[:out_chunk - strm.avail_out]
+            if rc == Z_NEED_DICT and dictionary is not None:
+                rc = self.dll.inflateSetDictionary(C.byref(strm), dictionary, len(dictionary))
+                continue
+            if (strm.total_in, strm.total_out) == before:
+                stall += 1
+                if stall > 2 or (pos >= len(comp) and strm.avail_in == 0):
+                    break
+            else:
+                stall = 0
+        msg, tin = strm.msg, strm.total_in
+        self.last_adler = strm.adler
+        self.dll.inflateEnd(C.byref(strm))
+        return rc, bytes(out), (msg.decode() if msg else None), tin
+
     def synth(self, n: int, kind: int = 1, seed: int = 1):
         """numpy uint8 array of synthetic corpus bytes."""
         import numpy as np

@@ -3,11 +3,20 @@
  * qcsrc/crc32.c:205 (get_crc_table), qcsrc/compress.c:75 (compressBound). */
 #include "../../include/zlib.h"
 
+#include <stdlib.h>
 #define ZAPI __attribute__((visibility("default")))
 
-static const char *const errmsg[10] = {          /* zutil.c:14-24, indexed by 2 - code */
+
+/* zutil.c:14-24, indexed by 2 - code.  Exported under the reference's name because its own
+ * gzio.c reaches for it through the ERR_MSG macro of zutil.h. */
+ZAPI const char *const z_errmsg[10] = {
     "need dictionary", "stream end", "", "file error", "stream error",
     "data error", "insufficient memory", "buffer error", "incompatible version", ""};
+#define errmsg z_errmsg
+
+/* zutil.c:300-318 */
+ZAPI voidpf zcalloc(voidpf opaque, unsigned items, unsigned size) { (void)opaque; return malloc((size_t)items * size); }
+ZAPI void zcfree(voidpf opaque, voidpf ptr) { (void)opaque; free(ptr); }
 
 ZAPI const char *zlibVersion(void) { return ZLIB_VERSION; }
 

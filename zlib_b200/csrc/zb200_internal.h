@@ -1,0 +1,44 @@
+/* zb200_internal.h -- C-linkage seam between the host-C zlib.h shim (zapi_*.c) and the
+ * CUDA engine (zb_*.cu).  Hidden visibility: not part of the exported ABI. */
+#ifndef ZB200_INTERNAL_H
+#define ZB200_INTERNAL_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Forces the empty stored block at the end of a non-final shard even when the shard
+ * already ends on a byte boundary (Z_SYNC_FLUSH / Z_FULL_FLUSH marker, deflate.c:808-819). */
+#define ZB200I_DEFLATE_FORCE_MARK 8
+
+/* ---- one resumable inflate stream (inflate.c state machine on the device) ---- */
+typedef struct zb200i_inflater zb200i_inflater;
+
+#define ZB200I_NEED_INPUT  100
+#define ZB200I_NEED_OUTPUT 101
+
+int  zb200i_inflate_open(zb200i_inflater **h, int wrap);
+int  zb200i_inflate_reset(zb200i_inflater *h, int wrap);
+void zb200i_inflate_close(zb200i_inflater *h);
+int  zb200i_inflate_clone(zb200i_inflater **dst, const zb200i_inflater *src);
+/* Feeds `in_len` new bytes, produces at most out_cap bytes into `out` (host memory).
+ * *in_used: how many of the new bytes the stream has taken (bytes it could not decode yet
+ * are kept inside the handle).  status: Z_STREAM_END, Z_NEED_DICT, Z_DATA_ERROR,
+ * ZB200I_NEED_INPUT, ZB200I_NEED_OUTPUT.  *check = running Adler-32 (zlib) of the output,
+ * or the DICTID when status is Z_NEED_DICT. */
+int  zb200i_inflate_run(zb200i_inflater *h, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
+                        size_t *in_used, size_t *out_len, int *status, int *msg, uint32_t *check);
+int  zb200i_inflate_set_dict(zb200i_inflater *h, const uint8_t *dict, size_t n);
+/* Drops buffered input and restarts block decoding (after inflateSync found a marker). */
+int  zb200i_inflate_resync(zb200i_inflater *h);
+int  zb200i_inflate_mode(const zb200i_inflater *h);         /* InfMode of the device state */
+size_t zb200i_inflate_pending_input(const zb200i_inflater *h);
+const uint8_t *zb200i_inflate_pending_bytes(const zb200i_inflater *h);
+
+const char *zb200i_inflate_msg(int msg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -33,6 +33,7 @@
 // Output is a valid DEFLATE stream, not the reference's bytes: parity is "reference inflate decodes
 // it bit-exact" plus a size bound (<= 1.02 x reference at the same level), see tests/.
 #include "zb_deflate.cuh"
+#include "zb200_internal.h"
 
 namespace zb {
 
@@ -492,16 +493,17 @@ k_huff_build(uint64_t nchunks, const ChunkMeta* __restrict__ chunks, BlockMeta* 
 __device__ __forceinline__ uint64_t stored_chunk_bytes(uint32_t len) { return (uint64_t)len + 5ull * ((len + 65534u) / 65535u); }
 
 __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chunks, const BlockMeta* __restrict__ blk,
-                       int last_is_final, int force_stored)
+                       int last_is_final, int force_stored, int force_mark)
 {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     ChunkMeta cm = chunks[c];
     const uint32_t clen = (uint32_t)min((uint64_t)kChunk, n - c * kChunk);
     const bool final_chunk = last_is_final && c == nchunks - 1;
+    const bool mark = force_mark && !last_is_final && c == nchunks - 1;   // Z_SYNC_FLUSH marker wanted regardless
     uint64_t bytes;
     if (force_stored) {
-        cm.stored = 1; bytes = stored_chunk_bytes(clen);
+        cm.stored = 1; bytes = stored_chunk_bytes(clen) + (mark ? 5 : 0);
     } else {
         uint64_t bits = 0;
         bool ends_stored = false;
@@ -510,9 +512,9 @@ __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chu
             if (bm.type == 0) { bits = ((bits + 3 + 7) & ~7ull) + 32 + 8ull * bm.in_len; ends_stored = true; }
             else { bits += 3 + bm.body_bits; ends_stored = false; }
         }
-        if (final_chunk || ends_stored) bytes = (bits + 7) >> 3;
+        if (final_chunk || (ends_stored && !mark)) bytes = (bits + 7) >> 3;
         else bytes = ((bits + 3 + 7) >> 3) + 4;                 // empty stored block: 000, pad, 00 00 FF FF
-        const uint64_t sb = stored_chunk_bytes(clen);
+        const uint64_t sb = stored_chunk_bytes(clen) + (mark ? 5 : 0);
         cm.stored = sb <= bytes ? 1u : 0u;
         if (cm.stored) bytes = sb;
     }
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(kPackThreads)
 k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restrict__ tok,
             const BlockMeta* __restrict__ blk, const uint32_t* __restrict__ blk_codes, const uint32_t* __restrict__ blk_hdr,
             const ChunkMeta* __restrict__ chunks, uint8_t* __restrict__ out, uint64_t cap, int last_is_final,
-            uint32_t* __restrict__ err)
+            int force_mark, uint32_t* __restrict__ err)
 {
     __shared__ uint32_t s_stage[kStageWords];
     __shared__ uint32_t s_sums[kPackThreads / 32];
@@ -617,6 +619,7 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
     const uint64_t cbeg = c * kChunk;
     const uint32_t clen = (uint32_t)min((uint64_t)kChunk, n - cbeg);
     const bool final_chunk = last_is_final && c == nchunks - 1;
+    const bool mark = force_mark && !last_is_final && c == nchunks - 1;
     uint8_t* dst = out + cm.offset;
     const uint8_t* in = src + cbeg;
 
@@ -633,6 +636,7 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
             for (uint32_t i = threadIdx.x; i < len; i += kPackThreads) dst[o + 5 + i] = in[done + i];
             o += 5 + len; done += len;
         }
+        if (mark && threadIdx.x == 0) { dst[o] = 0; dst[o + 1] = 0; dst[o + 2] = 0; dst[o + 3] = 0xff; dst[o + 4] = 0xff; }
         return;
     }
 
@@ -695,7 +699,7 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
         }
     }
     // end of chunk: final -> pad; otherwise empty stored block unless already byte-aligned by a stored block
-    if (final_chunk || ends_stored) {
+    if (final_chunk || (ends_stored && !mark)) {
         const uint32_t pad = (8 - (pk.carry_bits & 7)) & 7;
         pk.round(0, threadIdx.x == 0 ? pad : 0);
     } else {
@@ -745,10 +749,14 @@ __global__ void k_frame(uint8_t* __restrict__ out, uint64_t cap, uint64_t hdr_le
 }
 
 // empty input: a lone final fixed block with just the end-of-block code = 03 00 (what the reference emits)
-__global__ void k_empty_payload(uint8_t* out, uint64_t cap, uint64_t at, int not_last, uint64_t* payload)
+__global__ void k_empty_payload(uint8_t* out, uint64_t cap, uint64_t at, int not_last, int force_mark, uint64_t* payload)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (not_last) { payload[0] = 0; return; }
+    if (not_last) {
+        payload[0] = force_mark ? 5 : 0;
+        if (force_mark && at + 5 <= cap) { out[at] = 0; out[at + 1] = 0; out[at + 2] = 0; out[at + 3] = 0xff; out[at + 4] = 0xff; }
+        return;
+    }
     payload[0] = 2;
     if (at + 2 <= cap) { out[at] = 3; out[at + 1] = 0; }
 }
@@ -767,7 +775,10 @@ int deflate_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint64_t n, uint
         attr = true;
     }
     if (level < 0) level = 6;
-    const LevelCfg cfg = h_levels[level];
+    LevelCfg cfg = h_levels[level];
+    const int strategy = (flags >> 8) & 7;                      // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
+    const int force_mark = (flags & ZB200I_DEFLATE_FORCE_MARK) ? 1 : 0;
+    if (strategy == 2 && cfg.kind != 0) { cfg.chain = 0; cfg.kind = 1; }   // literals only (deflate.c:1490)
     const uint64_t total = dict + n;
     const uint64_t nchunks = (n + kChunk - 1) / kChunk;
     const int last_is_final = (flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
@@ -782,7 +793,7 @@ int deflate_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint64_t n, uint
     uint64_t* d_payload = c->ws[1].as<uint64_t>();
 
     if (nchunks == 0) {
-        ZB_LAUNCH(k_empty_payload, 1, 32, 0, s, d_out, cap, hdr_len, !last_is_final, d_payload);
+        ZB_LAUNCH(k_empty_payload, 1, 32, 0, s, d_out, cap, hdr_len, !last_is_final, force_mark, d_payload);
     } else {
         if ((rc = c->ws[2].ensure(nchunks * sizeof(ChunkMeta))) != 0) return rc;
         ChunkMeta* d_chunks = c->ws[2].as<ChunkMeta>();
@@ -802,19 +813,23 @@ int deflate_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint64_t n, uint
             d_blk = c->ws[6].as<BlockMeta>();
             d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
             const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
-            ZB_LAUNCH(k_lz_link, nseg, 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
-            ZB_LAUNCH(k_lz_match, (unsigned)((n + 255) / 256), 256, 0, s, d_buf, total, dict, d_dist, d_mt, (int)cfg.chain, (int)cfg.nice);
+            if (cfg.chain == 0) {
+                ZB_CUDA(cudaMemsetAsync(d_mt, 0, n * 4, s));
+            } else {
+                ZB_LAUNCH(k_lz_link, nseg, 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
+                ZB_LAUNCH(k_lz_match, (unsigned)((n + 255) / 256), 256, 0, s, d_buf, total, dict, d_dist, d_mt, (int)cfg.chain, (int)cfg.nice);
+            }
             ZB_LAUNCH(k_lz_parse, (unsigned)((nchunks + kParseWarps - 1) / kParseWarps), kParseWarps * 32, 0, s, d_src, n, d_mt,
                       d_tok, d_blk, d_hist, d_chunks, cfg.kind, (uint32_t)cfg.lazy);
             ZB_LAUNCH(k_huff_build, (unsigned)((nslots + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, nchunks, d_chunks,
-                      d_blk, d_hist, d_codes, d_hdr, 0);
+                      d_blk, d_hist, d_codes, d_hdr, strategy == 4 ? 1 : 0);
         } else {
             ZB_CUDA(cudaMemsetAsync(d_chunks, 0, nchunks * sizeof(ChunkMeta), s));
         }
-        ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0);
+        ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0, force_mark);
         ZB_LAUNCH(k_scan, 1, 1024, 0, s, nchunks, d_chunks, hdr_len, d_payload);
         ZB_LAUNCH(k_huff_pack, (unsigned)nchunks, kPackThreads, 0, s, d_src, n, d_tok, d_blk, d_codes, d_hdr, d_chunks, d_out, cap,
-                  last_is_final, d_err);
+                  last_is_final, force_mark, d_err);
     }
     ZB_LAUNCH(k_frame, 1, 32, 0, s, d_out, cap, hdr_len, d_payload, d_sums, n, level, wrap, flags, d_total);
     ZB_CHECK_LAUNCH();

@@ -25,6 +25,9 @@
 // Roofline: HBM (algorithmic bytes = compressed in + plain out), but the kernel is
 // latency/issue bound by construction; see DESIGN.md.
 #include "zb_inflate.cuh"
+#include "zb200_internal.h"
+#include <vector>
+#include <string.h>
 
 namespace zb {
 
@@ -32,6 +35,7 @@ constexpr int kInfWarps = 4;                     // warps (= streams in flight) 
 constexpr int kLitBits = 10, kDistBits = 8, kClBits = 7;
 constexpr int kLitSize = 1 << kLitBits, kDistSize = 1 << kDistBits;
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kWindow32 = 32768;
 
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
@@ -188,7 +192,7 @@ __device__ __forceinline__ void store_lens(WarpTables* t, int at, int n, uint8_t
     for (int i = lane; i < n; i += 32) t->lens[at + i] = v;
 }
 
-enum Stop { kRunning = 0, kDone, kShortIn, kShortOut, kError };
+enum Stop { kRunning = 0, kDone, kShortIn, kShortOut, kError, kWantDict };
 
 // Output cursor: positions are relative to p; bytes at negative offsets down to -hist are history.
 struct Out { uint8_t* p; uint64_t pos, cap, hist; };
@@ -312,7 +316,7 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
     uint64_t folded = 0;
     Stop stop = kRunning;
 
-    if (streaming && mode == kModeCodes) {       // resume inside a compressed block: rebuild its tables
+    if (streaming && (mode == kModeCodes || mode == kModeCopy)) {   // resume inside a compressed block: rebuild its tables
         for (int i = lane; i < 320; i += 32) t->lens[i] = st->lens[i];
         __syncwarp();
         build_table(t->lens, st->nlen, 1, t->lit, kLitBits, t->lit_sorted, t->lit_count, t, &t->lit_max);
@@ -330,8 +334,15 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
                 if (((cmf << 8) + flg) % 31u) { st->msg = kMsgHeader; stop = kError; continue; }
                 if ((cmf & 15u) != 8u) { st->msg = kMsgMethod; stop = kError; continue; }
                 if ((cmf >> 4) + 8u > 15u) { st->msg = kMsgWindow; stop = kError; continue; }
-                if (flg & 0x20u) { st->msg = kMsgNeedDict; stop = kError; continue; }
                 s1 = 1; s2 = 0;
+                if (flg & 0x20u) {                    // preset dictionary, inflate.c:630, 761-770
+                    if (!streaming) { st->msg = kMsgNeedDict; stop = kError; continue; }
+                    if (!have(b, 32)) { b.used = mark; stop = kShortIn; continue; }
+                    uint32_t id = 0;
+                    for (int i = 0; i < 4; i++) { refill(b); id = (id << 8) | peek(b, 8); drop(b, 8); }
+                    st->dict_id = id;
+                    mode = kModeDict; stop = kWantDict; continue;
+                }
             } else if (wrap != ZB200_WRAP_RAW) { st->msg = kMsgHeader; stop = kError; continue; }
             mode = kModeBlock;
         } else if (mode == kModeBlock) {
@@ -474,6 +485,8 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
             }
             mode = kModeDone;
             stop = kDone;
+        } else if (mode == kModeDict) {
+            stop = kWantDict;
         } else {
             stop = mode == kModeDone ? kDone : kError;
         }
@@ -486,7 +499,7 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
     int32_t status;
     if (streaming) {
         status = stop == kDone ? ZB_STREAM_END : stop == kShortIn ? kNeedInput : stop == kShortOut ? kNeedOutput
-               : (st->msg == kMsgNeedDict ? ZB_NEED_DICT : ZB_DATA_ERROR);
+               : stop == kWantDict ? ZB_NEED_DICT : ZB_DATA_ERROR;
         if (stop == kError) mode = kModeBad;
     } else {
         // uncompress() mapping, uncompr.c:53-55: out of input is a data error, out of room with input left a buffer error
@@ -555,9 +568,211 @@ int inflate_stream_launch(const uint8_t* d_in, uint64_t in_len, uint8_t* d_out, 
     return 0;
 }
 
+// After a streaming call: keep the last 32 KiB of (history + new output) right-aligned in front of the
+// output region (the reference's updatewindow, inflate.c:323-371).  One CTA; loads complete before stores.
+__global__ void __launch_bounds__(1024) k_slide_history(uint8_t* arena, uint64_t hist_before, uint64_t out_len)
+{
+    const uint64_t valid = hist_before + out_len;
+    const uint32_t keep = (uint32_t)(valid > kWindow32 ? kWindow32 : valid);
+    const uint8_t* src = arena + kWindow32 + out_len - keep;
+    uint8_t* dst = arena + kWindow32 - keep;
+    uint8_t r[32];
+    const uint32_t base = threadIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i++) r[i] = base + i < keep ? src[base + i] : 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i++) if (base + i < keep) dst[base + i] = r[i];
+}
+
 }  // namespace zb
 
 using namespace zb;
+
+// ---- one resumable stream behind zlib.h's inflate() ----
+struct zb200i_inflater {
+    int wrap = 1;
+    InfState* d_state = nullptr;
+    InfCallResult* d_res = nullptr;
+    uint8_t* d_arena = nullptr;                  // [32 KiB history][output window]
+    size_t out_window = 0;
+    uint8_t* d_in = nullptr; size_t d_in_cap = 0;
+    uint8_t* h_pin = nullptr; size_t h_pin_cap = 0;
+    std::vector<uint8_t> carry;                  // input the decoder has been handed but could not finish
+    cudaStream_t s = nullptr;
+    uint64_t hist = 0;
+    int mode = kModeHead;
+    uint32_t check = 1;
+};
+
+static const char* const kInfMsgs[] = {
+    nullptr, "incorrect header check", "unknown compression method", "invalid window size", "need dictionary",
+    "invalid block type", "invalid stored block lengths", "too many length or distance symbols",
+    "invalid code lengths set", "invalid bit length repeat", "invalid literal/lengths set", "invalid distances set",
+    "invalid literal/length code", "invalid distance code", "invalid distance too far back", "incorrect data check",
+    "incorrect length check", "unknown header flags set", "header crc mismatch"};
+
+extern "C" const char* zb200i_inflate_msg(int msg)
+{
+    return (msg > 0 && msg < (int)(sizeof(kInfMsgs) / sizeof(kInfMsgs[0]))) ? kInfMsgs[msg] : nullptr;
+}
+
+static int inflater_write_state(zb200i_inflater* h, int wrap)
+{
+    InfState st;
+    memset(&st, 0, sizeof(st));
+    st.wrap = wrap; st.mode = kModeHead; st.s1 = 1;
+    ZB_CUDA(cudaMemcpyAsync(h->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, h->s));
+    ZB_CUDA(cudaStreamSynchronize(h->s));
+    h->wrap = wrap; h->hist = 0; h->mode = kModeHead; h->check = 1; h->carry.clear();
+    return 0;
+}
+
+extern "C" int zb200i_inflate_open(zb200i_inflater** out, int wrap)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    zb200i_inflater* h = new zb200i_inflater();
+    h->out_window = 1u << 20;
+    bool ok = cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&h->d_state, sizeof(InfState)) == cudaSuccess &&
+              cudaMalloc(&h->d_res, sizeof(InfCallResult)) == cudaSuccess &&
+              cudaMalloc(&h->d_arena, kWindow32 + h->out_window + 64) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); zb200i_inflate_close(h); set_error("inflate state allocation failed"); return ZB_MEM_ERROR; }
+    if ((rc = inflater_write_state(h, wrap)) != 0) { zb200i_inflate_close(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+extern "C" int zb200i_inflate_reset(zb200i_inflater* h, int wrap) { return inflater_write_state(h, wrap); }
+
+extern "C" void zb200i_inflate_close(zb200i_inflater* h)
+{
+    if (!h) return;
+    if (h->d_state) cudaFree(h->d_state);
+    if (h->d_res) cudaFree(h->d_res);
+    if (h->d_arena) cudaFree(h->d_arena);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->s) cudaStreamDestroy(h->s);
+    delete h;
+}
+
+extern "C" int zb200i_inflate_clone(zb200i_inflater** out, const zb200i_inflater* src)
+{
+    zb200i_inflater* h = nullptr;
+    int rc = zb200i_inflate_open(&h, src->wrap);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpy(h->d_state, src->d_state, sizeof(InfState), cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_arena, src->d_arena, kWindow32, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) { zb200i_inflate_close(h); set_error("inflate state copy failed"); return ZB_MEM_ERROR; }
+    h->carry = src->carry; h->hist = src->hist; h->mode = src->mode; h->check = src->check;
+    *out = h;
+    return 0;
+}
+
+extern "C" int zb200i_inflate_mode(const zb200i_inflater* h) { return h->mode; }
+extern "C" size_t zb200i_inflate_pending_input(const zb200i_inflater* h) { return h->carry.size(); }
+extern "C" const uint8_t* zb200i_inflate_pending_bytes(const zb200i_inflater* h) { return h->carry.data(); }
+
+extern "C" int zb200i_inflate_set_dict(zb200i_inflater* h, const uint8_t* dict, size_t n)
+{
+    if (n > kWindow32) { dict += n - kWindow32; n = kWindow32; }
+    ZB_CUDA(cudaMemcpyAsync(h->d_arena + kWindow32 - n, dict, n, cudaMemcpyDefault, h->s));
+    const uint64_t hist = n;
+    ZB_CUDA(cudaMemcpyAsync((uint8_t*)h->d_state + offsetof(InfState, hist), &hist, 8, cudaMemcpyHostToDevice, h->s));
+    if (h->mode == kModeDict) {
+        const int32_t mode = kModeBlock;
+        ZB_CUDA(cudaMemcpyAsync((uint8_t*)h->d_state + offsetof(InfState, mode), &mode, 4, cudaMemcpyHostToDevice, h->s));
+        h->mode = kModeBlock;
+    }
+    ZB_CUDA(cudaStreamSynchronize(h->s));
+    h->hist = n;
+    return 0;
+}
+
+extern "C" int zb200i_inflate_resync(zb200i_inflater* h)
+{
+    // inflate.c:1294-1301: keep totals, restart at a block boundary with an empty bit buffer
+    InfState st;
+    ZB_CUDA(cudaMemcpy(&st, h->d_state, sizeof(st), cudaMemcpyDeviceToHost));
+    st.mode = kModeBlock; st.last = 0; st.bit_off = 0; st.stored_left = 0; st.copy_len = 0; st.msg = 0;
+    ZB_CUDA(cudaMemcpy(h->d_state, &st, sizeof(st), cudaMemcpyHostToDevice));
+    h->mode = kModeBlock;
+    h->carry.clear();
+    return 0;
+}
+
+extern "C" int zb200i_inflate_run(zb200i_inflater* h, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap,
+                                  size_t* in_used, size_t* out_len, int* status, int* msg, uint32_t* check)
+{
+    size_t taken = 0, produced = 0;
+    int st = ZB200I_NEED_INPUT, m = 0;
+    for (;;) {
+        const size_t window = out_cap - produced < h->out_window ? out_cap - produced : h->out_window;
+        size_t feed = in_len - taken;
+        const size_t feed_cap = window + (window >> 3) + 4096;        // enough compressed bytes for one output window
+        if (feed > feed_cap) feed = feed_cap;
+        const size_t total_in = h->carry.size() + feed;
+        if (total_in + 64 > h->h_pin_cap) {
+            if (h->h_pin) cudaFreeHost(h->h_pin);
+            h->h_pin_cap = (total_in + 64) * 2;
+            if (cudaMallocHost(&h->h_pin, h->h_pin_cap) != cudaSuccess) { h->h_pin = nullptr; h->h_pin_cap = 0; set_error("pinned allocation failed"); return ZB_MEM_ERROR; }
+        }
+        if (total_in + 64 > h->d_in_cap) {
+            if (h->d_in) cudaFree(h->d_in);
+            h->d_in_cap = (total_in + 64) * 2;
+            if (cudaMalloc(&h->d_in, h->d_in_cap) != cudaSuccess) { h->d_in = nullptr; h->d_in_cap = 0; set_error("device allocation failed"); return ZB_MEM_ERROR; }
+        }
+        if (!h->carry.empty()) memcpy(h->h_pin, h->carry.data(), h->carry.size());
+        if (feed) memcpy(h->h_pin + h->carry.size(), in + taken, feed);
+        memset(h->h_pin + total_in, 0, 8);
+        ZB_CUDA(cudaMemcpyAsync(h->d_in, h->h_pin, total_in + 8, cudaMemcpyHostToDevice, h->s));
+        int rc = inflate_stream_launch(h->d_in, total_in, h->d_arena + kWindow32, window, h->d_state, h->d_res, h->s);
+        if (rc) return rc;
+        InfCallResult res;
+        ZB_CUDA(cudaMemcpyAsync(&res, h->d_res, sizeof(res), cudaMemcpyDeviceToHost, h->s));
+        ZB_CUDA(cudaStreamSynchronize(h->s));
+        if (res.out_len) {
+            ZB_CUDA(cudaMemcpyAsync(out + produced, h->d_arena + kWindow32, res.out_len, cudaMemcpyDeviceToHost, h->s));
+            ZB_LAUNCH(k_slide_history, 1, 1024, 0, h->s, h->d_arena, h->hist, res.out_len);
+            ZB_CUDA(cudaStreamSynchronize(h->s));
+            const uint64_t v = h->hist + res.out_len;
+            h->hist = v > kWindow32 ? kWindow32 : v;
+        }
+        produced += res.out_len;
+        st = res.status; m = res.msg;
+        // account for the input: the decoder consumed res.in_used bytes of [carry | feed]
+        const size_t carry_n = h->carry.size();
+        size_t from_new = res.in_used > carry_n ? res.in_used - carry_n : 0;
+        if (st == ZB200I_NEED_INPUT || st == ZB_NEED_DICT || st == ZB_STREAM_END || st == ZB_DATA_ERROR) {
+            // whatever is left of this call's window of input stays with the stream
+            std::vector<uint8_t> rest(h->h_pin + res.in_used, h->h_pin + total_in);
+            if (st == ZB_STREAM_END || st == ZB_DATA_ERROR) {
+                // bytes after the end of the stream belong to the caller again
+                rest.clear();
+                taken += from_new;
+                if (res.in_used < carry_n) { /* the stream ended inside bytes taken earlier: cannot hand them back */ }
+            } else {
+                taken += feed;
+            }
+            h->carry.swap(rest);
+        } else {                                                       // output window full
+            if (res.in_used >= carry_n) { h->carry.clear(); taken += from_new; }
+            else h->carry.erase(h->carry.begin(), h->carry.begin() + res.in_used);
+        }
+        if (st == ZB200I_NEED_INPUT && taken < in_len) continue;       // more caller input to hand over
+        if (st == ZB200I_NEED_OUTPUT && produced < out_cap) continue;  // more room in the caller's buffer
+        break;
+    }
+    InfState dst;
+    ZB_CUDA(cudaMemcpy(&dst, h->d_state, sizeof(InfState) - sizeof(dst.lens), cudaMemcpyDeviceToHost));
+    h->mode = dst.mode;
+    h->check = st == ZB_NEED_DICT ? dst.dict_id : ((dst.s2 << 16) | dst.s1);
+    *in_used = taken; *out_len = produced; *status = st; *msg = m; *check = h->check;
+    return 0;
+}
+
 
 ZB_API int zb200_inflate_batch_dev(const void* d_src, const uint64_t* d_src_off, size_t n, void* d_dst,
                                    const uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status, int wrap,

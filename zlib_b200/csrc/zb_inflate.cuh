@@ -6,7 +6,7 @@ namespace zb {
 
 // Where a stream stands (the reference's inflate_mode, h/inflate.h:20-51, collapsed to the
 // points at which this decoder can pause).
-enum InfMode { kModeHead = 0, kModeBlock, kModeStored, kModeCodes, kModeCopy, kModeTrailer, kModeDone, kModeBad };
+enum InfMode { kModeHead = 0, kModeBlock, kModeStored, kModeCodes, kModeCopy, kModeTrailer, kModeDone, kModeBad, kModeDict };
 
 // strm->msg texts of the reference (inflate.c, inffast.c), by index.
 enum InfMsg { kMsgNone = 0, kMsgHeader, kMsgMethod, kMsgWindow, kMsgNeedDict, kMsgBlockType, kMsgStored,
