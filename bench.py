@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark (one JSON line on stdout).
+
+Workload = BASELINE.json configs[1]: 1 GiB of the synthetic mixed corpus,
+deflate in 128 KiB chunks on one B200, level 1 as the headline (`value`), with level 6, batch
+inflate and the fused checksum reported beside it under `extra`.
+
+  value     deflate level-1 throughput, GB/s of UNCOMPRESSED bytes, input and output resident in HBM,
+            timed with CUDA events on the launching stream (max over ranks for --gpus N).
+  e2e       the same metric through the reference-facing call compress2(dest, &destLen, source,
+            sourceLen, 1) of libzb200.so with HOST (pinned) buffers: H2D + kernels + D2H in the timed region.
+  roofline  dominant kernel of a step (per-kernel CUDA events inside the library, zb200_profile):
+            algorithmic bytes (n_in + n_out) / that kernel's time, against the measured HBM peak.
+  cpu_baseline / --impl reference
+            the UNMODIFIED reference (oracle/_ref/libzref.so, built from /root/reference by oracle/Makefile)
+            running compress2 level 1 on the host cores of this box, all threads, on a bounded sample.
+
+A step = one pass of the hot path over the 1 GiB batch (per GPU: weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "deflate_level1_GBps_uncompressed"
+UNIT = "GB/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:   # noqa: BLE001
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:   # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nme in enumerate(names):
+                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
+                    reasons.add(nme)
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------- reference arm
+def reference_compress_throughput(level, sample_bytes, kind=1, seed=1):
+    """compress2 of the unmodified reference on all host cores; returns (GB/s, cores, seconds, ratio)."""
+    import zhelpers
+    from zlib_b200 import load
+    if not os.path.exists(zhelpers.REF_PATH):
+        return None
+    ref = zhelpers.Ref()
+    lib = load()
+    cores = os.cpu_count() or 1
+    per = max(131072, (sample_bytes // cores) // 131072 * 131072)
+    data = lib.synth(per * cores, kind=kind, seed=seed)          # host generator only: no GPU involved
+    outs = [0] * cores
+    cap = ref.dll.compressBound(per)
+    bufs = [C.create_string_buffer(cap) for _ in range(cores)]
+
+    def work(i):
+        ol = C.c_ulong(cap)
+        rc = ref.dll.compress2(bufs[i], C.byref(ol), C.c_void_p(data.ctypes.data + i * per), per, level)
+        assert rc == 0
+        outs[i] = ol.value
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return per * cores / dt / 1e9, cores, dt, per * cores / max(1, sum(outs)), per * cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    size = args.size_mib << 20
+    cores = os.cpu_count() or 1
+    sample = min(size, cores * (48 << 20))
+    vals, ratio, nbytes = [], None, None
+    for i in range(args.warmup + args.steps):
+        r = reference_compress_throughput(1, sample)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libzref.so not built on this box"}))
+            return 0
+        if i >= args.warmup:
+            vals.append(r[0])
+        ratio, nbytes, cores = r[3], r[4], r[1]
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(nbytes / v / 1e6, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{args.size_mib} MiB synthetic mixed corpus, deflate level 1, 128 KiB chunks",
+                       "level": 1, "sample_bytes": nbytes},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": f"compress2 level 1 over {nbytes >> 20} MiB of the mixed corpus, one {nbytes // cores >> 20} MiB slice per host thread"},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ratio": round(ratio, 4), "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zb200", choices=["zb200", "reference"])
+    ap.add_argument("--size-mib", type=int, default=1024)
+    ap.add_argument("--no-extra", action="store_true", help="skip level 6 / inflate / checksum side measurements")
+    ap.add_argument("--no-verify", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from zlib_b200 import load, binding as zb, dist as zdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load()
+    assert lib.dll.zb200_init(local) == 0, lib.last_error()
+    s = torch.cuda.current_stream()
+
+    n = args.size_mib << 20
+    warm = max(3, args.warmup)
+    log(f"[rank {rank}] generating {args.size_mib} MiB mixed corpus")
+    pin_src = lib.dll.zb200_alloc_pinned(n)
+    cap = lib.compress_bound(n) + 64
+    pin_dst = lib.dll.zb200_alloc_pinned(cap)
+    assert pin_src and pin_dst
+    lib.dll.zb200_synth(C.c_void_p(pin_src), n, 1, 1 + rank)
+    host = np.ctypeslib.as_array(C.cast(pin_src, C.POINTER(C.c_uint8)), shape=(n,))
+    d_src = torch.empty(n, dtype=torch.uint8, device=dev)
+    lib.dll.zb200_copy(C.c_void_p(d_src.data_ptr()), C.c_void_p(pin_src), n, None)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device=dev)
+    halo = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    state = {}
+
+    def step_deflate(level):
+        if world == 1:
+            state["clen"] = lib.deflate(d_src.data_ptr(), n, d_dst.data_ptr(), cap, level, zb.WRAP_ZLIB, s)
+        else:   # shard + all-gather of {len, n, crc, adler}; bytes stay where they are (offsets known to all)
+            plan, _, clen, _ = zdist.deflate_sharded(lib, d_src, halo, level, zb.WRAP_ZLIB, out=d_dst, assemble=False, stream=s)
+            state["clen"], state["plan"] = clen, plan
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.kernel_launches()
+        e0.record(s)
+        for _ in range(steps):
+            fn()
+        e1.record(s)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, lib.kernel_launches() - l0
+
+    # ---- headline: deflate level 1, device resident ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms1, launches = timed(lambda: step_deflate(1), args.steps, warm)
+    clocks = sampler.summary()
+    clen1 = state["clen"]
+    value = world * n / ms1 / 1e6
+    log(f"[rank {rank}] deflate L1: {ms1:.2f} ms/step  {value:.2f} GB/s aggregate  ratio {n / clen1:.3f}")
+
+    # ---- per-kernel times (separate pass; events add overhead, so not part of `value`) ----
+    lib.profile(True)
+    step_deflate(1)
+    prof = lib.profile_report()
+    lib.profile(False)
+    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 1))
+    dom_ms = dom[1][0] / max(1, dom[1][1])
+    peaks, peak_kind = measured_peaks()
+    algo_bytes = n + clen1
+    achieved = algo_bytes / dom_ms / 1e6 if dom_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom[0].replace("zb::", ""))
+        except Exception:   # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(achieved / peaks["hbm_gbs"], 5), "traffic": traffic, "peak_source": peak_kind,
+                "algorithmic_bytes": algo_bytes, "kernel_ms": round(dom_ms, 4),
+                "kernel_share_of_step": round(dom_ms / sum(v[0] for v in prof.values()), 4) if prof else None,
+                "kernels_ms": {k.replace("zb::", ""): round(v[0], 4) for k, v in prof.items()}}
+
+    # ---- end to end through compress2 with host buffers (H2D + kernels + D2H inside the timed region) ----
+    def step_e2e():
+        ol = C.c_ulong(cap)
+        rc = lib.dll.compress2(C.c_void_p(pin_dst), C.byref(ol), C.c_void_p(pin_src), n, 1)
+        assert rc == 0, (rc, lib.last_error())
+        state["e2e_len"] = ol.value
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": round(world * n / e2e_s / 1e9, 4), "unit": UNIT, "h2d_bytes_per_step": n,
+           "d2h_bytes_per_step": int(state["e2e_len"]) + 32, "api": "compress2(dest,&destLen,source,sourceLen,1) on pinned host buffers"}
+    log(f"[rank {rank}] e2e compress2: {e2e_s * 1e3:.1f} ms/step {e2e['value']} GB/s")
+
+    extra, verified, cpu = {}, None, None
+    if rank == 0:
+        import zhelpers
+        # ---- correctness gate (a) on the measured output: the reference decodes it bit-exact ----
+        if not args.no_verify and world == 1:
+            comp = np.ctypeslib.as_array(C.cast(pin_dst, C.POINTER(C.c_uint8)), shape=(int(state["e2e_len"]),))
+            t0 = time.perf_counter()
+            if os.path.exists(zhelpers.REF_PATH):
+                ref = zhelpers.Ref()
+                outb = np.empty(n, dtype=np.uint8)
+                ol = C.c_ulong(n)
+                rc = ref.dll.uncompress(C.c_void_p(outb.ctypes.data), C.byref(ol), C.c_void_p(comp.ctypes.data), len(comp))
+                verified = bool(rc == 0 and ol.value == n and np.array_equal(outb, host))
+                who = "reference uncompress (oracle/_ref)"
+            else:
+                orc = zhelpers.Oracle()
+                rc, outb, used = orc.inflate(comp, n)
+                verified = bool(rc == 0 and outb == host.tobytes())
+                who = "oracle port"
+            log(f"[rank 0] output verified by {who}: {verified} ({time.perf_counter() - t0:.1f} s)")
+            assert verified, "reference could not decode the GPU deflate output"
+        # ---- CPU baseline beside it ----
+        cores = os.cpu_count() or 1
+        r = reference_compress_throughput(1, min(n, cores * (48 << 20)))
+        if r is not None:
+            cpu = {"value": round(r[0], 4), "unit": UNIT, "cores": r[1], "kind": "reference",
+                   "sample": f"reference compress2 level 1 over {r[4] >> 20} MiB of the same corpus, one {r[4] // r[1] >> 20} MiB slice per host thread",
+                   "ratio": round(r[3], 4)}
+            log(f"[rank 0] reference compress2 L1 on {r[1]} host threads: {r[0]:.3f} GB/s ratio {r[3]:.3f}")
+
+    if not args.no_extra and world == 1:
+        ms6, _ = timed(lambda: step_deflate(6), max(1, args.steps // 2), 1)
+        extra["deflate_level6"] = {"GBps": round(n / ms6 / 1e6, 3), "ratio": round(n / state["clen"], 4), "ms": round(ms6, 2)}
+        out2 = torch.zeros(2, dtype=torch.int32, device=dev)
+        msc, _ = timed(lambda: lib.checksum_dev(d_src.data_ptr(), n, out2.data_ptr(), s), 10, 3)
+        extra["crc32_adler32_fused"] = {"GBps": round(n / msc / 1e6, 1), "ms": round(msc, 4),
+                                        "frac_of_hbm_peak": round(n / msc / 1e6 / peaks["hbm_gbs"], 4)}
+        # batch inflate: 64 KiB zlib streams of the same corpus, level 6, produced by the reference when available
+        import zhelpers
+        sz, distinct = 65536, 2048
+        ns = n // sz
+        t0 = time.perf_counter()
+        if os.path.exists(zhelpers.REF_PATH):
+            ref = zhelpers.Ref()
+            zs, src_kind = [None] * distinct, "reference compress2 level 6"
+
+            def mk(lo, hi):
+                for i in range(lo, hi):
+                    zs[i] = ref.compress2(host[i * sz:(i + 1) * sz], 6)
+            nt = min(os.cpu_count() or 1, 32)
+            ths = [threading.Thread(target=mk, args=(distinct * t // nt, distinct * (t + 1) // nt)) for t in range(nt)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+        else:
+            import zlib as pyz
+            zs, src_kind = [pyz.compress(host[i * sz:(i + 1) * sz].tobytes(), 6) for i in range(distinct)], "system zlib level 6"
+        zs = (zs * ((ns + distinct - 1) // distinct))[:ns]
+        src_off = np.zeros(ns + 1, dtype=np.int64)
+        src_off[1:] = np.cumsum([len(z) for z in zs])
+        d_z = torch.from_numpy(np.frombuffer(b"".join(zs) + b"\0" * 8, dtype=np.uint8).copy()).to(dev)
+        d_so = torch.from_numpy(src_off).to(dev)
+        d_do = torch.arange(ns + 1, dtype=torch.int64, device=dev) * sz
+        d_len = torch.zeros(ns, dtype=torch.int64, device=dev)
+        d_st = torch.zeros(ns, dtype=torch.int32, device=dev)
+        log(f"[rank 0] prepared {ns} streams ({src_kind}) in {time.perf_counter() - t0:.1f} s")
+        msi, _ = timed(lambda: lib.inflate_batch_dev(d_z.data_ptr(), d_so.data_ptr(), ns, d_src.data_ptr(), d_do.data_ptr(),
+                                                     d_len.data_ptr(), d_st.data_ptr(), zb.WRAP_ZLIB, s), 3, 2)
+        ok = int(d_st.abs().sum()) == 0 and bool((d_len == sz).all())
+        extra["inflate_batch"] = {"GBps": round(ns * sz / msi / 1e6, 3), "streams": ns, "stream_bytes": sz, "ms": round(msi, 2),
+                                  "source": src_kind, "all_ok": ok, "compressed_fraction": round(int(src_off[-1]) / (ns * sz), 4)}
+        log(f"[rank 0] extras: {json.dumps(extra)}")
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": round(ms1, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"{args.size_mib} MiB synthetic mixed corpus per GPU (BASELINE.json configs[1]), deflate level 1, "
+                                       "128 KiB chunks with 32 KiB dictionary priming, one zlib stream",
+                           "level": 1, "chunk": 131072, "bytes_per_gpu": n, "l2": "inputs (1 GiB) exceed the 126 MB L2; no flush needed",
+                           "parallelism": f"chunk-sharded x{world}" if world > 1 else "single GPU"},
+                "ratio": round(n / clen1, 4), "compressed_bytes": int(clen1),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "verified_by_reference": verified, "extra": extra}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -111,6 +111,11 @@ int zb200_inflate_batch_dev(const void *d_src, const uint64_t *d_src_off, size_t
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t zb200_kernel_launches(void);
 
+/* Per-kernel device time: zb200_profile(1) starts bracketing every launch with CUDA events on its
+ * stream, zb200_profile_report() synchronises and writes "kernel=total_ms:launches;..." . */
+void zb200_profile(int enable);
+int  zb200_profile_report(char *out, size_t cap);
+
 /* Synthetic corpora of SURVEY.md section 8(d): kind 0 = text (T), 1 = mixed (M),
  * 2 = xorshift64* noise.  Deterministic in (kind, seed, offset); host memory only.
  * Workload generator for benchmarks and tests, not part of the codec. */

@@ -1,0 +1,95 @@
+"""CPU (gloo, world_size 2 and 3): the multi-GPU host logic -- shard ranges, the all-gather of
+{len, n, crc, adler}, checksum combination, variable-length gather and stream framing.
+The GPU compressor cannot run here, so a test-only stand-in (system zlib with a preset
+dictionary and Z_SYNC_FLUSH) produces the per-rank shards; the assembled stream is then decoded
+by the CPU oracle."""
+import os
+import socket
+import sys
+import zlib
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _standin_compress(data, halo, last, out):
+    raw = bytes(data.numpy())
+    zd = bytes(halo.numpy()) if halo is not None and halo.numel() else None
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY, zd) if zd else zlib.compressobj(6, zlib.DEFLATED, -15)
+    z = co.compress(raw) + (co.flush(zlib.Z_FINISH) if last else co.flush(zlib.Z_SYNC_FLUSH))
+    out[:len(z)] = torch.frombuffer(bytearray(z), dtype=torch.uint8)
+    return len(z), zlib.crc32(raw), zlib.adler32(raw)
+
+
+def _worker(rank, world, port, n, wrap, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import zhelpers
+        from zlib_b200 import dist as zd, load, binding as zb
+        lib = load()
+        data = zhelpers.corpus(1, n, 5)
+        ranges = zd.shard_ranges(n, world)
+        a, b = ranges[rank]
+        mine = torch.frombuffer(bytearray(data[a:b]), dtype=torch.uint8) if b > a else torch.empty(0, dtype=torch.uint8)
+        halo = torch.frombuffer(bytearray(data[max(0, a - zd.WINDOW):a]), dtype=torch.uint8) if a > 0 else None
+        plan, out, clen, full = zd.deflate_sharded(lib, mine, halo, 6, wrap, compress_fn=_standin_compress)
+        assert plan.n_in == n
+        assert plan.adler32 == zlib.adler32(data) and plan.crc32 == zlib.crc32(data)
+        if rank == 0:
+            orc = zhelpers.Oracle()
+            z = bytes(full.numpy())
+            assert len(z) == plan.total
+            rc, dec, used = orc.inflate(z, n, wrap)
+            assert rc == 0 and dec == data and used == len(z), (rc, used, len(z))
+        else:
+            assert full is None
+        q.put((rank, "ok"))
+    except Exception as e:          # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,wrap", [(2, 1_000_003, 1), (3, 131072 * 2 + 5, 2), (2, 100, 1)])
+def test_sharded_stream_assembly(world, n, wrap):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, n, wrap, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert all(m == "ok" for _, m in res), res
+
+
+def test_shard_ranges_and_adler_join():
+    from zlib_b200 import dist as zd
+    for n in (0, 1, 131072, 131073, 10 * 131072 + 7):
+        for w in (1, 2, 3, 8):
+            r = zd.shard_ranges(n, w)
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert all(a % 131072 == 0 for a, _ in r if a < n)
+    import random
+    rng = random.Random(1)
+    for _ in range(200):
+        x, y = rng.randbytes(rng.randint(0, 70000)), rng.randbytes(rng.randint(0, 70000))
+        assert zd.adler_join(zlib.adler32(x), zlib.adler32(y), len(y)) == zlib.adler32(x + y)

@@ -115,6 +115,7 @@ class Lib:
             "zb200_inflate_batch": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
             "zb200_inflate_batch_dev": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
             "zb200_kernel_launches": (C.c_uint64, []),
+            "zb200_profile": (None, [C.c_int]), "zb200_profile_report": (C.c_int, [C.c_char_p, sz]),
             "zb200_synth": (None, [vp, sz, C.c_int, C.c_uint64]),
         }
         self.missing = []
@@ -315,6 +316,21 @@ class Lib:
         a = np.empty(n, dtype=np.uint8)
         self.dll.zb200_synth(C.c_void_p(a.ctypes.data), n, kind, seed)
         return a
+
+    def profile(self, enable: bool) -> None:
+        self.dll.zb200_profile(1 if enable else 0)
+
+    def profile_report(self):
+        """{kernel: (total_ms, launches)} since profile(True)."""
+        buf = C.create_string_buffer(8192)
+        self.dll.zb200_profile_report(buf, 8192)
+        out = {}
+        for item in buf.value.decode().split(";"):
+            if "=" in item:
+                k, v = item.split("=")
+                ms, cnt = v.split(":")
+                out[k] = (float(ms), int(cnt))
+        return out
 
     def kernel_launches(self) -> int:
         return self.dll.zb200_kernel_launches()

@@ -68,9 +68,16 @@ const uint8_t* to_device(Ctx* c, const void* src, size_t len, cudaStream_t s, in
         }                                                                               \
     } while (0)
 
+// Per-kernel timing for bench.py's roofline line: when enabled, every launch is bracketed by CUDA
+// events on the launching stream (zb200_profile / zb200_profile_report in zb_runtime.cu).
+extern bool g_profile;
+void profile_mark(const char* name, cudaStream_t s, bool begin);
+
 #define ZB_LAUNCH(kernel, grid, block, smem, stream, ...)                               \
     do {                                                                                \
+        if (zb::g_profile) zb::profile_mark(#kernel, (stream), true);                   \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                     \
+        if (zb::g_profile) zb::profile_mark(#kernel, (stream), false);                  \
         zb::g_launches.fetch_add(1, std::memory_order_relaxed);                         \
     } while (0)
 

@@ -4,6 +4,9 @@
 #include "zb_common.cuh"
 
 #include <mutex>
+#include <vector>
+#include <string>
+#include <map>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -11,6 +14,23 @@
 namespace zb {
 
 std::atomic<uint64_t> g_launches{0};
+bool g_profile = false;
+
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+void profile_mark(const char* name, cudaStream_t s, bool begin)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (begin) {
+        ProfRec r{name, nullptr, nullptr};
+        cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, s);
+        g_prof.push_back(r);
+    } else if (!g_prof.empty()) {
+        cudaEventRecord(g_prof.back().e1, s);
+    }
+}
 
 static thread_local char t_err[512];
 void set_error(const char* fmt, ...)
@@ -210,3 +230,34 @@ ZB_API int zb200_sync(void* stream)
 }
 
 ZB_API uint64_t zb200_kernel_launches(void) { return g_launches.load(); }
+
+ZB_API void zb200_profile(int enable)
+{
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+    g_profile = enable != 0;
+}
+
+// "kernel=total_ms:launches;..." for everything launched since zb200_profile(1); synchronises the device.
+ZB_API int zb200_profile_report(char* out, size_t cap)
+{
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<std::string> order;
+    for (auto& r : g_prof) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (!acc.count(r.name)) order.push_back(r.name);
+        acc[r.name].first += ms; acc[r.name].second += 1;
+    }
+    std::string s;
+    for (auto& k : order) {
+        char b[160];
+        snprintf(b, sizeof(b), "%s=%.6f:%d;", k.c_str(), acc[k].first, acc[k].second);
+        s += b;
+    }
+    if (cap) { snprintf(out, cap, "%s", s.c_str()); }
+    return (int)s.size();
+}

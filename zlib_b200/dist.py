@@ -1,0 +1,145 @@
+"""Multi-GPU assembly of one DEFLATE stream (one process per GPU, torch.distributed).
+
+The path shards by input chunk: rank r compresses a contiguous,
+chunk-aligned range of the input with the 32 KiB in front of it as dictionary and ends
+on a byte boundary, so the shards concatenate.  The only exchange is
+  1. an all-gather of four integers per rank {compressed bytes, input bytes, crc32, adler32};
+  2. (optional) the variable-length gather of the compressed shards to the root rank,
+     which also writes the 2-byte header and the combined-checksum trailer.
+No codec arithmetic happens here; the compressor is `Lib.deflate_shard` (injectable so the
+host-side logic can be exercised on CPU with gloo, where no GPU kernel can run).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+from . import binding as zb
+
+CHUNK = 131072
+WINDOW = 32768
+ADLER_BASE = 65521
+
+
+def shard_ranges(n: int, world: int, chunk: int = CHUNK) -> List[Tuple[int, int]]:
+    """Contiguous chunk-aligned [begin, end) per rank, sizes differing by at most one chunk."""
+    nchunks = (n + chunk - 1) // chunk
+    out, c0 = [], 0
+    for r in range(world):
+        c1 = c0 + nchunks // world + (1 if r < nchunks % world else 0)
+        out.append((min(n, c0 * chunk), min(n, c1 * chunk)))
+        c0 = c1
+    return out
+
+
+def adler_join(a1: int, a2: int, len2: int) -> int:
+    """Exact Adler-32 of A||B (the reference's adler32_combine keeps non-canonical 65521 folds)."""
+    rem = len2 % ADLER_BASE
+    s1, s2, t1, t2 = a1 & 0xFFFF, (a1 >> 16) & 0xFFFF, a2 & 0xFFFF, (a2 >> 16) & 0xFFFF
+    return ((s1 + t1 + ADLER_BASE - 1) % ADLER_BASE) | (((s2 + t2 + rem * s1 + ADLER_BASE - rem) % ADLER_BASE) << 16)
+
+
+@dataclass
+class StreamPlan:
+    offsets: List[int]          # byte offset of every rank's shard inside the final stream
+    total: int                  # length of the final stream
+    n_in: int                   # total uncompressed bytes
+    crc32: int
+    adler32: int
+    header: bytes
+    trailer: bytes
+
+
+def zlib_header(level: int) -> bytes:
+    fl = 0 if level < 2 else 1 if level < 6 else 2 if level == 6 else 3     # deflate.c:625-649
+    h = (0x78 << 8) | (fl << 6)
+    h += 31 - h % 31
+    return bytes([h >> 8, h & 0xFF])
+
+
+def plan_stream(metas: Sequence[Sequence[int]], level: int, wrap: int, crc_combine: Callable[[int, int, int], int]) -> StreamPlan:
+    """metas[r] = (compressed bytes, input bytes, crc32, adler32) in rank order."""
+    header = zlib_header(level) if wrap == zb.WRAP_ZLIB else (
+        bytes([31, 139, 8, 0, 0, 0, 0, 0, 2 if level == 9 else 4 if level < 2 else 0, 3]) if wrap == zb.WRAP_GZIP else b"")
+    offsets, pos, crc, adl, n_in = [], len(header), 0, 1, 0
+    for clen, n, c, a in metas:
+        offsets.append(pos)
+        pos += clen
+        crc = crc_combine(crc, c, n) if n else crc
+        adl = adler_join(adl, a, n)
+        n_in += n
+    if wrap == zb.WRAP_ZLIB:
+        trailer = adl.to_bytes(4, "big")
+    elif wrap == zb.WRAP_GZIP:
+        trailer = crc.to_bytes(4, "little") + (n_in & 0xFFFFFFFF).to_bytes(4, "little")
+    else:
+        trailer = b""
+    return StreamPlan(offsets, pos + len(trailer), n_in, crc, adl, header, trailer)
+
+
+def exchange_meta(local: Sequence[int], device, group=None) -> List[List[int]]:
+    """All-gather of the four per-rank integers (the path's one small collective)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.tensor(list(local), dtype=torch.int64, device=device)
+    out = torch.empty(world * 4, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.view(world, 4).cpu().tolist()
+
+
+def gather_stream(local_bytes, local_len: int, plan: StreamPlan, root: int = 0, group=None):
+    """Variable-length gather of the shards into one buffer on `root` (uint8 tensor) incl. header/trailer."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if rank != root:
+        if local_len:
+            dist.send(local_bytes[:local_len], dst=root, group=group)
+        return None
+    out = torch.empty(plan.total, dtype=torch.uint8, device=local_bytes.device)
+    if plan.header:
+        out[:len(plan.header)] = torch.tensor(list(plan.header), dtype=torch.uint8, device=out.device)
+    if plan.trailer:
+        out[plan.total - len(plan.trailer):] = torch.tensor(list(plan.trailer), dtype=torch.uint8, device=out.device)
+    ends = plan.offsets[1:] + [plan.total - len(plan.trailer)]
+    for r in range(world):
+        a, b = plan.offsets[r], ends[r]
+        if r == root:
+            out[a:b] = local_bytes[:b - a]
+        elif b > a:
+            dist.recv(out[a:b], src=r, group=group)
+    return out
+
+
+def deflate_sharded(lib, data, halo, level: int = 6, wrap: int = zb.WRAP_ZLIB, group=None, out=None,
+                    assemble: bool = True, root: int = 0, compress_fn: Optional[Callable] = None, stream=None):
+    """Rank-local part of a multi-GPU deflate.
+
+    data : this rank's contiguous slice of the input (uint8 tensor on this rank's device)
+    halo : up to 32 KiB that precede it (uint8 tensor, same device) or None for rank 0
+    Returns (plan, local_compressed_tensor, local_len, assembled_or_None).
+    """
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = data.numel()
+    last = rank == world - 1
+    cap = n + (n >> 12) + (n >> 14) + 64
+    if out is None:
+        out = torch.empty(cap, dtype=torch.uint8, device=data.device)
+    if compress_fn is None:
+        flags = zb.ZB200_DEFLATE_NO_HEADER | zb.ZB200_DEFLATE_NO_TRAILER | (0 if last else zb.ZB200_DEFLATE_NOT_LAST)
+        if halo is not None and halo.numel():
+            joined = torch.cat([halo, data])                       # contiguous [dict][src] on the device
+            dptr, sptr, dlen = joined.data_ptr(), joined.data_ptr() + halo.numel(), halo.numel()
+        else:
+            joined, dptr, sptr, dlen = data, 0, data.data_ptr(), 0
+        clen, crc, adl = lib.deflate_shard(sptr, n, dptr if dlen else None, dlen, out.data_ptr(), out.numel(), level,
+                                           zb.WRAP_RAW, flags, stream)
+    else:
+        clen, crc, adl = compress_fn(data, halo, last, out)
+    metas = exchange_meta((clen, n, crc, adl), data.device, group)
+    plan = plan_stream(metas, level, wrap, lib.crc32_combine)
+    assembled = gather_stream(out, clen, plan, root, group) if assemble else None
+    return plan, out, clen, assembled
