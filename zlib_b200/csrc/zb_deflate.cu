@@ -66,14 +66,26 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
     const uint32_t* words = reinterpret_cast<const uint32_t*>(buf - mis);
     const uint64_t nwords = (mis + total + 3) >> 2;
 
-    // q = p + mis indexes bytes from the aligned base; tiles of 128 bytes, one word per lane
+    // q = p + mis indexes bytes from the aligned base; tiles of 128 bytes, one word per lane.
+    // Only the head[] read -> write chain is serial; loads are issued two tiles ahead and the hashes
+    // and intra-step groups of a whole tile are computed before that chain starts.
     const uint64_t tile_beg = (prime_beg + mis) >> 7, tile_end = (seg_end + mis + 127) >> 7;
-    uint64_t wi = tile_beg * 32 + lane;
-    uint32_t cur = wi < nwords ? __ldg(words + wi) : 0u;
+    const uint64_t q_lo = prime_beg + mis;                      // first position to insert
+    const uint64_t q_hi = min(seg_end, total >= 2 ? total - 2 : 0) + mis;   // one past the last hashable position
+    const uint64_t q_seg = seg_beg + mis, q_end = seg_end + mis;            // positions whose link is stored
+    auto ldw = [&](uint64_t t) { const uint64_t w = t * 32 + lane; return w < nwords ? __ldg(words + w) : 0u; };
+    uint32_t cur = ldw(tile_beg), nxt = ldw(tile_beg + 1);
     for (uint64_t tile = tile_beg; tile < tile_end; ++tile) {
-        const uint64_t wn = (tile + 1) * 32 + lane;
-        const uint32_t nxt = wn < nwords ? __ldg(words + wn) : 0u;
+        const uint32_t nxt2 = ldw(tile + 2);
         const uint32_t nxt0 = __shfl_sync(kFullMask, nxt, 0);
+        const uint64_t qbase = tile * 128;
+        // tile-relative bounds (clamped to [0,128])
+        const int lo = (int)(q_lo > qbase ? min((uint64_t)128, q_lo - qbase) : 0);
+        const int hi = (int)(q_hi > qbase ? min((uint64_t)128, q_hi - qbase) : 0);
+        const int slo = (int)(q_seg > qbase ? min((uint64_t)128, q_seg - qbase) : 0);
+        const int shi = (int)(q_end > qbase ? min((uint64_t)128, q_end - qbase) : 0);
+        uint32_t h[4], d[4];
+        bool valid[4], leader[4], from_head[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int li = 32 * k + lane, j = li >> 2;
@@ -81,29 +93,33 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
             uint32_t wb = __shfl_sync(kFullMask, cur, (j + 1) & 31);
             if (j == 31) wb = nxt0;
             const uint32_t v = __funnelshift_r(wa, wb, (li & 3) * 8);
-            const uint64_t q = tile * 128 + li;
-            const bool valid = q >= prime_beg + mis && q + 2 < total + mis && q < seg_end + mis;
-            const uint64_t p = q - mis;
-            const uint32_t h = valid ? hash3(v) : (0x10000u + lane);
-            const uint32_t grp = __match_any_sync(kFullMask, h);
-            uint32_t d = 0;
-            if (valid) {
-                const uint32_t lower = grp & lt;
-                if (lower) {
-                    d = lane - (31 - __clz(lower));
-                } else {
-                    d = ((uint32_t)q - s_head[h]) & 0xffffu;
-                    if (d == 0) d = 0x10000u;
-                    if (d > kWindow || d > p) d = 0;
-                }
+            valid[k] = li >= lo && li < hi;
+            h[k] = valid[k] ? hash3(v) : (0x10000u + lane);
+            const uint32_t grp = __match_any_sync(kFullMask, h[k]);
+            const uint32_t lower = grp & lt;
+            leader[k] = valid[k] && (grp >> lane) == 1u;         // highest lane of its group writes head[]
+            from_head[k] = valid[k] && lower == 0;
+            d[k] = (valid[k] && lower) ? (uint32_t)(lane - (31 - __clz(lower))) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t q32 = (uint32_t)qbase + 32 * k + lane;
+            if (from_head[k]) {
+                uint32_t dd = (q32 - s_head[h[k]]) & 0xffffu;
+                if (dd == 0) dd = 0x10000u;
+                const uint64_t p = qbase + 32 * k + lane - mis;
+                d[k] = (dd > kWindow || dd > p) ? 0u : dd;
             }
             __syncwarp();
-            if (valid && (grp >> lane) == 1u) s_head[h] = (uint16_t)q;   // highest lane of its group
+            if (leader[k]) s_head[h[k]] = (uint16_t)q32;
             __syncwarp();
-            if (valid && p >= seg_beg) dist16[p] = (uint16_t)d;
-            else if (q >= seg_beg + mis && q < seg_end + mis) dist16[p] = 0;   // the last two bytes of the input
         }
-        cur = nxt;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int li = 32 * k + lane;
+            if (li >= slo && li < shi) dist16[qbase + li - mis] = (uint16_t)d[k];
+        }
+        cur = nxt; nxt = nxt2;
     }
 }
 
