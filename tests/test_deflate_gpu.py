@@ -74,6 +74,57 @@ def test_ratio_gate_vs_reference(gpu_lib, oracle, kind):
         assert rc == 0 and out == data.tobytes()
 
 
+def test_huffman_length_limit(gpu_lib, oracle):
+    """Fibonacci-weighted symbols push the optimal code past 15 bits and the code-length code past 7:
+    the overflow repair of trees.c:527-545 must still give complete codes."""
+    fib = [1, 1]
+    while len(fib) < 25:
+        fib.append(fib[-1] + fib[-2])
+    buf = bytearray(b"".join(bytes([40 + i]) * f for i, f in enumerate(fib)))
+    random.Random(5).shuffle(buf)
+    data = bytes(buf)
+    for level in (1, 6, 9):
+        rc, z = gpu_lib.compress2(data, level)
+        assert rc == 0
+        _decode_everywhere(z, data, oracle)
+    # many distinct code lengths in one header stress the 7-bit limit of the code-length code
+    rng = random.Random(9)
+    for t in range(6):
+        weights = [rng.choice([1, 2, 3, 5, 8, 13, 40, 100, 400, 3000]) for _ in range(256)]
+        data = bytes(rng.choices(range(256), weights=weights, k=150000))
+        for level in (1, 6):
+            rc, z = gpu_lib.compress2(data, level)
+            assert rc == 0
+            _decode_everywhere(z, data, oracle)
+
+
+def test_multi_slab_host_pipeline(gpu_lib, oracle):
+    """Inputs longer than one pipeline slab (888 chunks) take the overlapped copy/compute path and must still
+    be one valid stream, from host memory and from device memory alike."""
+    import ctypes as C
+    n = (888 * 131072) * 2 + 777777
+    data = gpu_lib.synth(n, kind=1, seed=21)
+    rc, z = gpu_lib.compress2(data, 1)
+    assert rc == 0
+    assert zlib.decompress(z) == data.tobytes()
+    assert z[-4:] == oracle.adler32(data).to_bytes(4, "big")
+    rc, z2 = gpu_lib.compress2(data, 1, cap=len(z) - 1)
+    assert rc == zb.Z_BUF_ERROR
+    d_src = gpu_lib.dll.zb200_alloc_device(n)
+    cap = gpu_lib.compress_bound(n)
+    d_dst = gpu_lib.dll.zb200_alloc_device(cap)
+    assert d_src and d_dst
+    try:
+        assert gpu_lib.dll.zb200_copy(d_src, data.ctypes.data, n, None) == 0
+        m = gpu_lib.deflate(d_src, n, d_dst, cap, 1, zb.WRAP_ZLIB)
+        out = C.create_string_buffer(m)
+        assert gpu_lib.dll.zb200_copy(out, d_dst, m, None) == 0
+        assert out.raw == z                                      # same bytes whichever memory the buffers live in
+    finally:
+        gpu_lib.dll.zb200_free_device(d_src)
+        gpu_lib.dll.zb200_free_device(d_dst)
+
+
 def test_buf_error_and_bad_level(gpu_lib):
     data = zhelpers.corpus(1, 50000, 1)
     rc, _ = gpu_lib.compress2(data, 6, cap=100)

@@ -43,6 +43,9 @@ struct Ctx {
     DevBuf small;                          // few-KB result words
     void* pinned = nullptr; size_t pinned_cap = 0;
     int ensure_pinned(size_t bytes);
+    cudaStream_t aux[2] = {nullptr, nullptr};   // copy-in / copy-out streams of the slab pipeline
+    cudaEvent_t* evs = nullptr; int nev = 0;
+    int ensure_aux(int nevents);               // both streams and at least `nevents` events
     Ctx* next = nullptr;
 };
 

@@ -5,35 +5,39 @@
 // gen_codes/send_all_trees/compress_block/send_bits (qcsrc/trees.c:1022,921,619,490,577,838,1072,217).
 //
 // The reference interleaves these per input byte inside one sequential loop.  Here the same
-// decisions are taken in five passes over HBM-resident arrays, each with its own parallel axis:
+// decisions are taken in passes over HBM-resident arrays, each with its own parallel axis:
 //
-//   K1a link   one warp per 128 KiB segment walks it in order with a 15-bit hash -> last position
-//              table in shared memory (the reference's head[]), 32 positions per step, and writes for
-//              every position the distance to the previous position with the same 3-byte hash (the
-//              reference's prev[] chain, stored as deltas so chains cross chunk boundaries and the
-//              32 KiB of history in front of a chunk needs no copy -- it is simply there).
+//   K1a link   one CTA (8 warps) per 128 KiB segment shares a 15-bit hash -> last position table in
+//              shared memory (the reference's head[]).  The warps take 128-position tiles round robin; only
+//              the table accesses of a tile are serial and the turn is handed from warp to warp with named
+//              barriers.  Output: for every position the distance to the previous position with the same
+//              3-byte hash (the reference's prev[] chain, stored as deltas so chains cross chunk boundaries
+//              and the 32 KiB of history in front of a chunk needs no copy -- it is simply there).
 //   K1b match  one thread per input position follows that chain up to max_chain candidates
 //              (configuration_table, deflate.c:137-149) and keeps the longest match, with the
 //              reference's quick reject on the byte that would extend the best match so far.
-//   K1c parse  one warp per chunk turns per-position matches into the token stream: greedy
-//              (deflate_fast) or lazy with max_lazy and TOO_FAR (deflate_slow, deflate.c:1601-1612);
-//              the serial "next position" recurrence is resolved 32 positions at a time with shuffles.
-//              Tokens are tallied into per-block histograms (shared-memory atomics), blocks close every
-//              16 Ki symbols like the reference's lit_bufsize.
-//   K2 codes   one warp per block builds the three length-limited canonical codes exactly as trees.c
-//              does (same heap order, same tie-break, same overflow repair -- unit-tested against the
-//              oracle), prices stored / fixed / dynamic with the reference's rule (trees.c:955-1001) and
-//              serialises the dynamic header.
+//   K1c parse  one warp per 16 KiB unit turns per-position matches into tokens: greedy (deflate_fast) or
+//              lazy with max_lazy and TOO_FAR (deflate_slow, deflate.c:1601-1612); the serial "next
+//              position" recurrence is resolved 32 positions at a time by jump doubling.  Tokens are
+//              tallied into per-unit histograms (shared-memory atomics).
+//   K2 codes   one warp per block (4 units, 64 KiB of input) builds the three length-limited canonical
+//              codes (sort + two-queue merge, the reference's overflow repair), prices stored / fixed /
+//              dynamic with the reference's rule (trees.c:955-1001) and serialises the dynamic header.
 //   plan+scan  exact compressed size of every chunk -> exclusive prefix sum -> byte offsets.
 //   K3 pack    one CTA per chunk: per-symbol (code, length) -> prefix sum of lengths -> bits OR-ed into a
 //              shared-memory staging window -> bytes to their final place.  Chunks end byte-aligned (empty
 //              stored block, i.e. what Z_SYNC_FLUSH emits, deflate.c:808-819), so shards from several
 //              GPUs concatenate by byte copy.
 //
+// A call is cut into slabs of kSlabChunks chunks that run back to back on one stream and share one set of
+// scratch buffers; with host buffers the H2D copy of slab i+1 and the D2H copy of slab i-1 overlap the
+// kernels of slab i (separate copy streams).
+//
 // Output is a valid DEFLATE stream, not the reference's bytes: parity is "reference inflate decodes
 // it bit-exact" plus a size bound (<= 1.02 x reference at the same level), see tests/.
 #include "zb_deflate.cuh"
 #include "zb200_internal.h"
+#include <stdlib.h>
 
 namespace zb {
 
@@ -50,77 +54,136 @@ constexpr int kHashBits = 15;
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t hash3(uint32_t v) { return ((v & 0xffffffu) * 0x9E3779B1u) >> (32 - kHashBits); }
 
-__global__ void __launch_bounds__(32)
+// Ring version: kLinkWarps warps share one segment and one head[] table.  Warp w owns tiles
+// w, w+W, w+2W, ... (a tile = 128 consecutive positions).  Everything that does not touch head[]
+// -- loads, hashes, the intra-step same-hash groups, the dist16 stores -- runs concurrently in all
+// warps; only the short "read head[], then write head[]" section of a tile is serial, and it is
+// passed from warp to warp in position order with named barriers (producer bar.arrive, consumer
+// bar.sync, 64 threads each).  The links are exactly those of the one-warp version.
+constexpr int kLinkWarps = 8;
+
+__device__ __forceinline__ void ring_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void ring_pass(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+// One warp's turn: wait for the token, then for each of the tile's four 32-position steps read head[] (every lane, the
+// caller ignores what it does not need) and let the step's group leaders write their position; pass the token on.
+// Shared-memory accesses of one warp execute in program order, which is all the steps need from each other.
+__device__ __noinline__ uint2 ring_turn(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t q, uint32_t wmask,
+                                        int bar_in, int bar_out)
+{
+    uint32_t lo, hi;
+    asm volatile(
+        "{\n"
+        ".reg .pred w0, w1, w2, w3;\n"
+        ".reg .b16 t0, t1, t2, t3, s0, s1, s2, s3;\n"
+        ".reg .b32 x;\n"
+        "and.b32 x, %8, 1; setp.ne.u32 w0, x, 0;\n"
+        "and.b32 x, %8, 2; setp.ne.u32 w1, x, 0;\n"
+        "and.b32 x, %8, 4; setp.ne.u32 w2, x, 0;\n"
+        "and.b32 x, %8, 8; setp.ne.u32 w3, x, 0;\n"
+        "cvt.u16.u32 s0, %6; add.u32 x, %6, 32; cvt.u16.u32 s1, x; add.u32 x, %6, 64; cvt.u16.u32 s2, x; add.u32 x, %6, 96; cvt.u16.u32 s3, x;\n"
+        "bar.sync %9, 64;\n"
+        "ld.shared.u16 t0, [%2];\n"
+        "@w0 st.shared.u16 [%2], s0;\n"
+        "ld.shared.u16 t1, [%3];\n"
+        "@w1 st.shared.u16 [%3], s1;\n"
+        "ld.shared.u16 t2, [%4];\n"
+        "@w2 st.shared.u16 [%4], s2;\n"
+        "ld.shared.u16 t3, [%5];\n"
+        "@w3 st.shared.u16 [%5], s3;\n"
+        "bar.arrive %7, 64;\n"
+        "mov.b32 %0, {t0, t1}; mov.b32 %1, {t2, t3};\n"
+        "}\n"
+        : "=r"(lo), "=r"(hi)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(q), "r"(bar_out), "r"(wmask), "r"(bar_in)
+        : "memory");
+    return make_uint2(lo, hi);
+}
+
+template <bool kExact>
+__global__ void __launch_bounds__(kLinkWarps * 32)
 k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict__ dist16)
 {
     extern __shared__ uint16_t s_head[];                       // 2^15 entries: low 16 bits of the last position
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    for (int i = lane; i < (1 << kHashBits) / 2; i += 32) reinterpret_cast<uint32_t*>(s_head)[i] = 0;
-    __syncwarp();
+    for (int i = threadIdx.x; i < (1 << kHashBits) / 2; i += kLinkWarps * 32) reinterpret_cast<uint32_t*>(s_head)[i] = 0;
+    __syncthreads();
 
     const uint64_t seg_beg = (uint64_t)blockIdx.x * kChunk;
     const uint64_t seg_end = min(total, seg_beg + kChunk);
     const uint64_t prime_beg = seg_beg > kWindow ? seg_beg - kWindow : 0;
     const uint32_t mis = (uint32_t)((uintptr_t)buf & 3);
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(buf - mis);
-    const uint64_t nwords = (mis + total + 3) >> 2;
-
-    // q = p + mis indexes bytes from the aligned base; tiles of 128 bytes, one word per lane.
-    // Only the head[] read -> write chain is serial; loads are issued two tiles ahead and the hashes
-    // and intra-step groups of a whole tile are computed before that chain starts.
+    // q = p + mis indexes bytes from the 4-byte aligned base; a tile is 128 consecutive q.  Everything below is
+    // relative to the first tile of this segment, so it fits 32 bits (a segment spans <= 160 KiB + 128).
     const uint64_t tile_beg = (prime_beg + mis) >> 7, tile_end = (seg_end + mis + 127) >> 7;
-    const uint64_t q_lo = prime_beg + mis;                      // first position to insert
-    const uint64_t q_hi = min(seg_end, total >= 2 ? total - 2 : 0) + mis;   // one past the last hashable position
-    const uint64_t q_seg = seg_beg + mis, q_end = seg_end + mis;            // positions whose link is stored
-    auto ldw = [&](uint64_t t) { const uint64_t w = t * 32 + lane; return w < nwords ? __ldg(words + w) : 0u; };
-    uint32_t cur = ldw(tile_beg), nxt = ldw(tile_beg + 1);
-    for (uint64_t tile = tile_beg; tile < tile_end; ++tile) {
-        const uint32_t nxt2 = ldw(tile + 2);
-        const uint32_t nxt0 = __shfl_sync(kFullMask, nxt, 0);
-        const uint64_t qbase = tile * 128;
-        // tile-relative bounds (clamped to [0,128])
-        const int lo = (int)(q_lo > qbase ? min((uint64_t)128, q_lo - qbase) : 0);
-        const int hi = (int)(q_hi > qbase ? min((uint64_t)128, q_hi - qbase) : 0);
-        const int slo = (int)(q_seg > qbase ? min((uint64_t)128, q_seg - qbase) : 0);
-        const int shi = (int)(q_end > qbase ? min((uint64_t)128, q_end - qbase) : 0);
-        uint32_t h[4], d[4];
-        bool valid[4], leader[4], from_head[4];
+    const uint64_t q0 = tile_beg * 128;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(buf - mis) + tile_beg * 32;
+    const uint32_t nwords = (uint32_t)min((uint64_t)0x7fffffffu, ((mis + total + 3) >> 2) - tile_beg * 32);
+    uint16_t* dout = dist16 + q0 - mis;                         // dout[q - q0] = link of position q - mis (never dereferenced below q_seg)
+    const int q_lo = (int)(prime_beg + mis - q0);               // first position to insert
+    const int q_hi = (int)(min(seg_end, total >= 2 ? total - 2 : 0) + mis - q0);   // one past the last hashable position
+    const int q_seg = (int)(seg_beg + mis - q0), q_end = (int)(seg_end + mis - q0);   // positions whose link is stored
+    const int p_cap = (int)min((uint64_t)0x40000000u, q0 - mis + 128) - 128;   // global position of q0, saturated (only "dd > p" uses it)
+    const uint32_t ntiles = (uint32_t)(tile_end - tile_beg);
+    const uint32_t iters = (ntiles + kLinkWarps - 1) / kLinkWarps;
+    const uint32_t head_base = (uint32_t)__cvta_generic_to_shared(s_head);
+    const int bar_in = 1 + warp, bar_out = 1 + (warp + 1) % kLinkWarps;
+    auto ldw = [&](uint32_t t) { const uint32_t w = t * 32 + lane; return w < nwords ? __ldg(words + w) : 0u; };
+    auto ldx = [&](uint32_t t) { const uint32_t w = (t + 1) * 32; return w < nwords ? __ldg(words + w) : 0u; };
+
+    if (warp == kLinkWarps - 1) ring_pass(bar_out);            // lets warp 0 take the first turn
+    uint32_t tile = warp;
+    uint32_t cur = ldw(tile), ext = ldx(tile);
+    for (uint32_t it = 0; it < iters; ++it, tile += kLinkWarps) {
+        const uint32_t cur_n = ldw(tile + kLinkWarps), ext_n = ldx(tile + kLinkWarps);
+        const int qb = (int)(tile * 128);
+        const int lo = min(max(q_lo - qb, 0), 128), hi = min(max(q_hi - qb, 0), 128);
+        uint32_t h[4], d[4], hv[4], ha[4], rd[4], wr[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int li = 32 * k + lane, j = li >> 2;
             const uint32_t wa = __shfl_sync(kFullMask, cur, j);
             uint32_t wb = __shfl_sync(kFullMask, cur, (j + 1) & 31);
-            if (j == 31) wb = nxt0;
+            if (j == 31) wb = ext;
             const uint32_t v = __funnelshift_r(wa, wb, (li & 3) * 8);
-            valid[k] = li >= lo && li < hi;
-            h[k] = valid[k] ? hash3(v) : (0x10000u + lane);
-            const uint32_t grp = __match_any_sync(kFullMask, h[k]);
-            const uint32_t lower = grp & lt;
-            leader[k] = valid[k] && (grp >> lane) == 1u;         // highest lane of its group writes head[]
-            from_head[k] = valid[k] && lower == 0;
-            d[k] = (valid[k] && lower) ? (uint32_t)(lane - (31 - __clz(lower))) : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t q32 = (uint32_t)qbase + 32 * k + lane;
-            if (from_head[k]) {
-                uint32_t dd = (q32 - s_head[h[k]]) & 0xffffu;
-                if (dd == 0) dd = 0x10000u;
-                const uint64_t p = qbase + 32 * k + lane - mis;
-                d[k] = (dd > kWindow || dd > p) ? 0u : dd;
+            const bool valid = li >= lo && li < hi;
+            h[k] = valid ? hash3(v) : (0x10000u + lane);
+            if (kExact) {
+                const uint32_t grp = __match_any_sync(kFullMask, h[k]);
+                const uint32_t lower = grp & lt;
+                wr[k] = (valid && (grp >> lane) == 1u) ? 1u : 0u;    // highest lane of its group writes head[]
+                rd[k] = (valid && lower == 0) ? 1u : 0u;             // lowest lane of its group reads head[]
+                d[k] = (valid && lower) ? (uint32_t)(lane - (31 - __clz(lower))) : 0u;
+            } else {
+                // Relaxed: positions of one 32-wide step that share a hash all link to the entry from before the
+                // step (a valid, merely older, chain member) and the table keeps whichever of them the hardware
+                // writes last.  No cross-lane grouping (MATCH.ANY saturates the ADU pipe), ~0.1 % larger output.
+                wr[k] = rd[k] = valid ? 1u : 0u;
+                d[k] = 0;
             }
-            __syncwarp();
-            if (leader[k]) s_head[h[k]] = (uint16_t)q32;
-            __syncwarp();
+            ha[k] = head_base + (h[k] & 0x7fffu) * 2;
         }
+        // ---- serial section: this warp's turn on head[] (a real call, so that the compiler cannot schedule
+        // unrelated work between the two barriers) ----
+        const uint32_t wmask = wr[0] | (wr[1] << 1) | (wr[2] << 2) | (wr[3] << 3);
+        const uint2 got = ring_turn(ha[0], ha[1], ha[2], ha[3], (uint32_t)qb + lane, wmask, bar_in, bar_out);
+        hv[0] = got.x & 0xffffu; hv[1] = got.x >> 16; hv[2] = got.y & 0xffffu; hv[3] = got.y >> 16;
+        // ---- links out ----
+        const int slo = min(max(q_seg - qb, 0), 128), shi = min(max(q_end - qb, 0), 128);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int li = 32 * k + lane;
-            if (li >= slo && li < shi) dist16[qbase + li - mis] = (uint16_t)d[k];
+            if (rd[k]) {
+                uint32_t dd = ((uint32_t)(qb + li) - hv[k]) & 0xffffu;
+                if (dd == 0) dd = 0x10000u;
+                d[k] = (dd > kWindow || (int)dd > p_cap + qb + li) ? 0u : dd;
+            }
+            if (li >= slo && li < shi) dout[qb + li] = (uint16_t)d[k];
         }
-        cur = nxt; nxt = nxt2;
+        cur = cur_n; ext = ext_n;
     }
+    if (warp == 0) ring_wait(bar_in);                            // absorb the last hand-off
 }
 
 // ------------------------------------------------------------------------------------------
@@ -136,22 +199,15 @@ struct WordView {
     }
 };
 
-__global__ void __launch_bounds__(256)
-k_lz_match(const uint8_t* __restrict__ buf, uint64_t total, uint64_t dict, const uint16_t* __restrict__ dist16,
-           uint32_t* __restrict__ mt, int max_chain, int nice)
+// Bounds-checked search (every load clamped to the buffer): used for the last few hundred positions
+// of the input, where the fast path's 4-byte loads could run past the end.
+__device__ uint32_t match_careful(const uint8_t* __restrict__ buf, uint64_t total, uint64_t p, uint32_t maxlen,
+                                  const uint16_t* __restrict__ dist16, int max_chain, uint32_t nice_eff)
 {
-    const uint64_t rel = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    const uint64_t p = dict + rel;
-    if (p >= total) return;
-    const uint64_t chunk_end = min(total, dict + (rel / kChunk + 1) * kChunk);
-    const uint32_t maxlen = (uint32_t)min((uint64_t)kMaxMatch, chunk_end - p);
-    if (maxlen < kMinMatch) { mt[rel] = 0; return; }
     WordView wv;
     wv.mis = (uint32_t)((uintptr_t)buf & 3);
     wv.words = reinterpret_cast<const uint32_t*>(buf - wv.mis);
     wv.last = ((wv.mis + total + 3) >> 2) - 1;
-    const uint32_t nice_eff = min((uint32_t)nice, maxlen);
-
     uint32_t best_len = kMinMatch - 1, best_dist = 0, acc = 0;
     uint32_t d = dist16[p];
     const uint32_t head4 = wv.ld32(p);
@@ -176,55 +232,113 @@ k_lz_match(const uint8_t* __restrict__ buf, uint64_t total, uint64_t dict, const
         }
         d = dist16[cand];
     }
+    return best_len >= kMinMatch ? ((best_dist << 16) | best_len) : 0u;
+}
+
+// 4 bytes at an arbitrary address, little endian: two aligned loads and a funnel shift.  Reads up to the
+// end of the aligned word that holds byte a+3.
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* a)
+{
+    const uintptr_t u = (uintptr_t)a;
+    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3));
+    const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>((u + 3) & ~(uintptr_t)3));
+    return __funnelshift_r(lo, hi, (uint32_t)(u & 3) * 8);
+}
+
+// One thread per position.  Candidate order, the quick reject on the byte that would extend the best
+// match, "strictly longer wins" and the nice_match cut-off are the reference's (deflate.c:1090-1160);
+// the chain is the dist16 links.  All addressing is one 64-bit pointer per thread plus 32-bit offsets,
+// and every comparison is a 4-byte word (two aligned loads + funnel shift).
+__global__ void __launch_bounds__(256)
+k_lz_match(const uint8_t* __restrict__ buf, uint64_t total, uint64_t dict, const uint16_t* __restrict__ dist16,
+           uint32_t* __restrict__ mt, int max_chain, int nice)
+{
+    const uint64_t rel = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t p = dict + rel;
+    if (p >= total) return;
+    const uint64_t unit_end = min(total, dict + (rel / kUnit + 1) * kUnit);    // matches stay inside the parse unit
+    const uint32_t maxlen = (uint32_t)min((uint64_t)kMaxMatch, unit_end - p);
+    if (maxlen < kMinMatch) { mt[rel] = 0; return; }
+    const uint32_t nice_eff = min((uint32_t)nice, maxlen);
+    if (p + kMaxMatch + 8 > total) {                            // tail of the input: clamped loads
+        mt[rel] = match_careful(buf, total, p, maxlen, dist16, max_chain, nice_eff);
+        return;
+    }
+    const uint8_t* pp = buf + p;
+    const uint16_t* dp = dist16 + p;
+    uint32_t acc = dp[0];
+    uint32_t best_len = kMinMatch - 1, best_dist = 0;
+    if (acc != 0) {
+        uint32_t qoff = 0, qmask = 0xffffffu;                   // quick-reject word: offset into the match, bytes that must agree
+        uint32_t hq = ld32u(pp);
+        int chain = max_chain;
+        do {
+            if (acc > kWindow) break;
+            const uint8_t* cp = pp - acc;
+            const uint32_t x = ld32u(cp + qoff) ^ hq;
+            if ((x & qmask) == 0) {
+                uint32_t len;
+                if (qoff == 0 && x != 0) len = 3;               // first three agree, the fourth does not
+                else {
+                    len = qoff == 0 ? 4u : 0u;
+                    while (len < maxlen) {
+                        const uint32_t y = ld32u(pp + len) ^ ld32u(cp + len);
+                        if (y) { len += (uint32_t)(__ffs(y) - 1) >> 3; break; }
+                        len += 4;
+                    }
+                    len = min(len, maxlen);
+                }
+                if (len > best_len) {
+                    best_len = len; best_dist = acc;
+                    if (len >= nice_eff) break;
+                    qoff = len >= 4 ? len - 3 : 0u;             // bytes len-3 .. len must agree to do better
+                    qmask = 0xffffffffu;
+                    hq = ld32u(pp + qoff);
+                }
+            }
+            const uint32_t d = *(dp - acc);
+            if (d == 0) break;
+            acc += d;
+        } while (--chain > 0);
+    }
     mt[rel] = best_len >= kMinMatch ? ((best_dist << 16) | best_len) : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
-// K1c: parse (greedy / lazy), tokens, histograms, block boundaries
+// K1c: parse (greedy / lazy), tokens, histograms
 // ------------------------------------------------------------------------------------------
 constexpr int kParseWarps = 4;
-constexpr int kHistSize = 320;                                   // 0..287 literal/length, 288..319 distance
 
 __global__ void __launch_bounds__(kParseWarps * 32)
 k_lz_parse(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restrict__ mt, uint32_t* __restrict__ tok,
-           BlockMeta* __restrict__ blk, uint32_t* __restrict__ blk_hist, ChunkMeta* __restrict__ chunks,
-           int kind, uint32_t max_lazy)
+           uint32_t* __restrict__ unit_ntok, uint32_t* __restrict__ unit_hist, int kind, uint32_t max_lazy)
 {
     __shared__ uint32_t s_hist[kParseWarps][kHistSize];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint64_t nchunks = (n + kChunk - 1) / kChunk;
-    const uint64_t c = (uint64_t)blockIdx.x * kParseWarps + warp;
-    if (c >= nchunks) return;
+    const uint64_t nunits = (n + kUnit - 1) / kUnit;
+    const uint64_t u = (uint64_t)blockIdx.x * kParseWarps + warp;
+    if (u >= nunits) return;
     uint32_t* hist = s_hist[warp];
-    for (int i = lane; i < kHistSize; i += 32) hist[i] = 0;
+    for (int i = lane; i < (int)kHistSize; i += 32) hist[i] = 0;
     __syncwarp();
 
-    const uint64_t cbeg = c * kChunk;
-    const uint32_t clen = (uint32_t)min((uint64_t)kChunk, n - cbeg);
-    const uint32_t* m = mt + cbeg;
-    const uint8_t* in = src + cbeg;
-    uint32_t* out = tok + cbeg;
-    uint32_t pos = 0, ntok = 0, nblk = 0, blk_tok0 = 0, blk_in0 = 0;
+    const uint64_t ubeg = u * kUnit;
+    const uint32_t ulen = (uint32_t)min((uint64_t)kUnit, n - ubeg);
+    const uint32_t* m = mt + ubeg;
+    const uint8_t* in = src + ubeg;
+    uint32_t* out = tok + ubeg;
+    uint32_t pos = 0, ntok = 0;
 
-    auto close_block = [&](uint32_t end_pos) {
-        __syncwarp();
-        uint32_t* g = blk_hist + (c * kMaxBlocks + nblk) * kHistSize;
-        for (int i = lane; i < kHistSize; i += 32) { g[i] = hist[i] + (i == 256 ? 1u : 0u); hist[i] = 0; }
-        if (lane == 0) blk[c * kMaxBlocks + nblk] = BlockMeta{blk_tok0, ntok - blk_tok0, blk_in0, end_pos - blk_in0, 0, 0, 0, 0};
-        nblk++; blk_tok0 = ntok; blk_in0 = end_pos;
-        __syncwarp();
-    };
-
-    while (pos < clen) {
+    while (pos < ulen) {
         const uint32_t i = pos + lane;
-        uint32_t mv = i < clen ? m[i] : 0u;
-        uint32_t mn = __shfl_down_sync(kFullMask, mv, 1);
-        const uint32_t m32 = (pos + 32 < clen) ? m[pos + 32] : 0u;     // uniform load
-        if (lane == 31) mn = m32;
+        uint32_t mv = i < ulen ? m[i] : 0u;
         uint32_t L = mv & 0x1ffu, dist = mv >> 16;
         bool take;
         if (kind == 2) {
+            uint32_t mn = __shfl_down_sync(kFullMask, mv, 1);
+            const uint32_t m32 = (pos + 32 < ulen) ? m[pos + 32] : 0u;     // uniform load
+            if (lane == 31) mn = m32;
             uint32_t Ln = mn & 0x1ffu;
             if (L == kMinMatch && dist > kTooFar) L = 0;
             if (Ln == kMinMatch && (mn >> 16) > kTooFar) Ln = 0;
@@ -233,12 +347,21 @@ k_lz_parse(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restri
             take = L >= kMinMatch;
         }
         const uint32_t step = take ? L : 1u;
-        // follow the "next position" recurrence through the window
-        uint32_t cur = 0, mask = 0;
-        while (cur < 32 && pos + cur < clen) {
-            mask |= 1u << cur;
-            cur += __shfl_sync(kFullMask, step, cur);
+        // Follow the "next position" recurrence through the window.  Positions reached from the window's
+        // first position are found by jump doubling: after round k the first 2^k positions of the orbit are
+        // known, so 5 rounds cover any window (a serial walk needs up to 32 dependent shuffles).
+        const uint32_t lim = min(32u, ulen - pos);
+        const uint32_t land = lane + step;                      // where this position's token ends
+        uint32_t J = land < lim ? land : 32u;                   // 32 = leaves the window
+        uint32_t mask = 1u;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t img = (((mask >> lane) & 1u) && J < 32u) ? (1u << J) : 0u;
+            mask |= __reduce_or_sync(kFullMask, img);
+            const uint32_t Jn = __shfl_sync(kFullMask, J, J & 31u);
+            if (J < 32u) J = Jn;
         }
+        const uint32_t cur = __shfl_sync(kFullMask, land, 31 - __clz(mask));
         if (mask & (1u << lane)) {
             const uint32_t idx = ntok + __popc(mask & lt);
             if (take) {
@@ -253,29 +376,32 @@ k_lz_parse(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restri
         }
         ntok += __popc(mask);
         pos += cur;
-        if (ntok - blk_tok0 + 32 > kBlockTokens && pos < clen) close_block(pos);
     }
-    close_block(clen);
-    if (lane == 0) chunks[c] = ChunkMeta{nblk, 0, 0, 0};
+    __syncwarp();
+    uint32_t* g = unit_hist + u * kHistSize;
+    for (int i = lane; i < (int)kHistSize; i += 32) g[i] = hist[i];
+    if (lane == 0) unit_ntok[u] = ntok;
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: length-limited canonical codes per block (trees.c:490-860), block pricing (trees.c:921-1001)
 // ------------------------------------------------------------------------------------------
 constexpr int kCodeWarps = 4;
-constexpr int kTreeMax = 2 * 286 + 1;
 
 __constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 struct TreeScratch {
-    uint16_t freq[kTreeMax], up[kTreeMax], len[kTreeMax];
-    uint16_t heap[kTreeMax + 1];
-    uint8_t  depth[kTreeMax];
+    uint32_t hsum[kHistSize];                                   // block histogram = sum of its units' histograms
+    uint32_t freq[288];                                         // input of the code under construction
+    uint32_t key[512];                                          // freq << 9 | symbol, ascending
+    uint32_t wint[288];                                         // weights of internal nodes, in creation order
+    uint16_t parent[2 * 288];                                   // leaves [0,m) in sorted order, then internal nodes
+    uint8_t  idepth[288];
+    uint32_t run[16], next_code[16];
     uint16_t bl_count[16];
     uint16_t llen[288 + 2], dlen[32 + 2];                       // +sentinel slot for the run-length scan
     uint16_t blfreq[20], bllen[20], blcode[20];
     uint16_t lcode[288], dcode[32];
-    int heap_len, heap_max;
 };
 
 struct BitSink {                                                // serial bit writer into global words
@@ -288,88 +414,123 @@ struct BitSink {                                                // serial bit wr
     __device__ void finish() { if (n > 0) w[count++] = (uint32_t)acc; }
 };
 
-__device__ __forceinline__ bool node_lighter(const TreeScratch* t, int a, int b)
-{
-    return t->freq[a] < t->freq[b] || (t->freq[a] == t->freq[b] && t->depth[a] <= t->depth[b]);
-}
-__device__ void sift_down(TreeScratch* t, int k)
-{
-    const int v = t->heap[k];
-    for (int j = k << 1; j <= t->heap_len; j <<= 1) {
-        if (j < t->heap_len && node_lighter(t, t->heap[j + 1], t->heap[j])) j++;
-        if (node_lighter(t, v, t->heap[j])) break;
-        t->heap[k] = t->heap[j]; k = j;
-    }
-    t->heap[k] = (uint16_t)v;
-}
 __device__ __forceinline__ uint32_t bit_reverse(uint32_t v, int n) { return __brev(v) >> (32 - n); }
 
-// Serial (one lane).  freq[0..nsym) in t->freq; writes lengths to out_len[0..nsym) and codes to out_code.
-// Returns max_code.
-__device__ int make_code(TreeScratch* t, int nsym, int max_length, uint16_t* out_len, uint16_t* out_code)
-{
-    int max_code = -1;
-    t->heap_len = 0; t->heap_max = kTreeMax;
-    for (int n = 0; n < nsym; n++) {
-        if (t->freq[n]) { t->heap[++t->heap_len] = (uint16_t)(max_code = n); t->depth[n] = 0; }
-        else t->len[n] = 0;
-    }
-    while (t->heap_len < 2) {                                   // force two codes (trees.c:650-656)
-        const int n = (max_code < 2 ? ++max_code : 0);
-        t->heap[++t->heap_len] = (uint16_t)n;
-        t->freq[n] = 1; t->depth[n] = 0;
-    }
-    for (int n = t->heap_len / 2; n >= 1; n--) sift_down(t, n);
-    int node = nsym;
-    do {
-        const int n = t->heap[1];
-        t->heap[1] = t->heap[t->heap_len--]; sift_down(t, 1);
-        const int m = t->heap[1];
-        t->heap[--t->heap_max] = (uint16_t)n; t->heap[--t->heap_max] = (uint16_t)m;
-        t->freq[node] = (uint16_t)(t->freq[n] + t->freq[m]);
-        t->depth[node] = (uint8_t)((t->depth[n] >= t->depth[m] ? t->depth[n] : t->depth[m]) + 1);
-        t->up[n] = t->up[m] = (uint16_t)node;
-        t->heap[1] = (uint16_t)node++; sift_down(t, 1);
-    } while (t->heap_len >= 2);
-    t->heap[--t->heap_max] = t->heap[1];
 
-    // lengths with the reference's overflow repair (trees.c:490-567)
-    for (int b = 0; b <= 15; b++) t->bl_count[b] = 0;
-    int over = 0, h;
-    t->len[t->heap[t->heap_max]] = 0;
-    for (h = t->heap_max + 1; h < kTreeMax; h++) {
-        const int n = t->heap[h];
-        int bits = t->len[t->up[n]] + 1;
-        if (bits > max_length) { bits = max_length; over++; }
-        t->len[n] = (uint16_t)bits;
-        if (n > max_code) continue;
-        t->bl_count[bits]++;
+// Warp-cooperative replacement for make_code: same optimal total cost (a Huffman tree), built the way a
+// GPU likes it -- (1) compact the used symbols with ballots, (2) bitonic sort of (freq, symbol) keys in
+// shared memory, (3) the two-queue merge (leaves in sorted order + internal nodes in creation order are
+// both already sorted, so each step picks the two smallest heads: O(m), no heap), (4) depths top-down,
+// (5) the reference's overflow repair on the length histogram (trees.c:527-545) and lengths handed out
+// in frequency order, (6) canonical codes with ranks from match_any.  Steps 3, 4 are one lane; the rest
+// uses all 32.  Returns max_code.  All lanes must call it.
+__device__ int warp_make_code(TreeScratch* t, int nsym, int max_length, uint16_t* out_len, uint16_t* out_code)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    // (1) used symbols -> keys
+    int m = 0, max_code = -1;
+    for (int base = 0; base < nsym; base += 32) {
+        const int s = base + lane;
+        const uint32_t f = s < nsym ? t->freq[s] : 0u;
+        const uint32_t used = __ballot_sync(kFullMask, f != 0);
+        if (f) t->key[m + __popc(used & lt)] = (f << 9) | (uint32_t)s;
+        if (used) max_code = base + 31 - __clz(used);
+        m += __popc(used);
+        if (s < nsym) out_len[s] = 0;
     }
-    if (over) {
-        do {
-            int bits = max_length - 1;
-            while (t->bl_count[bits] == 0) bits--;
-            t->bl_count[bits]--; t->bl_count[bits + 1] += 2; t->bl_count[max_length]--;
-            over -= 2;
-        } while (over > 0);
-        for (int bits = max_length; bits != 0; bits--) {
-            int n = t->bl_count[bits];
-            while (n != 0) {
-                const int m = t->heap[--h];
-                if (m > max_code) continue;
-                t->len[m] = (uint16_t)bits;
-                n--;
+    while (m < 2) {                                             // force two codes (trees.c:650-656)
+        const int n = (max_code < 2 ? ++max_code : 0);
+        if (lane == 0) t->key[m] = (1u << 9) | (uint32_t)n;
+        m++;
+    }
+    int P = 32;
+    while (P < m) P <<= 1;
+    for (int i = m + lane; i < P; i += 32) t->key[i] = 0xffffffffu;
+    __syncwarp();
+    // (2) bitonic sort, ascending
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P / 2; i += 32) {
+                const int a = ((i & ~(j - 1)) << 1) | (i & (j - 1)), b = a | j;
+                const uint32_t x = t->key[a], y = t->key[b];
+                const bool up = (a & k) == 0;
+                if ((x > y) == up) { t->key[a] = y; t->key[b] = x; }
             }
+            __syncwarp();
         }
     }
-    // canonical codes (trees.c:577-609)
-    uint32_t next[16], code = 0;
-    for (int b = 1; b <= 15; b++) { code = (code + t->bl_count[b - 1]) << 1; next[b] = code; }
-    for (int n = 0; n < nsym; n++) {
-        const int l = n <= max_code ? t->len[n] : 0;
-        out_len[n] = (uint16_t)l;
-        out_code[n] = l ? (uint16_t)bit_reverse(next[l]++, l) : 0;
+    // (3) two-queue merge, (4) depths of the internal nodes
+    if (lane == 0) {
+        int i = 0, j = 0;
+        uint32_t lw = t->key[0] >> 9, iw = 0xffffffffu;
+        for (int ni = 0; ni < m - 1; ni++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (i < m && (j >= ni || lw <= iw)) {
+                    w += lw; t->parent[i] = (uint16_t)(m + ni);
+                    i++; lw = i < m ? t->key[i] >> 9 : 0xffffffffu;
+                } else {
+                    w += iw; t->parent[m + j] = (uint16_t)(m + ni);
+                    j++; iw = j < ni ? t->wint[j] : 0xffffffffu;
+                }
+            }
+            t->wint[ni] = w;
+            if (j == ni) iw = w;                                 // the node just made is now the head of its queue
+        }
+        t->idepth[m - 2] = 0;
+        for (int q = m - 3; q >= 0; q--) t->idepth[q] = (uint8_t)(t->idepth[t->parent[m + q] - m] + 1);
     }
+    if (lane < 16) { t->bl_count[lane] = 0; t->run[lane] = 0; }
+    __syncwarp();
+    // (5) length histogram, overflow repair, lengths in frequency order
+    uint32_t over = 0;
+    for (int i = lane; i < m; i += 32) {
+        int bits = t->idepth[t->parent[i] - m] + 1;
+        if (bits > max_length) { bits = max_length; over++; }
+        atomicAdd(&t->run[bits], 1u);
+    }
+    // the reference counts every node below the limit, internal ones included (their clamped length is what
+    // their children see, trees.c:506-512)
+    for (int q = lane; q < m - 1; q += 32) over += t->idepth[q] > max_length ? 1u : 0u;
+#pragma unroll
+    for (int k = 16; k; k >>= 1) over += __shfl_xor_sync(kFullMask, over, k);
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t cnt[16];
+        for (int b = 0; b < 16; b++) { cnt[b] = t->run[b]; t->run[b] = 0; }
+        int overflow = (int)over;
+        while (overflow > 0) {
+            int bits = max_length - 1;
+            while (cnt[bits] == 0) bits--;
+            cnt[bits]--; cnt[bits + 1] += 2; cnt[max_length]--;
+            overflow -= 2;
+        }
+        uint32_t code = 0;
+        for (int b = 0; b < 16; b++) t->bl_count[b] = (uint16_t)cnt[b];
+        t->next_code[0] = 0;
+        for (int b = 1; b <= 15; b++) { code = (code + cnt[b - 1]) << 1; t->next_code[b] = code; }
+    }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {                        // leaf i (ascending frequency) gets the i-th longest length
+        int L = max_length, cum = t->bl_count[max_length];
+        while (cum <= i) { L--; cum += t->bl_count[L]; }
+        out_len[t->key[i] & 511u] = (uint16_t)L;
+    }
+    __syncwarp();
+    // (6) canonical codes (trees.c:577-609): code = next_code[len] + rank among symbols of that length
+    for (int base = 0; base < nsym; base += 32) {
+        const int s = base + lane;
+        const uint32_t L = s < nsym ? out_len[s] : 0u;
+        const uint32_t grp = __match_any_sync(kFullMask, L);
+        const uint32_t rank = t->run[L] + __popc(grp & lt);
+        __syncwarp();
+        if ((grp & lt) == 0) t->run[L] += __popc(grp);
+        __syncwarp();
+        if (s < nsym) out_code[s] = L ? (uint16_t)bit_reverse(t->next_code[L] + rank, (int)L) : 0;
+    }
+    __syncwarp();
     return max_code;
 }
 
@@ -414,54 +575,60 @@ __device__ __forceinline__ uint32_t fixed_lit_code(uint32_t s)
 }
 
 __global__ void __launch_bounds__(kCodeWarps * 32)
-k_huff_build(uint64_t nchunks, const ChunkMeta* __restrict__ chunks, BlockMeta* __restrict__ blk,
-             const uint32_t* __restrict__ blk_hist, uint32_t* __restrict__ blk_codes, uint32_t* __restrict__ blk_hdr,
-             int force_fixed)
+k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict__ unit_hist,
+             uint32_t* __restrict__ blk_codes, uint32_t* __restrict__ blk_hdr, int force_fixed)
 {
     __shared__ TreeScratch s_t[kCodeWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t slot = (uint64_t)blockIdx.x * kCodeWarps + warp;
-    const uint64_t c = slot / kMaxBlocks;
-    if (c >= nchunks || (slot % kMaxBlocks) >= chunks[c].nblocks) return;
+    const uint64_t nblocks = (n + kBlockBytes - 1) / kBlockBytes, nunits = (n + kUnit - 1) / kUnit;
+    const uint64_t b = (uint64_t)blockIdx.x * kCodeWarps + warp;
+    if (b >= nblocks) return;
     TreeScratch* t = &s_t[warp];
-    const uint32_t* hist = blk_hist + slot * kHistSize;
-    uint32_t* codes = blk_codes + slot * kHistSize;
+    uint32_t* codes = blk_codes + b * kHistSize;
+    const uint32_t in_len = (uint32_t)min((uint64_t)kBlockBytes, n - b * kBlockBytes);
 
+    // ---- block histogram ----
+    const uint64_t u0 = b * kBlockUnits, u1 = min(nunits, u0 + kBlockUnits);
+    for (int i = lane; i < (int)kHistSize; i += 32) {
+        uint32_t f = i == 256 ? 1u : 0u;                        // the end-of-block symbol
+        for (uint64_t u = u0; u < u1; u++) f += unit_hist[u * kHistSize + i];
+        t->hsum[i] = f;
+    }
+    __syncwarp();
     // ---- literal/length and distance codes ----
-    for (int i = lane; i < 286; i += 32) t->freq[i] = (uint16_t)hist[i];
+    for (int i = lane; i < 286; i += 32) t->freq[i] = t->hsum[i];
     __syncwarp();
-    int lmax = 0, dmax = 0;
-    if (lane == 0) lmax = make_code(t, 286, 15, t->llen, t->lcode);
+    const int lmax = warp_make_code(t, 286, 15, t->llen, t->lcode);
+    if (lane < 30) t->freq[lane] = t->hsum[288 + lane];
     __syncwarp();
-    if (lane < 30) t->freq[lane] = (uint16_t)hist[288 + lane];
-    __syncwarp();
-    if (lane == 0) dmax = make_code(t, 30, 15, t->dlen, t->dcode);
-    __syncwarp();
-    lmax = __shfl_sync(kFullMask, lmax, 0); dmax = __shfl_sync(kFullMask, dmax, 0);
+    const int dmax = warp_make_code(t, 30, 15, t->dlen, t->dcode);
 
     // ---- cost of the data under the dynamic and the fixed code (all lanes) ----
     uint32_t dyn = 0, fix = 0;
     for (int s = lane; s < 286; s += 32) {
-        const uint32_t f = hist[s];
+        const uint32_t f = t->hsum[s];
         const uint32_t x = s >= 257 ? len_extra_bits((uint32_t)s - 257) : 0;
         dyn += f * (t->llen[s] + x); fix += f * (fixed_lit_len((uint32_t)s) + x);
     }
     if (lane < 30) {
-        const uint32_t f = hist[288 + lane], x = dist_extra_bits((uint32_t)lane);
+        const uint32_t f = t->hsum[288 + lane], x = dist_extra_bits((uint32_t)lane);
         dyn += f * (t->dlen[lane] + x); fix += f * (5 + x);
     }
 #pragma unroll
     for (int k = 16; k; k >>= 1) { dyn += __shfl_xor_sync(kFullMask, dyn, k); fix += __shfl_xor_sync(kFullMask, fix, k); }
 
-    // ---- code-length code and header (one lane) ----
-    BlockMeta bm = blk[slot];
-    uint32_t type = 0, body = 0, hdr_bits = 0;
+    // ---- code-length code and header ----
     if (lane == 0) {
         for (int i = 0; i < 19; i++) t->blfreq[i] = 0;
         walk_lengths(t, t->llen, lmax, nullptr);
         walk_lengths(t, t->dlen, dmax, nullptr);
         for (int i = 0; i < 19; i++) t->freq[i] = t->blfreq[i];
-        make_code(t, 19, 7, t->bllen, t->blcode);
+    }
+    __syncwarp();
+    warp_make_code(t, 19, 7, t->bllen, t->blcode);
+    uint32_t type = 0;
+    if (lane == 0) {
+        uint32_t body = 0, hdr_bits = 0;
         int max_bl = 18;
         while (max_bl >= 3 && t->bllen[c_bl_order[max_bl]] == 0) max_bl--;
         uint32_t tree_bits = 14 + 3 * (max_bl + 1);
@@ -470,11 +637,12 @@ k_huff_build(uint64_t nchunks, const ChunkMeta* __restrict__ chunks, BlockMeta* 
         uint32_t opt_lenb = (opt_len + 3 + 7) >> 3;
         const uint32_t static_lenb = (static_len + 3 + 7) >> 3;
         if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
-        if (bm.in_len + 4 <= opt_lenb && !force_fixed) { type = 0; body = 0; }
+        // a stored block holds at most 65535 bytes: a full 64 KiB block goes out as two (5 more bytes)
+        if (in_len + 4 + (in_len > 65535u ? 5u : 0u) <= opt_lenb && !force_fixed) { type = 0; body = 0; }
         else if (static_lenb == opt_lenb || force_fixed) { type = 1; body = static_len; }
         else {
-            type = 2; body = opt_len; hdr_bits = tree_bits;
-            BitSink sink{blk_hdr + slot * kHdrWords, 0, 0, 0, 0};
+            type = 2; body = opt_len;
+            BitSink sink{blk_hdr + b * kHdrWords, 0, 0, 0, 0};
             sink.put((uint32_t)lmax + 1 - 257, 5); sink.put((uint32_t)dmax + 1 - 1, 5); sink.put((uint32_t)max_bl + 1 - 4, 4);
             for (int r = 0; r <= max_bl; r++) sink.put(t->bllen[c_bl_order[r]], 3);
             walk_lengths(t, t->llen, lmax, &sink);
@@ -483,8 +651,7 @@ k_huff_build(uint64_t nchunks, const ChunkMeta* __restrict__ chunks, BlockMeta* 
             hdr_bits = sink.total;
         }
         t->llen[lmax + 1] = 0; t->dlen[dmax + 1] = 0;              // drop the run-length sentinels
-        bm.type = type; bm.body_bits = body; bm.hdr_bits = hdr_bits;
-        blk[slot] = bm;
+        blk[b] = BlockMeta{in_len, type, body, hdr_bits};
     }
     type = __shfl_sync(kFullMask, type, 0);
     __syncwarp();
@@ -513,8 +680,10 @@ __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chu
 {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
-    ChunkMeta cm = chunks[c];
+    ChunkMeta cm;
     const uint32_t clen = (uint32_t)min((uint64_t)kChunk, n - c * kChunk);
+    cm.nblocks = (clen + kBlockBytes - 1) / kBlockBytes;
+    cm.offset = 0;
     const bool final_chunk = last_is_final && c == nchunks - 1;
     const bool mark = force_mark && !last_is_final && c == nchunks - 1;   // Z_SYNC_FLUSH marker wanted regardless
     uint64_t bytes;
@@ -523,9 +692,12 @@ __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chu
     } else {
         uint64_t bits = 0;
         bool ends_stored = false;
-        for (uint32_t b = 0; b < cm.nblocks; b++) {
-            const BlockMeta bm = blk[c * kMaxBlocks + b];
-            if (bm.type == 0) { bits = ((bits + 3 + 7) & ~7ull) + 32 + 8ull * bm.in_len; ends_stored = true; }
+        for (uint32_t j = 0; j < cm.nblocks; j++) {
+            const BlockMeta bm = blk[c * kBlocksPerChunk + j];
+            if (bm.type == 0) {
+                bits = ((bits + 3 + 7) & ~7ull) + 32 + 8ull * bm.in_len; ends_stored = true;
+                if (bm.in_len > 65535u) bits += 8 + 32;         // second stored block: header byte, LEN, NLEN
+            }
             else { bits += 3 + bm.body_bits; ends_stored = false; }
         }
         if (final_chunk || (ends_stored && !mark)) bytes = (bits + 7) >> 3;
@@ -538,14 +710,16 @@ __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chu
     chunks[c] = cm;
 }
 
-// single CTA: exclusive prefix sum of chunk sizes; result[0] = total payload bytes
-__global__ void __launch_bounds__(1024) k_scan(uint64_t nchunks, ChunkMeta* __restrict__ chunks, uint64_t base,
-                                               uint64_t* __restrict__ result)
+// single CTA: exclusive prefix sum of chunk sizes starting at (*start_ptr or 0) + start_add; end[0] = where
+// the next slab starts
+__global__ void __launch_bounds__(1024) k_scan(uint64_t nchunks, ChunkMeta* __restrict__ chunks,
+                                               const uint64_t* __restrict__ start_ptr, uint64_t start_add,
+                                               uint64_t* __restrict__ end)
 {
     __shared__ uint64_t s_w[32];
     __shared__ uint64_t s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = base;
+    if (threadIdx.x == 0) s_carry = (start_ptr ? start_ptr[0] : 0) + start_add;
     __syncthreads();
     for (uint64_t i0 = 0; i0 < nchunks; i0 += 1024) {
         const uint64_t i = i0 + threadIdx.x;
@@ -569,7 +743,7 @@ __global__ void __launch_bounds__(1024) k_scan(uint64_t nchunks, ChunkMeta* __re
         if (threadIdx.x == 1023) s_carry = carry + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) result[0] = s_carry - base;
+    if (threadIdx.x == 0) end[0] = s_carry;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -621,7 +795,8 @@ struct Packer {
 
 __global__ void __launch_bounds__(kPackThreads)
 k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restrict__ tok,
-            const BlockMeta* __restrict__ blk, const uint32_t* __restrict__ blk_codes, const uint32_t* __restrict__ blk_hdr,
+            const uint32_t* __restrict__ unit_ntok, const BlockMeta* __restrict__ blk,
+            const uint32_t* __restrict__ blk_codes, const uint32_t* __restrict__ blk_hdr,
             const ChunkMeta* __restrict__ chunks, uint8_t* __restrict__ out, uint64_t cap, int last_is_final,
             int force_mark, uint32_t* __restrict__ err)
 {
@@ -660,26 +835,33 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
     __syncthreads();
     Packer pk{s_stage, s_sums, dst, 0, 0};
     bool ends_stored = false;
-    for (uint32_t b = 0; b < cm.nblocks; b++) {
-        const BlockMeta bm = blk[c * kMaxBlocks + b];
-        const uint32_t bfinal = (final_chunk && b == cm.nblocks - 1) ? 1u : 0u;
+    for (uint32_t j = 0; j < cm.nblocks; j++) {
+        const uint64_t b = c * kBlocksPerChunk + j;
+        const BlockMeta bm = blk[b];
+        const uint32_t bfinal = (final_chunk && j == cm.nblocks - 1) ? 1u : 0u;
+        const uint32_t in_start = j * kBlockBytes;
         if (bm.type == 0) {
-            // 3 header bits, pad to a byte, LEN, NLEN, then the raw bytes
-            const uint32_t pad = (8 - ((pk.carry_bits + 3) & 7)) & 7;
-            uint64_t v = 0; uint32_t nb = 0;
-            if (threadIdx.x == 0) { v = bfinal; nb = 3 + pad; }
-            else if (threadIdx.x == 1) { v = (bm.in_len & 0xffffu) | ((~bm.in_len & 0xffffu) << 16); nb = 32; }
-            pk.round(v, nb);
-            for (uint32_t i = threadIdx.x; i < bm.in_len; i += kPackThreads) dst[pk.bytepos + i] = in[bm.in_start + i];
-            pk.bytepos += bm.in_len;
+            // 3 header bits, pad to a byte, LEN, NLEN, then the raw bytes; at most 65535 bytes per stored block
+            for (uint32_t done = 0; done < bm.in_len;) {
+                const uint32_t len = min(65535u, bm.in_len - done);
+                const uint32_t fin = (bfinal && done + len == bm.in_len) ? 1u : 0u;
+                const uint32_t pad = (8 - ((pk.carry_bits + 3) & 7)) & 7;
+                uint64_t v = 0; uint32_t nb = 0;
+                if (threadIdx.x == 0) { v = fin; nb = 3 + pad; }
+                else if (threadIdx.x == 1) { v = (len & 0xffffu) | ((~len & 0xffffu) << 16); nb = 32; }
+                pk.round(v, nb);
+                for (uint32_t i = threadIdx.x; i < len; i += kPackThreads) dst[pk.bytepos + i] = in[in_start + done + i];
+                pk.bytepos += len;
+                done += len;
+            }
             ends_stored = true;
             continue;
         }
         ends_stored = false;
-        for (int i = threadIdx.x; i < kHistSize; i += kPackThreads) s_codes[i] = blk_codes[(c * kMaxBlocks + b) * kHistSize + i];
+        for (int i = threadIdx.x; i < (int)kHistSize; i += kPackThreads) s_codes[i] = blk_codes[b * kHistSize + i];
         {   // block header: 3 bits, then the serialised trees of a dynamic block
             const uint32_t hw = bm.type == 2 ? (bm.hdr_bits + 31) / 32 : 0;
-            const uint32_t* hdr = blk_hdr + (c * kMaxBlocks + b) * kHdrWords;
+            const uint32_t* hdr = blk_hdr + b * kHdrWords;
             uint64_t v = 0; uint32_t nb = 0;
             if (threadIdx.x == 0) { v = bfinal | (bm.type << 1); nb = 3; }
             else if (threadIdx.x <= hw) {
@@ -688,30 +870,36 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
             }
             pk.round(v, nb);                                    // also publishes s_codes (barrier inside)
         }
-        const uint32_t* t = tok + cbeg + bm.tok_start;
-        for (uint32_t i0 = 0; i0 <= bm.tok_count; i0 += kPackThreads) {
-            const uint32_t i = i0 + threadIdx.x;
-            uint64_t v = 0; uint32_t nb = 0;
-            if (i < bm.tok_count) {
-                const uint32_t tk = t[i], dist = tk >> 16;
-                if (dist == 0) {
-                    const uint32_t e = s_codes[tk & 0xff];
+        const uint32_t units = (bm.in_len + kUnit - 1) / kUnit;
+        for (uint32_t k = 0; k < units; k++) {
+            const uint64_t u = b * kBlockUnits + k;
+            const uint32_t* t = tok + u * kUnit;
+            const uint32_t cnt = unit_ntok[u];
+            const uint32_t end = cnt + (k == units - 1 ? 1u : 0u);   // the block's last round also carries end-of-block
+            for (uint32_t i0 = 0; i0 < end; i0 += kPackThreads) {
+                const uint32_t i = i0 + threadIdx.x;
+                uint64_t v = 0; uint32_t nb = 0;
+                if (i < cnt) {
+                    const uint32_t tk = t[i], dist = tk >> 16;
+                    if (dist == 0) {
+                        const uint32_t e = s_codes[tk & 0xff];
+                        v = e & 0xffffu; nb = e >> 16;
+                    } else {
+                        const uint32_t l = tk & 0xff, lc = len_code(l), le = len_extra_bits(lc);
+                        const uint32_t e = s_codes[257 + lc];
+                        v = e & 0xffffu; nb = e >> 16;
+                        if (le) { v |= (uint64_t)(l & ((1u << le) - 1u)) << nb; nb += le; }
+                        const uint32_t d = dist - 1, dc = dist_code(d), de = dist_extra_bits(dc);
+                        const uint32_t f = s_codes[288 + dc];
+                        v |= (uint64_t)(f & 0xffffu) << nb; nb += f >> 16;
+                        if (de) { v |= (uint64_t)(d & ((1u << de) - 1u)) << nb; nb += de; }
+                    }
+                } else if (i == cnt && k == units - 1) {
+                    const uint32_t e = s_codes[256];            // end of block
                     v = e & 0xffffu; nb = e >> 16;
-                } else {
-                    const uint32_t l = tk & 0xff, lc = len_code(l), le = len_extra_bits(lc);
-                    const uint32_t e = s_codes[257 + lc];
-                    v = e & 0xffffu; nb = e >> 16;
-                    if (le) { v |= (uint64_t)(l & ((1u << le) - 1u)) << nb; nb += le; }
-                    const uint32_t d = dist - 1, dc = dist_code(d), de = dist_extra_bits(dc);
-                    const uint32_t f = s_codes[288 + dc];
-                    v |= (uint64_t)(f & 0xffffu) << nb; nb += f >> 16;
-                    if (de) { v |= (uint64_t)(d & ((1u << de) - 1u)) << nb; nb += de; }
                 }
-            } else if (i == bm.tok_count) {
-                const uint32_t e = s_codes[256];                // end of block
-                v = e & 0xffffu; nb = e >> 16;
+                pk.round(v, nb);
             }
-            pk.round(v, nb);
         }
     }
     // end of chunk: final -> pad; otherwise empty stored block unless already byte-aligned by a stored block
@@ -731,11 +919,11 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
 // ------------------------------------------------------------------------------------------
 // stream framing: header and trailer (deflate.c:577-650, 832-850)
 // ------------------------------------------------------------------------------------------
-__global__ void k_frame(uint8_t* __restrict__ out, uint64_t cap, uint64_t hdr_len, const uint64_t* __restrict__ payload,
+__global__ void k_frame(uint8_t* __restrict__ out, uint64_t cap, uint64_t hdr_len, const uint64_t* __restrict__ d_end,
                         const uint32_t* __restrict__ sums, uint64_t n, int level, int wrap, int flags, uint64_t* __restrict__ total_out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t pos = hdr_len + payload[0];
+    uint64_t pos = d_end[0];                                    // header + every slab's payload
     uint8_t trailer[8]; int tl = 0;
     if (!(flags & (ZB200_DEFLATE_NO_TRAILER | ZB200_DEFLATE_NOT_LAST))) {
         if (wrap == ZB200_WRAP_ZLIB) {
@@ -765,89 +953,74 @@ __global__ void k_frame(uint8_t* __restrict__ out, uint64_t cap, uint64_t hdr_le
 }
 
 // empty input: a lone final fixed block with just the end-of-block code = 03 00 (what the reference emits)
-__global__ void k_empty_payload(uint8_t* out, uint64_t cap, uint64_t at, int not_last, int force_mark, uint64_t* payload)
+__global__ void k_empty_payload(uint8_t* out, uint64_t cap, uint64_t at, int not_last, int force_mark, uint64_t* d_end)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (not_last) {
-        payload[0] = force_mark ? 5 : 0;
+        d_end[0] = at + (force_mark ? 5 : 0);
         if (force_mark && at + 5 <= cap) { out[at] = 0; out[at + 1] = 0; out[at + 2] = 0; out[at + 3] = 0xff; out[at + 4] = 0xff; }
         return;
     }
-    payload[0] = 2;
+    d_end[0] = at + 2;
     if (at + 2 <= cap) { out[at] = 3; out[at + 1] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// d_buf = [dict bytes][n source bytes], contiguous in device memory.  d_res: u64[0] total bytes,
-// u32 at +8.. : crc, adler, error count.
-int deflate_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint64_t n, uint8_t* d_out, uint64_t cap, int level,
-                   int wrap, int flags, uint64_t* d_total, uint32_t* d_sums, uint32_t* d_err, cudaStream_t s)
+struct DeflateParams {
+    LevelCfg cfg; int level, strategy, wrap, flags;
+};
+
+// One slab: d_buf = [dict bytes][n source bytes], contiguous in device memory.  The slab's payload starts at
+// out[(*d_start or 0) + start_add]; *d_end receives where the next slab starts.  Everything is asynchronous on s.
+static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint64_t n, uint8_t* d_out, uint64_t cap,
+                               const DeflateParams& P, int last_is_final, int force_mark, const uint64_t* d_start,
+                               uint64_t start_add, uint64_t* d_end, uint32_t* d_err, cudaStream_t s)
 {
-    static bool attr = false;
-    if (!attr) {
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_link, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
-        attr = true;
-    }
-    if (level < 0) level = 6;
-    LevelCfg cfg = h_levels[level];
-    const int strategy = (flags >> 8) & 7;                      // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
-    const int force_mark = (flags & ZB200I_DEFLATE_FORCE_MARK) ? 1 : 0;
-    if (strategy == 2 && cfg.kind != 0) { cfg.chain = 0; cfg.kind = 1; }   // literals only (deflate.c:1490)
+    const LevelCfg& cfg = P.cfg;
     const uint64_t total = dict + n;
-    const uint64_t nchunks = (n + kChunk - 1) / kChunk;
-    const int last_is_final = (flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
-    const uint64_t hdr_len = (flags & ZB200_DEFLATE_NO_HEADER) ? 0 : wrap == ZB200_WRAP_ZLIB ? 2 : wrap == ZB200_WRAP_GZIP ? 10 : 0;
+    const uint64_t nchunks = (n + kChunk - 1) / kChunk, nunits = (n + kUnit - 1) / kUnit;
+    const uint64_t nblocks = (n + kBlockBytes - 1) / kBlockBytes;
     const uint8_t* d_src = d_buf + dict;
     int rc;
-
-    // checksums of the uncompressed data (read_buf, deflate.c:956-981)
-    if ((rc = checksum_launch(c, d_src, n, d_sums, s)) != 0) return rc;
-    ZB_CUDA(cudaMemsetAsync(d_err, 0, 4, s));
-    if ((rc = c->ws[1].ensure(16)) != 0) return rc;
-    uint64_t* d_payload = c->ws[1].as<uint64_t>();
-
-    if (nchunks == 0) {
-        ZB_LAUNCH(k_empty_payload, 1, 32, 0, s, d_out, cap, hdr_len, !last_is_final, force_mark, d_payload);
-    } else {
-        if ((rc = c->ws[2].ensure(nchunks * sizeof(ChunkMeta))) != 0) return rc;
-        ChunkMeta* d_chunks = c->ws[2].as<ChunkMeta>();
-        const uint64_t nslots = nchunks * kMaxBlocks;
-        BlockMeta* d_blk = nullptr; uint32_t *d_hist = nullptr, *d_codes = nullptr, *d_hdr = nullptr, *d_tok = nullptr;
-        if (cfg.kind != 0) {
-            if ((rc = c->ws[3].ensure(total * 2 + 64)) != 0) return rc;          // dist16
-            if ((rc = c->ws[4].ensure(n * 4 + 64)) != 0) return rc;              // per-position matches
-            if ((rc = c->ws[5].ensure(n * 4 + 64)) != 0) return rc;              // tokens
-            if ((rc = c->ws[6].ensure(nslots * sizeof(BlockMeta))) != 0) return rc;
-            if ((rc = c->ws[7].ensure(nslots * kHistSize * 4)) != 0) return rc;
-            if ((rc = c->ws[8].ensure(nslots * kHistSize * 4)) != 0) return rc;
-            if ((rc = c->ws[9].ensure(nslots * kHdrWords * 4)) != 0) return rc;
-            uint16_t* d_dist = c->ws[3].as<uint16_t>();
-            uint32_t* d_mt = c->ws[4].as<uint32_t>();
-            d_tok = c->ws[5].as<uint32_t>();
-            d_blk = c->ws[6].as<BlockMeta>();
-            d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
-            const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
-            if (cfg.chain == 0) {
-                ZB_CUDA(cudaMemsetAsync(d_mt, 0, n * 4, s));
-            } else {
-                ZB_LAUNCH(k_lz_link, nseg, 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
-                ZB_LAUNCH(k_lz_match, (unsigned)((n + 255) / 256), 256, 0, s, d_buf, total, dict, d_dist, d_mt, (int)cfg.chain, (int)cfg.nice);
-            }
-            ZB_LAUNCH(k_lz_parse, (unsigned)((nchunks + kParseWarps - 1) / kParseWarps), kParseWarps * 32, 0, s, d_src, n, d_mt,
-                      d_tok, d_blk, d_hist, d_chunks, cfg.kind, (uint32_t)cfg.lazy);
-            ZB_LAUNCH(k_huff_build, (unsigned)((nslots + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, nchunks, d_chunks,
-                      d_blk, d_hist, d_codes, d_hdr, strategy == 4 ? 1 : 0);
+    if ((rc = c->ws[2].ensure(nchunks * sizeof(ChunkMeta))) != 0) return rc;
+    ChunkMeta* d_chunks = c->ws[2].as<ChunkMeta>();
+    BlockMeta* d_blk = nullptr;
+    uint32_t *d_hist = nullptr, *d_codes = nullptr, *d_hdr = nullptr, *d_tok = nullptr, *d_ntok = nullptr;
+    if (cfg.kind != 0) {
+        if ((rc = c->ws[3].ensure(total * 2 + 64)) != 0) return rc;          // dist16
+        if ((rc = c->ws[4].ensure(n * 4 + 64)) != 0) return rc;              // per-position matches
+        if ((rc = c->ws[5].ensure(nunits * kUnit * 4 + 64)) != 0) return rc; // tokens, one kUnit-sized region per unit
+        if ((rc = c->ws[6].ensure(nblocks * sizeof(BlockMeta))) != 0) return rc;
+        if ((rc = c->ws[7].ensure(nunits * kHistSize * 4)) != 0) return rc;
+        if ((rc = c->ws[8].ensure(nblocks * kHistSize * 4)) != 0) return rc;
+        if ((rc = c->ws[9].ensure(nblocks * kHdrWords * 4)) != 0) return rc;
+        if ((rc = c->ws[10].ensure(nunits * 4)) != 0) return rc;
+        uint16_t* d_dist = c->ws[3].as<uint16_t>();
+        uint32_t* d_mt = c->ws[4].as<uint32_t>();
+        d_tok = c->ws[5].as<uint32_t>();
+        d_blk = c->ws[6].as<BlockMeta>();
+        d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
+        d_ntok = c->ws[10].as<uint32_t>();
+        const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
+        if (cfg.chain == 0) {
+            ZB_CUDA(cudaMemsetAsync(d_mt, 0, n * 4, s));
         } else {
-            ZB_CUDA(cudaMemsetAsync(d_chunks, 0, nchunks * sizeof(ChunkMeta), s));
+            // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
+            if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
+            else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
+            ZB_LAUNCH(k_lz_match, (unsigned)((n + 255) / 256), 256, 0, s, d_buf, total, dict, d_dist, d_mt, (int)cfg.chain, (int)cfg.nice);
         }
-        ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0, force_mark);
-        ZB_LAUNCH(k_scan, 1, 1024, 0, s, nchunks, d_chunks, hdr_len, d_payload);
-        ZB_LAUNCH(k_huff_pack, (unsigned)nchunks, kPackThreads, 0, s, d_src, n, d_tok, d_blk, d_codes, d_hdr, d_chunks, d_out, cap,
-                  last_is_final, force_mark, d_err);
+        ZB_LAUNCH(k_lz_parse, (unsigned)((nunits + kParseWarps - 1) / kParseWarps), kParseWarps * 32, 0, s, d_src, n, d_mt,
+                  d_tok, d_ntok, d_hist, cfg.kind, (uint32_t)cfg.lazy);
+        ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, n, d_blk, d_hist,
+                  d_codes, d_hdr, P.strategy == 4 ? 1 : 0);
     }
-    ZB_LAUNCH(k_frame, 1, 32, 0, s, d_out, cap, hdr_len, d_payload, d_sums, n, level, wrap, flags, d_total);
+    ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0, force_mark);
+    ZB_LAUNCH(k_scan, 1, 1024, 0, s, nchunks, d_chunks, d_start, start_add, d_end);
+    ZB_LAUNCH(k_huff_pack, (unsigned)nchunks, kPackThreads, 0, s, d_src, n, d_tok, d_ntok, d_blk, d_codes, d_hdr, d_chunks, d_out, cap,
+              last_is_final, force_mark, d_err);
     ZB_CHECK_LAUNCH();
     return 0;
 }
@@ -865,51 +1038,136 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
         set_error("zb200_deflate: bad argument");
         return ZB_STREAM_ERROR;
     }
+    static bool attr = false;
+    if (!attr) {
+        ZB_CUDA(cudaFuncSetAttribute(k_lz_link<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
+        ZB_CUDA(cudaFuncSetAttribute(k_lz_link<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
+        attr = true;
+    }
+    if (level < 0) level = 6;
+    DeflateParams P;
+    P.cfg = h_levels[level]; P.level = level; P.wrap = wrap; P.flags = flags;
+    P.strategy = (flags >> 8) & 7;                              // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
+    if (P.strategy == 2 && P.cfg.kind != 0) { P.cfg.chain = 0; P.cfg.kind = 1; }   // literals only (deflate.c:1490)
+    const int force_mark = (flags & ZB200I_DEFLATE_FORCE_MARK) ? 1 : 0;
+    const int last_is_final = (flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
+    const uint64_t hdr_len = (flags & ZB200_DEFLATE_NO_HEADER) ? 0 : wrap == ZB200_WRAP_ZLIB ? 2 : wrap == ZB200_WRAP_GZIP ? 10 : 0;
+    const uint64_t n = src_len;
+    const uint64_t slab = (uint64_t)kSlabChunks * kChunk;
+    const uint64_t nslabs = n ? (n + slab - 1) / slab : 0;
+
     Ctx* c = ctx_acquire((cudaStream_t)stream);
     if (!c) return ZB_MEM_ERROR;
     cudaStream_t s = pick_stream(c, stream);
     const size_t cap = *dst_len;
     do {
-        // bring [dict][src] to one contiguous device range
-        const uint8_t* d_buf;
-        if (dict_len == 0) {
-            d_buf = to_device(c, src, src_len, s, &rc);
-            if (rc) break;
-        } else if (classify(src) == kDevice && classify(dict) == kDevice &&
-                   (const uint8_t*)dict + dict_len == (const uint8_t*)src) {
-            d_buf = (const uint8_t*)dict;
-        } else {
-            if ((rc = c->in.ensure(dict_len + src_len + 64)) != 0) break;
-            cudaError_t e = cudaMemcpyAsync(c->in.p, dict, dict_len, cudaMemcpyDefault, s);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(c->in.as<uint8_t>() + dict_len, src, src_len, cudaMemcpyDefault, s);
-            if (e != cudaSuccess) { set_error("input staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
-            d_buf = c->in.as<uint8_t>();
-        }
+        const bool src_on_host = n != 0 && classify(src) != kDevice;
         const bool dst_on_host = classify(dst) != kDevice;
+        if ((rc = c->ensure_aux((int)(2 * nslabs + 2))) != 0) break;
+        cudaStream_t s_in = c->aux[0], s_out = c->aux[1];
+        cudaEvent_t* ev_in = c->evs;
+        cudaEvent_t* ev_done = c->evs + nslabs;
+        cudaError_t e = cudaSuccess;
+        // ---- [dict][src] as one contiguous device range ----
+        const uint8_t* d_buf;
+        bool stage_slabs = false;                               // source slabs still have to be copied in
+        if (n == 0) {
+            if ((rc = c->in.ensure(64)) != 0) break;
+            d_buf = c->in.as<uint8_t>();
+            dict_len = 0;
+        } else if (!src_on_host && (dict_len == 0 || (classify(dict) == kDevice && (const uint8_t*)dict + dict_len == (const uint8_t*)src))) {
+            d_buf = (const uint8_t*)src - dict_len;
+        } else {
+            if ((rc = c->in.ensure(dict_len + n + 64)) != 0) break;
+            d_buf = c->in.as<uint8_t>();
+            stage_slabs = true;
+            cudaStreamWaitEvent(s_in, c->idle, 0);              // the staging buffer may still be read by the previous borrower
+            if (!src_on_host) {                                 // device source produced on the caller's stream
+                cudaEventRecord(c->evs[2 * nslabs], s);
+                cudaStreamWaitEvent(s_in, c->evs[2 * nslabs], 0);
+            }
+            if (dict_len) {
+                e = cudaMemcpyAsync(c->in.p, dict, dict_len, cudaMemcpyDefault, s_in);
+                if (e != cudaSuccess) { set_error("dictionary staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+            }
+        }
         uint8_t* d_out = (uint8_t*)dst;
         if (dst_on_host) {
             if ((rc = c->out.ensure(cap + 16)) != 0) break;
             d_out = c->out.as<uint8_t>();
         }
         if ((rc = c->small.ensure(256)) != 0) break;
-        if ((rc = c->ensure_pinned(256)) != 0) break;
+        if ((rc = c->ws[1].ensure((nslabs + 2) * 8)) != 0) break;
+        if ((rc = c->ensure_pinned((nslabs + 8) * 8)) != 0) break;
         uint64_t* d_total = c->small.as<uint64_t>();
         uint32_t* d_sums = c->small.as<uint32_t>() + 2;
         uint32_t* d_err = c->small.as<uint32_t>() + 4;
-        if ((rc = deflate_launch(c, d_buf, dict_len, src_len, d_out, cap, level, wrap, flags, d_total, d_sums, d_err, s)) != 0) break;
-        cudaError_t e = cudaMemcpyAsync(c->pinned, c->small.p, 32, cudaMemcpyDeviceToHost, s);
+        uint64_t* d_pos = c->ws[1].as<uint64_t>();              // d_pos[i] = end of slab i in the output
+        uint64_t* h_res = (uint64_t*)c->pinned;                 // [0..3] result words, [4..] slab ends
+        uint64_t* h_pos = h_res + 4;
+        if ((e = cudaMemsetAsync(d_err, 0, 4, s)) != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+
+        // ---- slabs: copy in (own stream) -> kernels (s) -> slab end to the host ----
+        const uint8_t* d_src = d_buf + dict_len;
+        if (n == 0) {
+            ZB_LAUNCH(k_empty_payload, 1, 32, 0, s, d_out, cap, hdr_len, !last_is_final, force_mark, d_pos);
+        }
+        for (uint64_t i = 0; i < nslabs; i++) {
+            const uint64_t off = i * slab, len = n - off < slab ? n - off : slab;
+            if (stage_slabs) {
+                e = cudaMemcpyAsync((uint8_t*)d_src + off, (const uint8_t*)src + off, len, cudaMemcpyDefault, s_in);
+                if (e == cudaSuccess) e = cudaEventRecord(ev_in[i], s_in);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev_in[i], 0);
+                if (e != cudaSuccess) { set_error("input staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+            }
+            const uint64_t dlen = i == 0 ? dict_len : kWindow;  // later slabs see the tail of the previous one
+            const bool last = i == nslabs - 1;
+            rc = deflate_slab_launch(c, d_src + off - dlen, dlen, len, d_out, cap, P, last && last_is_final, last ? force_mark : 0,
+                                     i ? d_pos + i - 1 : nullptr, i ? 0 : hdr_len, d_pos + i, d_err, s);
+            if (rc) break;
+            if (dst_on_host && !last) {
+                e = cudaMemcpyAsync(h_pos + i, d_pos + i, 8, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaEventRecord(ev_done[i], s);
+                if (e != cudaSuccess) { set_error("slab bookkeeping failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+            }
+        }
+        if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(s_in); break; }
+        // ---- checksums of the uncompressed data (read_buf, deflate.c:956-981), header, trailer ----
+        if ((rc = checksum_launch(c, d_src, n, d_sums, s)) != 0) { cudaStreamSynchronize(s); break; }
+        ZB_LAUNCH(k_frame, 1, 32, 0, s, d_out, cap, hdr_len, d_pos + (nslabs ? nslabs - 1 : 0), d_sums, n, level, wrap, flags, d_total);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_res, c->small.p, 32, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { set_error("deflate launch failed: %s", cudaGetErrorString(e)); cudaStreamSynchronize(s); rc = ZB_STREAM_ERROR; break; }
+
+        // ---- copy out finished slabs while later ones are still running ----
+        uint64_t copied = hdr_len;                              // out[0, hdr_len) is written last, by k_frame
+        if (dst_on_host) {
+            for (uint64_t i = 0; i + 1 < nslabs; i++) {
+                if ((e = cudaEventSynchronize(ev_done[i])) != cudaSuccess) break;
+                const uint64_t end = h_pos[i];
+                if (end > cap) break;                           // does not fit: reported below from the total
+                if (end > copied) e = cudaMemcpyAsync((uint8_t*)dst + copied, d_out + copied, end - copied, cudaMemcpyDeviceToHost, s_out);
+                if (e != cudaSuccess) break;
+                copied = end;
+            }
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { set_error("deflate failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
-        const uint64_t total = *(const uint64_t*)c->pinned;
-        const uint32_t* r32 = (const uint32_t*)c->pinned;
+        if (e != cudaSuccess) { set_error("deflate failed: %s", cudaGetErrorString(e)); cudaStreamSynchronize(s_out); rc = ZB_STREAM_ERROR; break; }
+        const uint64_t total = h_res[0];
+        const uint32_t* r32 = (const uint32_t*)h_res;
         if (crc) *crc = r32[2];
         if (adler) *adler = r32[3];
-        if (r32[4] != 0) { set_error("internal error: %u chunks packed to a size other than planned", r32[4]); rc = ZB_STREAM_ERROR; break; }
+        if (r32[4] != 0) { cudaStreamSynchronize(s_out); set_error("internal error: %u chunks packed to a size other than planned", r32[4]); rc = ZB_STREAM_ERROR; break; }
         *dst_len = (size_t)total;
-        if (total > cap) { rc = ZB_BUF_ERROR; set_error("output buffer too small: need %llu, have %zu", (unsigned long long)total, cap); break; }
+        if (total > cap) {
+            cudaStreamSynchronize(s_out);
+            rc = ZB_BUF_ERROR; set_error("output buffer too small: need %llu, have %zu", (unsigned long long)total, cap);
+            break;
+        }
         if (dst_on_host && total) {
-            e = cudaMemcpyAsync(dst, d_out, total, cudaMemcpyDeviceToHost, s);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (total > copied) e = cudaMemcpyAsync((uint8_t*)dst + copied, d_out + copied, total - copied, cudaMemcpyDeviceToHost, s_out);
+            if (e == cudaSuccess && hdr_len) e = cudaMemcpyAsync(dst, d_out, hdr_len, cudaMemcpyDeviceToHost, s_out);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s_out);
             if (e != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         }
     } while (0);

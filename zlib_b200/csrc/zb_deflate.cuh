@@ -4,26 +4,28 @@
 
 namespace zb {
 
-constexpr uint32_t kChunk = ZB200_CHUNK;         // input bytes parsed by one warp / packed by one CTA
+constexpr uint32_t kChunk = ZB200_CHUNK;         // input bytes linked by one CTA / packed by one CTA; ends byte-aligned
+constexpr uint32_t kUnit = 16384;                // input bytes parsed by one warp (matches never cross a unit boundary)
+constexpr uint32_t kUnitsPerChunk = kChunk / kUnit;
+constexpr uint32_t kBlockUnits = 4;              // units per DEFLATE block: 64 KiB of input (the reference closes a
+constexpr uint32_t kBlockBytes = kUnit * kBlockUnits;   // block every 16 Ki symbols, about 45-60 KiB of text, deflate.c:291)
+constexpr uint32_t kBlocksPerChunk = kChunk / kBlockBytes;
 constexpr uint32_t kWindow = 32768;              // DEFLATE history (h/zconf.h MAX_WBITS = 15)
 constexpr uint32_t kMinMatch = 3, kMaxMatch = 258;
-constexpr uint32_t kBlockTokens = 16384;         // symbols per DEFLATE block (lit_bufsize, deflate.c:291)
-constexpr uint32_t kMaxBlocks = 10;              // block slots per chunk
+constexpr uint32_t kHistSize = 320;              // 0..287 literal/length, 288..319 distance
 constexpr uint32_t kHdrWords = 144;              // dynamic-block header, <= 4495 bits
 constexpr uint32_t kTooFar = 4096;               // deflate.c:108-110
+constexpr uint32_t kSlabChunks = 888;            // chunks per pipeline slab (2 waves of 3 link CTAs on 148 SMs)
 
 // configuration_table of the reference (deflate.c:137-149); kind 0 stored, 1 greedy, 2 lazy
 struct LevelCfg { uint16_t good, lazy, nice, chain; int kind; };
 
-// One DEFLATE block, produced by the parse kernel, completed by the code-construction kernel.
+// One DEFLATE block = kBlockUnits consecutive units; filled in by the code-construction kernel.
 struct BlockMeta {
-    uint32_t tok_start;                          // index into the chunk's token array
-    uint32_t tok_count;
-    uint32_t in_start, in_len;                   // input span (relative to the chunk) the tokens cover
+    uint32_t in_len;                             // input bytes the block covers
     uint32_t type;                               // 0 stored, 1 fixed, 2 dynamic
     uint32_t body_bits;                          // bits after the 3 header bits (types 1, 2)
     uint32_t hdr_bits;                           // dynamic header length in bits (type 2)
-    uint32_t pad;
 };
 
 struct ChunkMeta {

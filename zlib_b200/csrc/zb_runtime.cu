@@ -81,6 +81,35 @@ int Ctx::ensure_pinned(size_t bytes)
     return 0;
 }
 
+int Ctx::ensure_aux(int nevents)
+{
+    for (int i = 0; i < 2; i++) {
+        if (!aux[i] && cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError(); aux[i] = nullptr;
+            set_error("copy stream creation failed");
+            return ZB_MEM_ERROR;
+        }
+    }
+    if (nevents > nev) {
+        const int want = nevents + 16;
+        cudaEvent_t* ne = (cudaEvent_t*)calloc((size_t)want, sizeof(cudaEvent_t));
+        if (!ne) { set_error("out of host memory"); return ZB_MEM_ERROR; }
+        for (int i = 0; i < nev; i++) ne[i] = evs[i];
+        for (int i = nev; i < want; i++) {
+            if (cudaEventCreateWithFlags(&ne[i], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                for (int k = nev; k < i; k++) cudaEventDestroy(ne[k]);
+                free(ne);
+                set_error("event creation failed");
+                return ZB_MEM_ERROR;
+            }
+        }
+        free(evs);
+        evs = ne; nev = want;
+    }
+    return 0;
+}
+
 int ensure_init()
 {
     if (g_state == 1) {
