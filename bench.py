@@ -235,10 +235,12 @@ def main():
     prof = lib.profile_report()
     lib.profile(False)
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 1))
-    dom_ms = dom[1][0] / max(1, dom[1][1])
+    dom_launches = max(1, dom[1][1])                    # one launch per pipeline slab
+    dom_ms = dom[1][0] / dom_launches                   # average launch duration of the dominant kernel
     peaks, peak_kind = measured_peaks()
-    algo_bytes = n + clen1
-    achieved = algo_bytes / dom_ms / 1e6 if dom_ms > 0 else 0.0
+    algo_bytes = n + clen1                              # every input byte read once, every output byte written once
+    launch_bytes = algo_bytes / dom_launches            # algorithmic bytes one launch (one slab) accounts for
+    achieved = launch_bytes / dom_ms / 1e6 if dom_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -248,8 +250,9 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm_gbs"], 5), "traffic": traffic, "peak_source": peak_kind,
-                "algorithmic_bytes": algo_bytes, "kernel_ms": round(dom_ms, 4),
-                "kernel_share_of_step": round(dom_ms / sum(v[0] for v in prof.values()), 4) if prof else None,
+                "algorithmic_bytes": algo_bytes, "algorithmic_bytes_per_launch": round(launch_bytes),
+                "launches_per_step": dom_launches, "kernel_ms": round(dom_ms, 4),
+                "kernel_share_of_step": round(dom[1][0] / sum(v[0] for v in prof.values()), 4) if prof else None,
                 "kernels_ms": {k.replace("zb::", ""): round(v[0], 4) for k, v in prof.items()}}
 
     # ---- end to end through compress2 with host buffers (H2D + kernels + D2H inside the timed region) ----

@@ -249,15 +249,16 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t* a)
 // match, "strictly longer wins" and the nice_match cut-off are the reference's (deflate.c:1090-1160);
 // the chain is the dist16 links.  All addressing is one 64-bit pointer per thread plus 32-bit offsets,
 // and every comparison is a 4-byte word (two aligned loads + funnel shift).
-__global__ void __launch_bounds__(256)
-k_lz_match(const uint8_t* __restrict__ buf, uint64_t total, uint64_t dict, const uint16_t* __restrict__ dist16,
+__global__ void __launch_bounds__(256, 8)
+k_lz_match(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
            uint32_t* __restrict__ mt, int max_chain, int nice)
 {
-    const uint64_t rel = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    const uint64_t p = dict + rel;
+    // a slab (plus its dictionary) is far below 2 GiB, so positions are 32-bit
+    const uint32_t rel = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t p = dict + rel;
     if (p >= total) return;
-    const uint64_t unit_end = min(total, dict + (rel / kUnit + 1) * kUnit);    // matches stay inside the parse unit
-    const uint32_t maxlen = (uint32_t)min((uint64_t)kMaxMatch, unit_end - p);
+    const uint32_t unit_end = min(total, dict + (rel / kUnit + 1) * kUnit);    // matches stay inside the parse unit
+    const uint32_t maxlen = min(kMaxMatch, unit_end - p);
     if (maxlen < kMinMatch) { mt[rel] = 0; return; }
     const uint32_t nice_eff = min((uint32_t)nice, maxlen);
     if (p + kMaxMatch + 8 > total) {                            // tail of the input: clamped loads
@@ -352,14 +353,12 @@ k_lz_parse(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restri
         // known, so 5 rounds cover any window (a serial walk needs up to 32 dependent shuffles).
         const uint32_t lim = min(32u, ulen - pos);
         const uint32_t land = lane + step;                      // where this position's token ends
-        uint32_t J = land < lim ? land : 32u;                   // 32 = leaves the window
+        uint32_t J = land < lim ? land : (uint32_t)lane;        // a token that leaves the window jumps to itself
         uint32_t mask = 1u;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const uint32_t img = (((mask >> lane) & 1u) && J < 32u) ? (1u << J) : 0u;
-            mask |= __reduce_or_sync(kFullMask, img);
-            const uint32_t Jn = __shfl_sync(kFullMask, J, J & 31u);
-            if (J < 32u) J = Jn;
+            mask |= __reduce_or_sync(kFullMask, ((mask >> lane) & 1u) << J);
+            J = __shfl_sync(kFullMask, J, J);
         }
         const uint32_t cur = __shfl_sync(kFullMask, land, 31 - __clz(mask));
         if (mask & (1u << lane)) {
@@ -1010,7 +1009,7 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
             // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
             if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
             else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
-            ZB_LAUNCH(k_lz_match, (unsigned)((n + 255) / 256), 256, 0, s, d_buf, total, dict, d_dist, d_mt, (int)cfg.chain, (int)cfg.nice);
+            ZB_LAUNCH(k_lz_match, (unsigned)((n + 255) / 256), 256, 0, s, d_buf, (uint32_t)total, (uint32_t)dict, d_dist, d_mt, (int)cfg.chain, (int)cfg.nice);
         }
         ZB_LAUNCH(k_lz_parse, (unsigned)((nunits + kParseWarps - 1) / kParseWarps), kParseWarps * 32, 0, s, d_src, n, d_mt,
                   d_tok, d_ntok, d_hist, cfg.kind, (uint32_t)cfg.lazy);

@@ -28,6 +28,7 @@
 #include "zb200_internal.h"
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 
 namespace zb {
 
@@ -217,7 +218,7 @@ __device__ __forceinline__ uint32_t copy_match(Out& o, uint32_t len, uint32_t di
 
 // Decodes symbols of the current block until end-of-block or a stop condition (the work of
 // inflate_fast, inffast.c:67-302, plus the careful tail of inflate.c:951-1076).
-__device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st, bool streaming)
+__device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st, bool streaming, bool one)
 {
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -239,6 +240,7 @@ __device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st,
             if (o.pos >= o.cap) { if (streaming) b.used = mark; return kShortOut; }
             if (lane == 0) o.p[o.pos] = (uint8_t)(e >> 16);
             o.pos++;
+            if (one) return kRunning;
             continue;
         }
         if (kind == kEob) return kDone;
@@ -271,7 +273,80 @@ __device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st,
             st->copy_len = mlen - done; st->copy_dist = dist;
             return kShortOut;
         }
+        if (one) return kRunning;
     }
+}
+
+// The same decode without the bookkeeping, for the stretch of a block where neither buffer can run out: at
+// least 72 valid input bits beyond the bit buffer (a symbol takes at most 48) and 258 bytes of room (the
+// reference's inflate_fast makes the same deal, inffast.c:24-30,67-70).  Bit accounting is one 32-bit counter,
+// there are no per-field input checks and no state for resuming.  Anything unusual -- a code longer than the
+// primary table, an invalid symbol, a distance beyond the history -- rewinds to the start of that symbol and
+// returns kRunning, and the careful decoder above deals with it (and produces the error, if it is one).
+// Returns kDone at end-of-block, kRunning otherwise.
+__device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t* in)
+{
+    const int lane = threadIdx.x & 31;
+    uint64_t buf = b.buf;
+    int cnt = b.cnt;
+    uint32_t nextw = b.nextw;
+    const uint32_t nwords = b.nwords;
+    const uint32_t* words = b.words;
+    uint8_t* p = o.p + o.pos;
+    const uint64_t room64 = o.cap - o.pos, back64 = o.pos + o.hist;
+    const uint32_t room = room64 > 0x7fffffffu ? 0x7fffffffu : (uint32_t)room64;
+    const uint32_t back = back64 > 0x7fffffffu ? 0x7fffffffu : (uint32_t)back64;   // bytes behind p at entry
+    uint32_t consumed = 0, produced = 0, mark = 0;
+    bool rewind = false;
+    Stop result = kRunning;
+    for (;;) {
+        if (nextw + 3 > nwords || produced + 258 > room) break;
+        mark = consumed;
+        if (cnt <= 32) { buf |= (uint64_t)__ldg(words + nextw) << cnt; nextw++; cnt += 32; }
+        const uint32_t e = t->lit[(uint32_t)buf & (kLitSize - 1)];
+        const uint32_t len = e & 15u;
+        if (len == 0) { rewind = true; break; }
+        buf >>= len; cnt -= (int)len; consumed += len;
+        const uint32_t kind = (e >> 8) & 3u;
+        if (kind == kLit) {
+            if (lane == 0) p[produced] = (uint8_t)(e >> 16);
+            produced++;
+            continue;
+        }
+        if (kind != kBase) {
+            if (kind == kEob) { result = kDone; break; }
+            rewind = true; break;
+        }
+        const uint32_t xl = (e >> 4) & 15u;
+        const uint32_t mlen = (e >> 16) + ((uint32_t)buf & ((1u << xl) - 1u));
+        buf >>= xl; cnt -= (int)xl; consumed += xl;
+        if (cnt <= 32) { buf |= (uint64_t)__ldg(words + nextw) << cnt; nextw++; cnt += 32; }
+        const uint32_t de = t->dist[(uint32_t)buf & (kDistSize - 1)];
+        const uint32_t dl = de & 15u;
+        if (dl == 0 || ((de >> 8) & 3u) != kBase) { rewind = true; break; }
+        buf >>= dl; cnt -= (int)dl; consumed += dl;
+        const uint32_t xd = (de >> 4) & 15u;
+        const uint32_t dist = (de >> 16) + ((uint32_t)buf & ((1u << xd) - 1u));
+        buf >>= xd; cnt -= (int)xd; consumed += xd;
+        if (dist > back + produced) { rewind = true; break; }
+        uint8_t* d = p + produced;
+        const uint8_t* s = d - dist;
+        __syncwarp();
+        if (dist >= mlen) {
+            for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i];
+        } else {
+            for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i % dist];
+        }
+        __syncwarp();
+        produced += mlen;
+    }
+    o.pos += produced;
+    if (rewind) {
+        seek_bits(b, in, b.used + mark);
+    } else {
+        b.buf = buf; b.cnt = cnt; b.nextw = nextw; b.used += consumed;
+    }
+    return result;
 }
 
 // Adds out[0..n) to the running Adler-32 (s1, s2) of the stream; all lanes cooperate.
@@ -461,7 +536,10 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
             if (st->stored_left == 0) { seek_bits(b, in, b.used); mode = kModeBlock; }
             else stop = (c == ain) ? kShortIn : kShortOut;
         } else if (mode == kModeCodes) {
-            stop = decode_block(b, o, t, st, streaming);
+            if (!streaming) {                             // batch path: lean loop, one careful symbol whenever it stops short
+                if (decode_fast(b, o, t, in) == kDone) { mode = kModeBlock; continue; }
+            }
+            stop = decode_block(b, o, t, st, streaming, !streaming);
             if (stop == kDone) { stop = kRunning; mode = kModeBlock; }
             else if (stop == kShortOut && st->copy_len) mode = kModeCopy;
         } else if (mode == kModeCopy) {
