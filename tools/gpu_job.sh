@@ -1,2 +1,3 @@
-python -m pytest tests/test_inflate_gpu.py tests/test_stream_gpu.py -m gpu -x -q 2>&1 | tail -4
-timeout 300 python tools/probe_codec.py 1024 2>&1 | grep inflate
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/bench4.json 2> gpurun_out/bench4.log; echo bench rc=$?
+tail -4 gpurun_out/bench4.log | cut -c1-400

@@ -187,199 +187,237 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// K1b: longest match per position
+// K1b: match search + parse, one thread per 128-byte sub-unit, window staged in shared memory
 // ------------------------------------------------------------------------------------------
-struct WordView {
-    const uint32_t* words; uint32_t mis; uint64_t last;         // last valid word index
-    __device__ __forceinline__ uint32_t ld32(uint64_t p) const  // 4 bytes at byte position p (little endian)
-    {
-        const uint64_t q = p + mis, w = q >> 2;
-        const uint32_t a = __ldg(words + w), b = __ldg(words + min(w + 1, last));
-        return __funnelshift_r(a, b, (uint32_t)(q & 3) * 8);
-    }
-};
+// A parse only needs a match where a token starts (one position in three on text), and a kernel with one thread per
+// position both searches everywhere and leaves lanes idle while a neighbour extends a match (round 1 measured it:
+// 4x the instructions of this kernel).  This kernel works the way deflate_fast / deflate_slow do -- search, emit,
+// skip the matched bytes (deflate.c:1448-1674) -- with one thread per 128-byte sub-unit, so every lane is always
+// searching a position that matters.
+//   * One CTA per 64 KiB block: the block, the 32 KiB in front of it and 272 bytes of lookahead are staged in
+//     shared memory once (16-byte loads); every candidate comparison then reads shared memory.  Only the chain
+//     links (dist16) come from global memory; they are L2 hits because the CTAs in flight cover a few tens of MiB.
+//   * Sub-units start parsing at their boundary without knowing where the previous sub-unit's last token ends.
+//     A match may run past the end of its sub-unit; afterwards a prefix maximum over the threads' end positions
+//     gives every thread the frontier it really starts at, and it drops the tokens in front of it -- a match that
+//     straddles the frontier is shortened (the tail of a match is a match at the same distance) or, below three
+//     bytes, turned into literals.
+//   * Tokens go to a private region per thread, then each warp copies its 32 regions into the block's contiguous
+//     token array with coalesced stores and tallies the block histogram on the way (dense shared-memory atomics).
+constexpr int kWalkThreads = 512;
+constexpr uint32_t kSub = kBlockBytes / kWalkThreads;           // 128 input bytes per thread
+constexpr uint32_t kSubSlots = kSub + 2;                        // token slots per thread; two spare in front for the fix-up
+constexpr uint32_t kWalkPad = 272;                              // lookahead behind the block (kMaxMatch + word slack)
+// Shared-memory image of the window: rows of 128 bytes followed by one pad word that repeats the first word of
+// the next row.  The lanes of a warp sit 128 bytes apart (one sub-unit each); with 132-byte rows their words fall
+// into 32 different banks, and an unaligned 4-byte read that starts in the last bytes of a row still finds its
+// continuation in the pad word.
+constexpr uint32_t kWalkRows = (kWindow + kBlockBytes + kWalkPad + 16 + 127) / 128 + 1;
+constexpr uint32_t kWalkSmem = kWalkRows * 132;
+__device__ __forceinline__ uint32_t smap(uint32_t off) { return off + ((off >> 7) << 2); }
 
-// Bounds-checked search (every load clamped to the buffer): used for the last few hundred positions
-// of the input, where the fast path's 4-byte loads could run past the end.
-__device__ uint32_t match_careful(const uint8_t* __restrict__ buf, uint64_t total, uint64_t p, uint32_t maxlen,
-                                  const uint16_t* __restrict__ dist16, int max_chain, uint32_t nice_eff)
+__device__ __forceinline__ uint32_t lds32u(const uint8_t* s_mem, uint32_t off)   // 4 bytes at any window-image offset
 {
-    WordView wv;
-    wv.mis = (uint32_t)((uintptr_t)buf & 3);
-    wv.words = reinterpret_cast<const uint32_t*>(buf - wv.mis);
-    wv.last = ((wv.mis + total + 3) >> 2) - 1;
-    uint32_t best_len = kMinMatch - 1, best_dist = 0, acc = 0;
-    uint32_t d = dist16[p];
-    const uint32_t head4 = wv.ld32(p);
-    int chain = max_chain;
-    while (d != 0 && chain-- > 0) {
-        acc += d;
-        if (acc > kWindow) break;
-        const uint64_t cand = p - acc;
-        // quick rejects: the byte that must match to beat best_len, then the first three (deflate.c:1121-1124)
-        if (buf[cand + best_len] == buf[p + best_len] && ((wv.ld32(cand) ^ head4) & 0xffffffu) == 0) {
-            uint32_t len = 3;
-            while (len < maxlen) {
-                const uint32_t x = wv.ld32(p + len) ^ wv.ld32(cand + len);
-                if (x) { len += (__ffs(x) - 1) >> 3; break; }
-                len += 4;
-            }
-            if (len > maxlen) len = maxlen;
-            if (len > best_len) {
-                best_len = len; best_dist = acc;
-                if (len >= nice_eff) break;
-            }
-        }
-        d = dist16[cand];
-    }
-    return best_len >= kMinMatch ? ((best_dist << 16) | best_len) : 0u;
+    const uint32_t m = smap(off);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(s_mem + (m & ~3u));
+    return __funnelshift_r(w[0], w[1], (m & 3u) * 8);
 }
 
-// 4 bytes at an arbitrary address, little endian: two aligned loads and a funnel shift.  Reads up to the
-// end of the aligned word that holds byte a+3.
-__device__ __forceinline__ uint32_t ld32u(const uint8_t* a)
-{
-    const uintptr_t u = (uintptr_t)a;
-    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3));
-    const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>((u + 3) & ~(uintptr_t)3));
-    return __funnelshift_r(lo, hi, (uint32_t)(u & 3) * 8);
-}
+struct Found { uint32_t len, dist; };
 
-// One thread per position.  Candidate order, the quick reject on the byte that would extend the best
-// match, "strictly longer wins" and the nice_match cut-off are the reference's (deflate.c:1090-1160);
-// the chain is the dist16 links.  All addressing is one 64-bit pointer per thread plus 32-bit offsets,
-// and every comparison is a 4-byte word (two aligned loads + funnel shift).
-__global__ void __launch_bounds__(256, 8)
-k_lz_match(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
-           uint32_t* __restrict__ mt, int max_chain, int nice)
+// longest_match (deflate.c:1027-1168) at window offset `o` (= absolute position gp): candidates from the dist16 chain,
+// quick reject on the word that ends at the byte a better match must reach, strictly longer wins, stop at nice.
+__device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, const uint16_t* __restrict__ dp, uint32_t maxlen,
+                                             int chain, uint32_t nice_eff, uint32_t prev_len)
 {
-    // a slab (plus its dictionary) is far below 2 GiB, so positions are 32-bit
-    const uint32_t rel = blockIdx.x * 256u + threadIdx.x;
-    const uint32_t p = dict + rel;
-    if (p >= total) return;
-    const uint32_t unit_end = min(total, dict + (rel / kUnit + 1) * kUnit);    // matches stay inside the parse unit
-    const uint32_t maxlen = min(kMaxMatch, unit_end - p);
-    if (maxlen < kMinMatch) { mt[rel] = 0; return; }
-    const uint32_t nice_eff = min((uint32_t)nice, maxlen);
-    if (p + kMaxMatch + 8 > total) {                            // tail of the input: clamped loads
-        mt[rel] = match_careful(buf, total, p, maxlen, dist16, max_chain, nice_eff);
-        return;
-    }
-    const uint8_t* pp = buf + p;
-    const uint16_t* dp = dist16 + p;
+    Found f{kMinMatch - 1, 0};
+    if (prev_len > f.len) f.len = prev_len;                     // deflate_slow: only a longer match is of interest
     uint32_t acc = dp[0];
-    uint32_t best_len = kMinMatch - 1, best_dist = 0;
-    if (acc != 0) {
-        uint32_t qoff = 0, qmask = 0xffffffu;                   // quick-reject word: offset into the match, bytes that must agree
-        uint32_t hq = ld32u(pp);
-        int chain = max_chain;
-        do {
-            if (acc > kWindow) break;
-            const uint8_t* cp = pp - acc;
-            const uint32_t x = ld32u(cp + qoff) ^ hq;
-            if ((x & qmask) == 0) {
-                uint32_t len;
-                if (qoff == 0 && x != 0) len = 3;               // first three agree, the fourth does not
-                else {
-                    len = qoff == 0 ? 4u : 0u;
-                    while (len < maxlen) {
-                        const uint32_t y = ld32u(pp + len) ^ ld32u(cp + len);
-                        if (y) { len += (uint32_t)(__ffs(y) - 1) >> 3; break; }
-                        len += 4;
-                    }
-                    len = min(len, maxlen);
+    if (acc == 0 || f.len >= maxlen) return f;
+    uint32_t qoff = f.len >= 4 ? f.len - 3 : 0u, qmask = f.len >= 3 ? 0xffffffffu : 0xffffffu;
+    uint32_t hq = lds32u(s_mem, o + qoff);
+    do {
+        if (acc > kWindow) break;
+        const uint32_t co = o - acc;
+        const uint32_t x = lds32u(s_mem, co + qoff) ^ hq;
+        if ((x & qmask) == 0) {
+            uint32_t len;
+            if (qoff == 0 && x != 0) len = 3;                   // first three agree, the fourth does not
+            else {
+                len = qoff == 0 ? 4u : 0u;
+                while (len < maxlen) {
+                    const uint32_t y = lds32u(s_mem, o + len) ^ lds32u(s_mem, co + len);
+                    if (y) { len += (uint32_t)(__ffs(y) - 1) >> 3; break; }
+                    len += 4;
                 }
-                if (len > best_len) {
-                    best_len = len; best_dist = acc;
-                    if (len >= nice_eff) break;
-                    qoff = len >= 4 ? len - 3 : 0u;             // bytes len-3 .. len must agree to do better
-                    qmask = 0xffffffffu;
-                    hq = ld32u(pp + qoff);
-                }
+                len = min(len, maxlen);
             }
-            const uint32_t d = *(dp - acc);
-            if (d == 0) break;
-            acc += d;
-        } while (--chain > 0);
-    }
-    mt[rel] = best_len >= kMinMatch ? ((best_dist << 16) | best_len) : 0u;
+            if (len > f.len) {
+                f.len = len; f.dist = acc;
+                if (len >= nice_eff) break;
+                qoff = len >= 4 ? len - 3 : 0u;
+                qmask = 0xffffffffu;
+                hq = lds32u(s_mem, o + qoff);
+            }
+        }
+        const uint32_t d = *(dp - acc);
+        if (d == 0) break;
+        acc += d;
+    } while (--chain > 0);
+    return f;
 }
 
-// ------------------------------------------------------------------------------------------
-// K1c: parse (greedy / lazy), tokens, histograms
-// ------------------------------------------------------------------------------------------
-constexpr int kParseWarps = 4;
-
-__global__ void __launch_bounds__(kParseWarps * 32)
-k_lz_parse(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restrict__ mt, uint32_t* __restrict__ tok,
-           uint32_t* __restrict__ unit_ntok, uint32_t* __restrict__ unit_hist, int kind, uint32_t max_lazy)
+__global__ void __launch_bounds__(kWalkThreads, 2)
+k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
+          uint32_t* __restrict__ tok_tmp, uint32_t* __restrict__ tok, uint32_t* __restrict__ blk_ntok,
+          uint32_t* __restrict__ blk_hist, int kind, int max_chain, uint32_t nice, uint32_t max_lazy, uint32_t good)
 {
-    __shared__ uint32_t s_hist[kParseWarps][kHistSize];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint64_t nunits = (n + kUnit - 1) / kUnit;
-    const uint64_t u = (uint64_t)blockIdx.x * kParseWarps + warp;
-    if (u >= nunits) return;
-    uint32_t* hist = s_hist[warp];
-    for (int i = lane; i < (int)kHistSize; i += 32) hist[i] = 0;
-    __syncwarp();
+    extern __shared__ __align__(16) uint8_t s_mem[];
+    __shared__ uint32_t s_hist[kHistSize];
+    __shared__ uint32_t s_end[kWalkThreads];                    // end position of each thread's walk, then its prefix maximum
+    __shared__ uint32_t s_cnt[kWalkThreads];                    // kept tokens per thread, then their exclusive prefix sum
+    __shared__ uint32_t s_first[kWalkThreads];
+    __shared__ uint32_t s_wsum[kWalkThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t b = blockIdx.x;
+    const uint32_t blk_beg = dict + b * kBlockBytes;            // absolute positions in buf
+    const uint32_t blk_end = min(total, blk_beg + kBlockBytes);
+    const uint32_t win_beg = blk_beg > kWindow ? blk_beg - kWindow : 0u;
+    const uint32_t stage_end = min(total, blk_end + kWalkPad);
+    // ---- stage [win_beg, stage_end) ----
+    const uintptr_t g_lo = (uintptr_t)(buf + win_beg) & ~(uintptr_t)15;
+    const uint32_t mis = (uint32_t)((uintptr_t)(buf + win_beg) - g_lo);     // window offset w lives at s_mem[w + mis]
+    const uint32_t nvec = (mis + (stage_end - win_beg) + 15) >> 4;
+    for (uint32_t i = tid; i < nvec; i += kWalkThreads) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(g_lo) + i);
+        uint32_t* d = reinterpret_cast<uint32_t*>(s_mem + smap(i * 16));    // a 16-byte vector never straddles a row
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    for (int i = tid; i < (int)kHistSize; i += kWalkThreads) s_hist[i] = 0;
+    __syncthreads();
+    for (uint32_t r = tid; r + 1 < kWalkRows; r += kWalkThreads)            // pad word = first word of the next row
+        reinterpret_cast<uint32_t*>(s_mem)[r * 33 + 32] = reinterpret_cast<const uint32_t*>(s_mem)[(r + 1) * 33];
+    __syncthreads();
+    const uint32_t sm_off = mis;                                 // image offset of window offset 0
+    auto byte_at = [&](uint32_t q) { return (uint32_t)s_mem[smap(sm_off + q - win_beg)]; };   // buf[q]
 
-    const uint64_t ubeg = u * kUnit;
-    const uint32_t ulen = (uint32_t)min((uint64_t)kUnit, n - ubeg);
-    const uint32_t* m = mt + ubeg;
-    const uint8_t* in = src + ubeg;
-    uint32_t* out = tok + ubeg;
-    uint32_t pos = 0, ntok = 0;
-
-    while (pos < ulen) {
-        const uint32_t i = pos + lane;
-        uint32_t mv = i < ulen ? m[i] : 0u;
-        uint32_t L = mv & 0x1ffu, dist = mv >> 16;
-        bool take;
-        if (kind == 2) {
-            uint32_t mn = __shfl_down_sync(kFullMask, mv, 1);
-            const uint32_t m32 = (pos + 32 < ulen) ? m[pos + 32] : 0u;     // uniform load
-            if (lane == 31) mn = m32;
-            uint32_t Ln = mn & 0x1ffu;
-            if (L == kMinMatch && dist > kTooFar) L = 0;
-            if (Ln == kMinMatch && (mn >> 16) > kTooFar) Ln = 0;
-            take = L >= kMinMatch && !(L < max_lazy && Ln > L);
-        } else {
-            take = L >= kMinMatch;
-        }
-        const uint32_t step = take ? L : 1u;
-        // Follow the "next position" recurrence through the window.  Positions reached from the window's
-        // first position are found by jump doubling: after round k the first 2^k positions of the orbit are
-        // known, so 5 rounds cover any window (a serial walk needs up to 32 dependent shuffles).
-        const uint32_t lim = min(32u, ulen - pos);
-        const uint32_t land = lane + step;                      // where this position's token ends
-        uint32_t J = land < lim ? land : (uint32_t)lane;        // a token that leaves the window jumps to itself
-        uint32_t mask = 1u;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            mask |= __reduce_or_sync(kFullMask, ((mask >> lane) & 1u) << J);
-            J = __shfl_sync(kFullMask, J, J);
-        }
-        const uint32_t cur = __shfl_sync(kFullMask, land, 31 - __clz(mask));
-        if (mask & (1u << lane)) {
-            const uint32_t idx = ntok + __popc(mask & lt);
-            if (take) {
-                out[idx] = (dist << 16) | (L - kMinMatch);
-                atomicAdd(&hist[257 + len_code(L - kMinMatch)], 1u);
-                atomicAdd(&hist[288 + dist_code(dist - 1)], 1u);
-            } else {
-                const uint32_t b = in[i];
-                out[idx] = b;
-                atomicAdd(&hist[b], 1u);
+    // ---- walk this thread's sub-unit ----
+    const uint32_t s0 = blk_beg + tid * kSub, s1 = min(s0 + kSub, blk_end);
+    uint32_t* mine = tok_tmp + ((size_t)b * kWalkThreads + tid) * kSubSlots + 2;
+    uint32_t ntok = 0, pos = s0;
+    if (s0 < blk_end) {
+        if (kind == 1) {                                        // deflate_fast, deflate.c:1448-1546
+            while (pos < s1) {
+                const uint32_t maxlen = min(kMaxMatch, blk_end - pos);
+                Found f{0, 0};
+                if (maxlen >= kMinMatch && max_chain > 0)
+                    f = walk_search(s_mem, sm_off + pos - win_beg, dist16 + pos, maxlen, max_chain, min(nice, maxlen), 0);
+                if (f.len >= kMinMatch) { mine[ntok++] = (f.dist << 16) | (f.len - kMinMatch); pos += f.len; }
+                else { mine[ntok++] = byte_at(pos); pos++; }
+            }
+        } else {                                                // deflate_slow, deflate.c:1554-1674
+            uint32_t prev_len = kMinMatch - 1, prev_dist = 0;
+            bool avail = false;                                 // position pos-1 is pending (as a literal or as prev match)
+            for (;;) {
+                if (!avail && pos >= s1) break;
+                if (avail && pos - 1 >= s1) { pos--; break; }   // the pending position belongs to the next sub-unit: leave it
+                Found f{kMinMatch - 1, 0};
+                if (pos < blk_end) {
+                    const uint32_t maxlen = blk_end - pos < kMaxMatch ? blk_end - pos : kMaxMatch;
+                    if (maxlen >= kMinMatch && prev_len < max_lazy) {
+                        const int chain = prev_len >= good ? max(max_chain >> 2, 1) : max_chain;
+                        f = walk_search(s_mem, sm_off + pos - win_beg, dist16 + pos, maxlen, chain, min(nice, maxlen), prev_len);
+                        if (f.dist == 0) f.len = kMinMatch - 1;                  // nothing longer than the pending match
+                        if (f.len == kMinMatch && f.dist > kTooFar) f.len = kMinMatch - 1;
+                    }
+                }
+                if (prev_len >= kMinMatch && f.len <= prev_len) {               // the pending match wins
+                    mine[ntok++] = (prev_dist << 16) | (prev_len - kMinMatch);
+                    pos += prev_len - 1;
+                    avail = false; prev_len = kMinMatch - 1;
+                } else if (avail) {                                             // pending literal goes out, the new match waits
+                    mine[ntok++] = byte_at(pos - 1);
+                    prev_len = f.len; prev_dist = f.dist;
+                    pos++;
+                } else {
+                    avail = true;
+                    prev_len = f.len; prev_dist = f.dist;
+                    pos++;
+                }
             }
         }
-        ntok += __popc(mask);
-        pos += cur;
+    } else {
+        pos = blk_end;
     }
-    __syncwarp();
-    uint32_t* g = unit_hist + u * kHistSize;
-    for (int i = lane; i < (int)kHistSize; i += 32) g[i] = hist[i];
-    if (lane == 0) unit_ntok[u] = ntok;
+    // ---- frontier: where the tokens of the threads before this one end ----
+    {
+        uint32_t m = pos;                                       // inclusive prefix maximum: warp scan, then across warps
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(kFullMask, m, k); if (lane >= k && y > m) m = y; }
+        if (lane == 31) s_wsum[warp] = m;
+        __syncthreads();
+        uint32_t prevmax = 0;
+#pragma unroll
+        for (int w = 0; w < kWalkThreads / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp && v > prevmax) prevmax = v; }
+        s_end[tid] = m > prevmax ? m : prevmax;
+        __syncthreads();
+    }
+    const uint32_t front = tid ? s_end[tid - 1] : blk_beg;
+    int first = 0;                                              // index of the first kept token (may go to -2)
+    if (front > s0) {
+        uint32_t q = s0;
+        uint32_t i = 0;
+        while (i < ntok) {
+            const uint32_t t = mine[i];
+            const uint32_t l = (t >> 16) ? (t & 0xffffu) + kMinMatch : 1u;
+            if (q + l > front) break;
+            q += l; i++;
+        }
+        first = (int)i;
+        if (i < ntok && q < front) {                            // a match straddles the frontier: keep its tail
+            const uint32_t t = mine[i];
+            const uint32_t l = (t & 0xffffu) + kMinMatch, rem = q + l - front;
+            if (rem >= kMinMatch) mine[i] = (t & 0xffff0000u) | (rem - kMinMatch);
+            else {
+                for (uint32_t k = 0; k < rem; k++) mine[(int)i - (int)k] = byte_at(front + (rem - 1 - k));
+                first = (int)i - (int)(rem - 1);
+            }
+        }
+    }
+    const uint32_t keep = (uint32_t)((int)ntok - first);
+    // ---- compact: exclusive prefix sum of the kept counts ----
+    uint32_t x = keep;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(kFullMask, x, k); if (lane >= k) x += y; }
+    if (lane == 31) s_wsum[warp] = x;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kWalkThreads / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; all += v; }
+    s_cnt[tid] = before + x - keep;
+    s_first[tid] = (uint32_t)(first + 2);                       // relative to the region base (2 spare slots in front)
+    s_end[tid] = keep;
+    __syncthreads();
+    // ---- each warp moves its 32 regions, coalesced, and tallies ----
+    uint32_t* out = tok + (size_t)b * kBlockBytes;
+    for (int r = 0; r < 32; r++) {
+        const int t = warp * 32 + r;
+        const uint32_t cnt = s_end[t], off = s_cnt[t];
+        const uint32_t* srcp = tok_tmp + ((size_t)b * kWalkThreads + t) * kSubSlots + s_first[t];
+        for (uint32_t k = lane; k < cnt; k += 32) {
+            const uint32_t v = srcp[k];
+            out[off + k] = v;
+            if (v >> 16) {
+                atomicAdd(&s_hist[257 + len_code(v & 0xffffu)], 1u);
+                atomicAdd(&s_hist[288 + dist_code((v >> 16) - 1)], 1u);
+            } else {
+                atomicAdd(&s_hist[v], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < (int)kHistSize; i += kWalkThreads) blk_hist[(size_t)b * kHistSize + i] = s_hist[i];
+    if (tid == 0) blk_ntok[b] = all;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -390,7 +428,7 @@ constexpr int kCodeWarps = 4;
 __constant__ uint8_t c_bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 struct TreeScratch {
-    uint32_t hsum[kHistSize];                                   // block histogram = sum of its units' histograms
+    uint32_t hsum[kHistSize];                                   // block histogram
     uint32_t freq[288];                                         // input of the code under construction
     uint32_t key[512];                                          // freq << 9 | symbol, ascending
     uint32_t wint[288];                                         // weights of internal nodes, in creation order
@@ -574,25 +612,20 @@ __device__ __forceinline__ uint32_t fixed_lit_code(uint32_t s)
 }
 
 __global__ void __launch_bounds__(kCodeWarps * 32)
-k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict__ unit_hist,
+k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict__ blk_hist,
              uint32_t* __restrict__ blk_codes, uint32_t* __restrict__ blk_hdr, int force_fixed)
 {
     __shared__ TreeScratch s_t[kCodeWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t nblocks = (n + kBlockBytes - 1) / kBlockBytes, nunits = (n + kUnit - 1) / kUnit;
+    const uint64_t nblocks = (n + kBlockBytes - 1) / kBlockBytes;
     const uint64_t b = (uint64_t)blockIdx.x * kCodeWarps + warp;
     if (b >= nblocks) return;
     TreeScratch* t = &s_t[warp];
     uint32_t* codes = blk_codes + b * kHistSize;
     const uint32_t in_len = (uint32_t)min((uint64_t)kBlockBytes, n - b * kBlockBytes);
 
-    // ---- block histogram ----
-    const uint64_t u0 = b * kBlockUnits, u1 = min(nunits, u0 + kBlockUnits);
-    for (int i = lane; i < (int)kHistSize; i += 32) {
-        uint32_t f = i == 256 ? 1u : 0u;                        // the end-of-block symbol
-        for (uint64_t u = u0; u < u1; u++) f += unit_hist[u * kHistSize + i];
-        t->hsum[i] = f;
-    }
+    // ---- block histogram (+ the end-of-block symbol) ----
+    for (int i = lane; i < (int)kHistSize; i += 32) t->hsum[i] = blk_hist[b * kHistSize + i] + (i == 256 ? 1u : 0u);
     __syncwarp();
     // ---- literal/length and distance codes ----
     for (int i = lane; i < 286; i += 32) t->freq[i] = t->hsum[i];
@@ -794,7 +827,7 @@ struct Packer {
 
 __global__ void __launch_bounds__(kPackThreads)
 k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restrict__ tok,
-            const uint32_t* __restrict__ unit_ntok, const BlockMeta* __restrict__ blk,
+            const uint32_t* __restrict__ blk_ntok, const BlockMeta* __restrict__ blk,
             const uint32_t* __restrict__ blk_codes, const uint32_t* __restrict__ blk_hdr,
             const ChunkMeta* __restrict__ chunks, uint8_t* __restrict__ out, uint64_t cap, int last_is_final,
             int force_mark, uint32_t* __restrict__ err)
@@ -869,36 +902,31 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
             }
             pk.round(v, nb);                                    // also publishes s_codes (barrier inside)
         }
-        const uint32_t units = (bm.in_len + kUnit - 1) / kUnit;
-        for (uint32_t k = 0; k < units; k++) {
-            const uint64_t u = b * kBlockUnits + k;
-            const uint32_t* t = tok + u * kUnit;
-            const uint32_t cnt = unit_ntok[u];
-            const uint32_t end = cnt + (k == units - 1 ? 1u : 0u);   // the block's last round also carries end-of-block
-            for (uint32_t i0 = 0; i0 < end; i0 += kPackThreads) {
-                const uint32_t i = i0 + threadIdx.x;
-                uint64_t v = 0; uint32_t nb = 0;
-                if (i < cnt) {
-                    const uint32_t tk = t[i], dist = tk >> 16;
-                    if (dist == 0) {
-                        const uint32_t e = s_codes[tk & 0xff];
-                        v = e & 0xffffu; nb = e >> 16;
-                    } else {
-                        const uint32_t l = tk & 0xff, lc = len_code(l), le = len_extra_bits(lc);
-                        const uint32_t e = s_codes[257 + lc];
-                        v = e & 0xffffu; nb = e >> 16;
-                        if (le) { v |= (uint64_t)(l & ((1u << le) - 1u)) << nb; nb += le; }
-                        const uint32_t d = dist - 1, dc = dist_code(d), de = dist_extra_bits(dc);
-                        const uint32_t f = s_codes[288 + dc];
-                        v |= (uint64_t)(f & 0xffffu) << nb; nb += f >> 16;
-                        if (de) { v |= (uint64_t)(d & ((1u << de) - 1u)) << nb; nb += de; }
-                    }
-                } else if (i == cnt && k == units - 1) {
-                    const uint32_t e = s_codes[256];            // end of block
+        const uint32_t* t = tok + b * kBlockBytes;
+        const uint32_t cnt = blk_ntok[b];
+        for (uint32_t i0 = 0; i0 <= cnt; i0 += kPackThreads) {
+            const uint32_t i = i0 + threadIdx.x;
+            uint64_t v = 0; uint32_t nb = 0;
+            if (i < cnt) {
+                const uint32_t tk = t[i], dist = tk >> 16;
+                if (dist == 0) {
+                    const uint32_t e = s_codes[tk & 0xff];
                     v = e & 0xffffu; nb = e >> 16;
+                } else {
+                    const uint32_t l = tk & 0xff, lc = len_code(l), le = len_extra_bits(lc);
+                    const uint32_t e = s_codes[257 + lc];
+                    v = e & 0xffffu; nb = e >> 16;
+                    if (le) { v |= (uint64_t)(l & ((1u << le) - 1u)) << nb; nb += le; }
+                    const uint32_t d = dist - 1, dc = dist_code(d), de = dist_extra_bits(dc);
+                    const uint32_t f = s_codes[288 + dc];
+                    v |= (uint64_t)(f & 0xffffu) << nb; nb += f >> 16;
+                    if (de) { v |= (uint64_t)(d & ((1u << de) - 1u)) << nb; nb += de; }
                 }
-                pk.round(v, nb);
+            } else if (i == cnt) {
+                const uint32_t e = s_codes[256];                // end of block
+                v = e & 0xffffu; nb = e >> 16;
             }
+            pk.round(v, nb);
         }
     }
     // end of chunk: final -> pad; otherwise empty stored block unless already byte-aligned by a stored block
@@ -979,7 +1007,7 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
 {
     const LevelCfg& cfg = P.cfg;
     const uint64_t total = dict + n;
-    const uint64_t nchunks = (n + kChunk - 1) / kChunk, nunits = (n + kUnit - 1) / kUnit;
+    const uint64_t nchunks = (n + kChunk - 1) / kChunk;
     const uint64_t nblocks = (n + kBlockBytes - 1) / kBlockBytes;
     const uint8_t* d_src = d_buf + dict;
     int rc;
@@ -989,30 +1017,27 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
     uint32_t *d_hist = nullptr, *d_codes = nullptr, *d_hdr = nullptr, *d_tok = nullptr, *d_ntok = nullptr;
     if (cfg.kind != 0) {
         if ((rc = c->ws[3].ensure(total * 2 + 64)) != 0) return rc;          // dist16
-        if ((rc = c->ws[4].ensure(n * 4 + 64)) != 0) return rc;              // per-position matches
-        if ((rc = c->ws[5].ensure(nunits * kUnit * 4 + 64)) != 0) return rc; // tokens, one kUnit-sized region per unit
+        if ((rc = c->ws[4].ensure(nblocks * kWalkThreads * kSubSlots * 4 + 64)) != 0) return rc;   // private token regions
+        if ((rc = c->ws[5].ensure(nblocks * kBlockBytes * 4 + 64)) != 0) return rc;               // tokens, contiguous per block
         if ((rc = c->ws[6].ensure(nblocks * sizeof(BlockMeta))) != 0) return rc;
-        if ((rc = c->ws[7].ensure(nunits * kHistSize * 4)) != 0) return rc;
+        if ((rc = c->ws[7].ensure(nblocks * kHistSize * 4)) != 0) return rc;
         if ((rc = c->ws[8].ensure(nblocks * kHistSize * 4)) != 0) return rc;
         if ((rc = c->ws[9].ensure(nblocks * kHdrWords * 4)) != 0) return rc;
-        if ((rc = c->ws[10].ensure(nunits * 4)) != 0) return rc;
+        if ((rc = c->ws[10].ensure(nblocks * 4)) != 0) return rc;
         uint16_t* d_dist = c->ws[3].as<uint16_t>();
-        uint32_t* d_mt = c->ws[4].as<uint32_t>();
+        uint32_t* d_tmp = c->ws[4].as<uint32_t>();
         d_tok = c->ws[5].as<uint32_t>();
         d_blk = c->ws[6].as<BlockMeta>();
         d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
         d_ntok = c->ws[10].as<uint32_t>();
         const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
-        if (cfg.chain == 0) {
-            ZB_CUDA(cudaMemsetAsync(d_mt, 0, n * 4, s));
-        } else {
+        if (cfg.chain != 0) {
             // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
             if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
             else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
-            ZB_LAUNCH(k_lz_match, (unsigned)((n + 255) / 256), 256, 0, s, d_buf, (uint32_t)total, (uint32_t)dict, d_dist, d_mt, (int)cfg.chain, (int)cfg.nice);
         }
-        ZB_LAUNCH(k_lz_parse, (unsigned)((nunits + kParseWarps - 1) / kParseWarps), kParseWarps * 32, 0, s, d_src, n, d_mt,
-                  d_tok, d_ntok, d_hist, cfg.kind, (uint32_t)cfg.lazy);
+        ZB_LAUNCH(k_lz_walk, (unsigned)nblocks, kWalkThreads, kWalkSmem, s, d_buf, (uint32_t)total, (uint32_t)dict, d_dist, d_tmp,
+                  d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy, (uint32_t)cfg.good);
         ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, n, d_blk, d_hist,
                   d_codes, d_hdr, P.strategy == 4 ? 1 : 0);
     }
@@ -1041,6 +1066,7 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
     if (!attr) {
         ZB_CUDA(cudaFuncSetAttribute(k_lz_link<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
         ZB_CUDA(cudaFuncSetAttribute(k_lz_link<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
+        ZB_CUDA(cudaFuncSetAttribute(k_lz_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem));
         attr = true;
     }
     if (level < 0) level = 6;

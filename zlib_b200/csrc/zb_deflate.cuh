@@ -5,11 +5,8 @@
 namespace zb {
 
 constexpr uint32_t kChunk = ZB200_CHUNK;         // input bytes linked by one CTA / packed by one CTA; ends byte-aligned
-constexpr uint32_t kUnit = 16384;                // input bytes parsed by one warp (matches never cross a unit boundary)
-constexpr uint32_t kUnitsPerChunk = kChunk / kUnit;
-constexpr uint32_t kBlockUnits = 4;              // units per DEFLATE block: 64 KiB of input (the reference closes a
-constexpr uint32_t kBlockBytes = kUnit * kBlockUnits;   // block every 16 Ki symbols, about 45-60 KiB of text, deflate.c:291)
-constexpr uint32_t kBlocksPerChunk = kChunk / kBlockBytes;
+constexpr uint32_t kBlockBytes = 65536;          // input bytes per DEFLATE block = per CTA of the walk kernel (the reference
+constexpr uint32_t kBlocksPerChunk = kChunk / kBlockBytes;   // closes a block every 16 Ki symbols, 45-60 KiB of text, deflate.c:291)
 constexpr uint32_t kWindow = 32768;              // DEFLATE history (h/zconf.h MAX_WBITS = 15)
 constexpr uint32_t kMinMatch = 3, kMaxMatch = 258;
 constexpr uint32_t kHistSize = 320;              // 0..287 literal/length, 288..319 distance
