@@ -13,14 +13,13 @@
 //              barriers.  Output: for every position the distance to the previous position with the same
 //              3-byte hash (the reference's prev[] chain, stored as deltas so chains cross chunk boundaries
 //              and the 32 KiB of history in front of a chunk needs no copy -- it is simply there).
-//   K1b match  one thread per input position follows that chain up to max_chain candidates
-//              (configuration_table, deflate.c:137-149) and keeps the longest match, with the
-//              reference's quick reject on the byte that would extend the best match so far.
-//   K1c parse  one warp per 16 KiB unit turns per-position matches into tokens: greedy (deflate_fast) or
-//              lazy with max_lazy and TOO_FAR (deflate_slow, deflate.c:1601-1612); the serial "next
-//              position" recurrence is resolved 32 positions at a time by jump doubling.  Tokens are
-//              tallied into per-unit histograms (shared-memory atomics).
-//   K2 codes   one warp per block (4 units, 64 KiB of input) builds the three length-limited canonical
+//   K1b walk   one CTA per 64 KiB block, window staged in shared memory, one thread per 128-byte sub-unit
+//              running the reference's own search-emit-skip loop (deflate_fast, or deflate_slow with max_lazy,
+//              good_match and TOO_FAR, deflate.c:1448-1674): chain candidates up to max_chain
+//              (configuration_table, deflate.c:137-149), quick reject on the word a longer match must reach,
+//              nice_match.  Sub-unit boundaries are reconciled afterwards (prefix maximum of end positions);
+//              tokens are compacted per block and tallied into the block histogram.
+//   K2 codes   one warp per block (64 KiB of input) builds the three length-limited canonical
 //              codes (sort + two-queue merge, the reference's overflow repair), prices stored / fixed /
 //              dynamic with the reference's rule (trees.c:955-1001) and serialises the dynamic header.
 //   plan+scan  exact compressed size of every chunk -> exclusive prefix sum -> byte offsets.
