@@ -93,3 +93,18 @@ def test_full_size_property(gpu_lib, oracle):
     assert gpu_lib.adler32_combine(a[1], b[1], n - h) == whole[1]
     pre = tile.cpu().numpy()
     assert gpu_lib.checksum(dev.data_ptr(), 64 << 20) == (oracle.crc32(pre), oracle.adler32(pre))
+
+
+def test_checksum_batch(gpu_lib, oracle):
+    """zb200_checksum_batch: per-buffer crc32 / adler32 of n buffers in one launch (empty, tiny, unaligned, large)."""
+    import random
+    rng = random.Random(4)
+    sizes = [0, 1, 2, 3, 15, 16, 17, 255, 256, 257, 4095, 4096, 4097, 65521, 65522, 100001, 1 << 20, (3 << 20) + 7] + \
+            [rng.randint(0, 50000) for _ in range(40)]
+    bufs = [rng.randbytes(n) for n in sizes]
+    crcs, adls = gpu_lib.checksum_batch(bufs)
+    for b, c, a in zip(bufs, crcs, adls):
+        assert c == oracle.crc32(b) and a == oracle.adler32(b), len(b)
+    bufs = [bytes([255]) * 70000, bytes(70000)]                # extreme sums
+    crcs, adls = gpu_lib.checksum_batch(bufs)
+    assert crcs == [oracle.crc32(b) for b in bufs] and adls == [oracle.adler32(b) for b in bufs]

@@ -172,3 +172,26 @@ def test_raw_gzip_and_shards(gpu_lib, oracle):
     assert zlib.decompress(out.raw[:n], 31) == data
     rc, o2, _ = oracle.inflate(out.raw[:n], len(data), 2)
     assert rc == 0 and o2 == data
+
+
+def test_deflate_batch_independent_streams(gpu_lib, oracle):
+    """zb200_deflate_batch: n inputs -> n streams (minizip-style per-file streams), each decodable by the reference,
+    with the CRC-32 / Adler-32 of each input; a slot that is too small fails alone."""
+    rng = random.Random(12)
+    sizes = [0, 1, 2, 100, 4096, 65535, 65536, 70000, 131072, 131073, 300000, 1 << 20, (1 << 21) + 5] + \
+            [rng.randint(1, 200000) for _ in range(27)]
+    bufs = [zhelpers.corpus(rng.randrange(5), n, 300 + i) for i, n in enumerate(sizes)]
+    for level, wrap, wbits in ((6, zb.WRAP_ZLIB, 15), (1, zb.WRAP_RAW, -15), (6, zb.WRAP_GZIP, 31)):
+        outs, st, crcs, adls = gpu_lib.deflate_batch(bufs, level, wrap)
+        assert st == [0] * len(bufs), st
+        for d, z, c, a in zip(bufs, outs, crcs, adls):
+            assert zlib.decompress(z, wbits) == d
+            assert c == oracle.crc32(d) and a == oracle.adler32(d)
+            if wrap == zb.WRAP_ZLIB:
+                rc, out, used = oracle.inflate(z, len(d))
+                assert rc == 0 and out == d and used == len(z)
+    caps = [gpu_lib.compress_bound(len(b)) + 16 for b in bufs]
+    caps[7] = 10                                               # 70000 random-ish bytes cannot fit
+    outs, st, _, _ = gpu_lib.deflate_batch(bufs, 6, zb.WRAP_ZLIB, caps=caps)
+    assert st[7] == zb.Z_BUF_ERROR and all(s == 0 for i, s in enumerate(st) if i != 7)
+    assert zlib.decompress(outs[8]) == bufs[8]

@@ -1,1 +1,1 @@
-ncu --set full --clock-control none --import-source on -k regex:'k_lz_|k_huff' --launch-skip 8 -c 4 -o gpurun_out/r1_d python bench.py --steps 1 --warmup 1 --no-extra --no-verify > gpurun_out/ncu_d.log 2>&1; echo rc=$?
+python -m pytest tests/test_checksum_gpu.py tests/test_deflate_gpu.py -m gpu -x -q 2>&1 | tail -12

@@ -205,6 +205,40 @@ class Lib:
                                                  C.byref(crc), C.byref(adl), _stream(stream)), "zb200_deflate_shard")
         return ol.value, crc.value, adl.value
 
+    def checksum_batch(self, bufs, stream=None):
+        """zb200_checksum_batch over a list of bytes objects -> ([crc32], [adler32])."""
+        import numpy as np
+        n = len(bufs)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(b) for b in bufs], dtype=np.uint64)
+        base = np.frombuffer(b"".join(bufs) + b"\0" * 8, dtype=np.uint8)
+        crc = np.zeros(max(n, 1), dtype=np.uint32)
+        adl = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self.dll.zb200_checksum_batch(base.ctypes.data, off.ctypes.data, n, crc.ctypes.data, adl.ctypes.data,
+                                                  _stream(stream)), "zb200_checksum_batch")
+        return [int(x) for x in crc[:n]], [int(x) for x in adl[:n]]
+
+    def deflate_batch(self, bufs, level: int = 6, wrap: int = WRAP_ZLIB, caps=None, stream=None):
+        """zb200_deflate_batch over a list of bytes objects -> (streams, statuses, crcs, adlers)."""
+        import numpy as np
+        n = len(bufs)
+        caps = [self.compress_bound(len(b)) + 16 for b in bufs] if caps is None else caps
+        src_off = np.zeros(n + 1, dtype=np.uint64)
+        dst_off = np.zeros(n + 1, dtype=np.uint64)
+        src_off[1:] = np.cumsum([len(b) for b in bufs], dtype=np.uint64)
+        dst_off[1:] = np.cumsum(caps, dtype=np.uint64)
+        src = np.frombuffer(b"".join(bufs) + b"\0" * 8, dtype=np.uint8)
+        dst = np.zeros(int(dst_off[-1]) + 8, dtype=np.uint8)
+        dst_len = np.zeros(max(n, 1), dtype=np.uint64)
+        crc = np.zeros(max(n, 1), dtype=np.uint32)
+        adl = np.zeros(max(n, 1), dtype=np.uint32)
+        status = np.full(max(n, 1), -99, dtype=np.int32)
+        self._check(self.dll.zb200_deflate_batch(src.ctypes.data, src_off.ctypes.data, n, dst.ctypes.data, dst_off.ctypes.data,
+                                                 dst_len.ctypes.data, crc.ctypes.data, adl.ctypes.data, status.ctypes.data,
+                                                 level, wrap, _stream(stream)), "zb200_deflate_batch")
+        outs = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + int(dst_len[i])]) if status[i] == 0 else b"" for i in range(n)]
+        return outs, [int(x) for x in status[:n]], [int(x) for x in crc[:n]], [int(x) for x in adl[:n]]
+
     def inflate_batch(self, streams, caps, wrap: int = WRAP_ZLIB, stream=None):
         """zb200_inflate_batch over a list of bytes objects; returns (outputs, statuses)."""
         import numpy as np

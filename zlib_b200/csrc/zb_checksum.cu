@@ -266,6 +266,78 @@ k_checksum_final(const Partial* __restrict__ parts, uint32_t n_parts, const uint
     }
 }
 
+// ---- batch kernel: one CTA per buffer (per-member CRCs of an archive, per-stream checks after a batch inflate) ----
+// Thread t runs the byte table over its contiguous stripe (crc32.c:244-252 DO1, adler32.c:66-70), then the CTA moves
+// every stripe's register to the end of the buffer and folds -- the combine tree of k_checksum_final, per buffer.
+// len == nullptr: buffer i is [off[i], off[i+1]).  expect != nullptr: out2 is not written; instead ok[i] is cleared
+// to Z_DATA_ERROR when the pair differs from expect[2i], expect[2i+1] (crc32, length mod 2^32: a gzip trailer).
+__global__ void __launch_bounds__(kStripeThreads)
+k_checksum_batch(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ lens,
+                 uint32_t* __restrict__ crc_out, uint32_t* __restrict__ adler_out, const uint32_t* __restrict__ expect,
+                 int32_t* __restrict__ ok)
+{
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_reg[kStripeThreads / 32], s_a[kStripeThreads / 32], s_b[kStripeThreads / 32];
+    s_tab[threadIdx.x] = g_tab_byte[threadIdx.x];
+    __syncthreads();
+    const uint64_t i = blockIdx.x;
+    if (expect && ok[i] != 0) return;                         // nothing to verify for a stream that already failed
+    const uint8_t* buf = base + off[i];
+    const uint64_t len = lens ? lens[i] : off[i + 1] - off[i];
+    const uint64_t stripe = (len + kStripeThreads - 1) / kStripeThreads;
+    const uint64_t beg = min(len, (uint64_t)threadIdx.x * stripe), end = min(len, beg + stripe);
+    uint32_t c = 0, a = 0, b = 0;                             // raw register, byte sum, sum of prefix sums (both mod 65521)
+    for (uint64_t p = beg; p < end;) {
+        const uint64_t stop = min(end, p + 4096);             // u32 bound for the deferred modulo
+        uint32_t aa = 0, bb = 0;
+        const uint32_t n = (uint32_t)(stop - p);
+        for (; p < stop; ++p) {
+            const uint32_t v = buf[p];
+            c = s_tab[(c ^ v) & 0xffu] ^ (c >> 8);
+            aa += v; bb += aa;
+        }
+        b = (b + (uint32_t)((uint64_t)n * a % kAdlerBase) + bb % kAdlerBase) % kAdlerBase;
+        a = (a + aa) % kAdlerBase;
+    }
+    // move to the end of the buffer: register times x^(8*suffix); Adler sums shift by suffix * a
+    const uint64_t suffix = len - end;
+    uint32_t reg = (end > beg && suffix) ? gf2_mul(c, pow8(suffix)) : c;
+    if (end == beg) { reg = 0; a = 0; b = 0; }
+    b = (b + (uint32_t)((suffix % kAdlerBase) * a % kAdlerBase)) % kAdlerBase;
+    if (threadIdx.x == 0) reg ^= len ? gf2_mul(0xffffffffu, pow8(len)) : 0xffffffffu;   // the 0xffffffff pre-conditioning
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_reg[warp] = reg; s_a[warp] = a % kAdlerBase; s_b[warp] = b % kAdlerBase; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        reg = 0; a = 0; b = 0;
+        for (int w = 0; w < kStripeThreads / 32; w++) { reg ^= s_reg[w]; a += s_a[w]; b += s_b[w]; }
+        const uint32_t s1 = (1u + a) % kAdlerBase;
+        const uint32_t s2 = (uint32_t)((len % kAdlerBase + b) % kAdlerBase);
+        const uint32_t crc = ~reg, adl = (s2 << 16) | s1;
+        if (expect) {
+            if (crc != expect[2 * i] || (uint32_t)len != expect[2 * i + 1]) ok[i] = ZB_DATA_ERROR;
+        } else {
+            if (crc_out) crc_out[i] = crc;
+            if (adler_out) adler_out[i] = adl;
+        }
+    }
+}
+
+int checksum_batch_launch(const uint8_t* d_base, const uint64_t* d_off, const uint64_t* d_lens, size_t n, uint32_t* d_crc,
+                          uint32_t* d_adler, const uint32_t* d_expect, int32_t* d_ok, cudaStream_t s)
+{
+    if (n == 0) return 0;
+    ZB_LAUNCH(k_checksum_batch, (unsigned)n, kStripeThreads, 0, s, d_base, d_off, d_lens, d_crc, d_adler, d_expect, d_ok);
+    ZB_CHECK_LAUNCH();
+    return 0;
+}
+
 int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, cudaStream_t s)
 {
     static bool attr_set = false;
@@ -349,6 +421,40 @@ ZB_API int zb200_checksum(const void* buf, size_t len, uint32_t* crc, uint32_t* 
         const uint32_t* r = static_cast<const uint32_t*>(c->pinned);
         if (crc) *crc = r[0];
         if (adler) *adler = r[1];
+    } while (0);
+    ctx_release(c, s);
+    return rc;
+}
+
+ZB_API int zb200_checksum_batch(const void* base, const uint64_t* offsets, size_t n, uint32_t* crc, uint32_t* adler, void* stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (n == 0) return 0;
+    if (!offsets) { set_error("zb200_checksum_batch: bad argument"); return ZB_STREAM_ERROR; }
+    Ctx* c = ctx_acquire((cudaStream_t)stream);
+    if (!c) return ZB_MEM_ERROR;
+    cudaStream_t s = pick_stream(c, stream);
+    do {
+        const uint8_t* d = to_device(c, base, (size_t)offsets[n], s, &rc);
+        if (rc) break;
+        // [offsets n+1 (u64)][crc n][adler n]
+        if ((rc = c->ws[0].ensure((n + 1) * 8 + n * 8)) != 0) break;
+        if ((rc = c->ensure_pinned(n * 8)) != 0) break;
+        uint64_t* d_off = c->ws[0].as<uint64_t>();
+        uint32_t* d_crc = (uint32_t*)(d_off + n + 1);
+        uint32_t* d_adl = d_crc + n;
+        cudaError_t e = cudaMemcpyAsync(d_off, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { set_error("offset upload failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        if ((rc = checksum_batch_launch(d, d_off, nullptr, n, d_crc, d_adl, nullptr, nullptr, s)) != 0) break;
+        e = cudaMemcpyAsync(c->pinned, d_crc, n * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_error("checksum batch failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        const uint32_t* r = static_cast<const uint32_t*>(c->pinned);
+        for (size_t i = 0; i < n; i++) {
+            if (crc) crc[i] = r[i];
+            if (adler) adler[i] = r[n + i];
+        }
     } while (0);
     ctx_release(c, s);
     return rc;

@@ -51,6 +51,7 @@ struct Ctx {
 
 int  ensure_init();                        // 0 or negative zlib code
 Ctx* ctx_acquire(cudaStream_t use);        // waits (on `use`) for the context's previous work
+Ctx* ctx_acquire_own();                    // for work on the context's own stream
 void ctx_release(Ctx* c, cudaStream_t used);
 // NULL means CUDA's legacy default stream (stream 0), which orders with torch's default stream.
 inline cudaStream_t pick_stream(Ctx*, void* user) { return (cudaStream_t)user; }
@@ -97,6 +98,10 @@ void profile_mark(const char* name, cudaStream_t s, bool begin);
 int checksum_setup();                      // uploads tables; called from ensure_init
 // crc32(0,..)/adler32(1,..) of d_buf[0..len) -> d_out2[0..1]; async on s.
 int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, cudaStream_t s);
+// n buffers in one launch: buffer i = d_base[d_off[i] .. +len) with len = d_lens[i] or d_off[i+1]-d_off[i].
+// Either writes crc/adler per buffer, or (d_expect != nullptr) checks {crc32, length} pairs and flags d_ok[i].
+int checksum_batch_launch(const uint8_t* d_base, const uint64_t* d_off, const uint64_t* d_lens, size_t n, uint32_t* d_crc,
+                          uint32_t* d_adler, const uint32_t* d_expect, int32_t* d_ok, cudaStream_t s);
 const unsigned long* host_crc_table();
 
 }  // namespace zb

@@ -1048,6 +1048,54 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
     return 0;
 }
 
+// A whole device-resident job, asynchronous on s with the scratch of context c: slabs, checksums of the input,
+// header and trailer.  d_res (device, 32 bytes): u64 total length, then u32 crc32, adler32, error count.
+static int deflate_enqueue_dev(Ctx* c, cudaStream_t s, const uint8_t* d_buf, uint64_t dict_len, uint64_t n, uint8_t* d_out,
+                               uint64_t cap, const DeflateParams& P, uint32_t* d_res)
+{
+    const int force_mark = (P.flags & ZB200I_DEFLATE_FORCE_MARK) ? 1 : 0;
+    const int last_is_final = (P.flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
+    const uint64_t hdr_len = (P.flags & ZB200_DEFLATE_NO_HEADER) ? 0 : P.wrap == ZB200_WRAP_ZLIB ? 2 : P.wrap == ZB200_WRAP_GZIP ? 10 : 0;
+    const uint64_t slab = (uint64_t)kSlabChunks * kChunk;
+    const uint64_t nslabs = n ? (n + slab - 1) / slab : 0;
+    int rc;
+    if ((rc = c->ws[1].ensure((nslabs + 2) * 8)) != 0) return rc;
+    uint64_t* d_pos = c->ws[1].as<uint64_t>();
+    uint64_t* d_total = reinterpret_cast<uint64_t*>(d_res);
+    uint32_t* d_sums = d_res + 2;
+    uint32_t* d_err = d_res + 4;
+    ZB_CUDA(cudaMemsetAsync(d_err, 0, 4, s));
+    const uint8_t* d_src = d_buf + dict_len;
+    if (n == 0) ZB_LAUNCH(k_empty_payload, 1, 32, 0, s, d_out, cap, hdr_len, !last_is_final, force_mark, d_pos);
+    for (uint64_t i = 0; i < nslabs; i++) {
+        const uint64_t off = i * slab, len = n - off < slab ? n - off : slab;
+        const uint64_t dlen = i == 0 ? dict_len : kWindow;
+        const bool last = i == nslabs - 1;
+        if ((rc = deflate_slab_launch(c, d_src + off - dlen, dlen, len, d_out, cap, P, last && last_is_final, last ? force_mark : 0,
+                                      i ? d_pos + i - 1 : nullptr, i ? 0 : hdr_len, d_pos + i, d_err, s)) != 0) return rc;
+    }
+    if ((rc = checksum_launch(c, d_src, n, d_sums, s)) != 0) return rc;
+    ZB_LAUNCH(k_frame, 1, 32, 0, s, d_out, cap, hdr_len, d_pos + (nslabs ? nslabs - 1 : 0), d_sums, n, P.level, P.wrap, P.flags, d_total);
+    ZB_CHECK_LAUNCH();
+    return 0;
+}
+
+static int deflate_params(DeflateParams& P, int level, int wrap, int flags)
+{
+    static bool attr = false;
+    if (!attr) {
+        ZB_CUDA(cudaFuncSetAttribute(k_lz_link<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
+        ZB_CUDA(cudaFuncSetAttribute(k_lz_link<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
+        ZB_CUDA(cudaFuncSetAttribute(k_lz_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem));
+        attr = true;
+    }
+    if (level < 0) level = 6;
+    P.cfg = h_levels[level]; P.level = level; P.wrap = wrap; P.flags = flags;
+    P.strategy = (flags >> 8) & 7;                              // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
+    if (P.strategy == 2 && P.cfg.kind != 0) { P.cfg.chain = 0; P.cfg.kind = 1; }   // literals only (deflate.c:1490)
+    return 0;
+}
+
 }  // namespace zb
 
 using namespace zb;
@@ -1061,18 +1109,9 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
         set_error("zb200_deflate: bad argument");
         return ZB_STREAM_ERROR;
     }
-    static bool attr = false;
-    if (!attr) {
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_link<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_link<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem));
-        attr = true;
-    }
-    if (level < 0) level = 6;
     DeflateParams P;
-    P.cfg = h_levels[level]; P.level = level; P.wrap = wrap; P.flags = flags;
-    P.strategy = (flags >> 8) & 7;                              // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
-    if (P.strategy == 2 && P.cfg.kind != 0) { P.cfg.chain = 0; P.cfg.kind = 1; }   // literals only (deflate.c:1490)
+    if ((rc = deflate_params(P, level, wrap, flags)) != 0) return rc;
+    level = P.level;
     const int force_mark = (flags & ZB200I_DEFLATE_FORCE_MARK) ? 1 : 0;
     const int last_is_final = (flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
     const uint64_t hdr_len = (flags & ZB200_DEFLATE_NO_HEADER) ? 0 : wrap == ZB200_WRAP_ZLIB ? 2 : wrap == ZB200_WRAP_GZIP ? 10 : 0;
@@ -1202,4 +1241,82 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
 ZB_API int zb200_deflate(const void* src, size_t src_len, void* dst, size_t* dst_len, int level, int wrap, void* stream)
 {
     return zb200_deflate_shard(src, src_len, nullptr, 0, dst, dst_len, level, wrap, 0, nullptr, nullptr, stream);
+}
+
+// n independent inputs -> n independent streams.  Jobs are enqueued round robin on a few contexts (each with its own
+// stream and scratch), so small files overlap on the GPU; there is one synchronisation, at the end.
+ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t n, void* dst, const uint64_t* dst_off,
+                               uint64_t* dst_len, uint32_t* crc, uint32_t* adler, int32_t* status, int level, int wrap,
+                               void* stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (level < -1 || level > 9 || wrap < 0 || wrap > 2 || (n && (!src_off || !dst_off || !dst || !dst_len))) {
+        set_error("zb200_deflate_batch: bad argument");
+        return ZB_STREAM_ERROR;
+    }
+    if (n == 0) return 0;
+    for (size_t i = 0; i < n; i++)
+        if (src_off[i + 1] < src_off[i] || dst_off[i + 1] < dst_off[i]) { set_error("zb200_deflate_batch: offsets must not decrease"); return ZB_STREAM_ERROR; }
+    DeflateParams P;
+    if ((rc = deflate_params(P, level, wrap, 0)) != 0) return rc;
+    constexpr int kLanes = 4;
+    cudaStream_t s0 = (cudaStream_t)stream;
+    Ctx* c0 = ctx_acquire(s0);
+    if (!c0) return ZB_MEM_ERROR;
+    Ctx* lane[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+    int nl = 0;
+    do {
+        if ((rc = c0->ensure_aux(kLanes + 2)) != 0) break;
+        const size_t nlanes = n < (size_t)kLanes ? n : (size_t)kLanes;
+        for (; nl < (int)nlanes; nl++) {
+            lane[nl] = ctx_acquire_own();
+            if (!lane[nl]) { rc = ZB_MEM_ERROR; break; }
+        }
+        if (rc) break;
+        const uint64_t src_total = src_off[n], dst_total = dst_off[n];
+        const uint8_t* d_src = to_device(c0, src, src_total, s0, &rc);
+        if (rc) break;
+        const bool dst_on_host = classify(dst) != kDevice;
+        uint8_t* d_dst = (uint8_t*)dst;
+        if (dst_on_host) {
+            if ((rc = c0->out.ensure(dst_total + 16)) != 0) break;
+            d_dst = c0->out.as<uint8_t>();
+        }
+        if ((rc = c0->ws[11].ensure(n * 32)) != 0) break;
+        if ((rc = c0->ensure_pinned(n * 32)) != 0) break;
+        uint32_t* d_res = c0->ws[11].as<uint32_t>();
+        cudaError_t e = cudaEventRecord(c0->evs[0], s0);         // the input is on the device (and the caller's stream has reached us)
+        for (int k = 0; k < nl && e == cudaSuccess; k++) e = cudaStreamWaitEvent(lane[k]->own_stream, c0->evs[0], 0);
+        if (e != cudaSuccess) { set_error("batch setup failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        for (size_t i = 0; i < n; i++) {
+            Ctx* ck = lane[i % nl];
+            if ((rc = deflate_enqueue_dev(ck, ck->own_stream, d_src + src_off[i], 0, src_off[i + 1] - src_off[i], d_dst + dst_off[i],
+                                          dst_off[i + 1] - dst_off[i], P, d_res + 8 * i)) != 0) break;
+        }
+        for (int k = 0; k < nl; k++) {                           // join the lanes (also after a failed enqueue)
+            cudaEventRecord(c0->evs[1 + k], lane[k]->own_stream);
+            cudaStreamWaitEvent(s0, c0->evs[1 + k], 0);
+        }
+        if (rc) { cudaStreamSynchronize(s0); break; }
+        e = cudaMemcpyAsync(c0->pinned, d_res, n * 32, cudaMemcpyDeviceToHost, s0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
+        if (e != cudaSuccess) { set_error("deflate batch failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        const uint32_t* r = (const uint32_t*)c0->pinned;
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t total = *(const uint64_t*)(r + 8 * i), cap = dst_off[i + 1] - dst_off[i];
+            dst_len[i] = total;
+            if (crc) crc[i] = r[8 * i + 2];
+            if (adler) adler[i] = r[8 * i + 3];
+            const int32_t st = r[8 * i + 4] ? ZB_STREAM_ERROR : total > cap ? ZB_BUF_ERROR : ZB_OK;
+            if (status) status[i] = st;
+            if (dst_on_host && st == ZB_OK && total)
+                if (cudaMemcpyAsync((uint8_t*)dst + dst_off[i], d_dst + dst_off[i], total, cudaMemcpyDeviceToHost, s0) != cudaSuccess) rc = ZB_STREAM_ERROR;
+        }
+        if (dst_on_host && cudaStreamSynchronize(s0) != cudaSuccess) rc = ZB_STREAM_ERROR;
+        if (rc) set_error("deflate batch readback failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } while (0);
+    for (int k = 0; k < nl; k++) if (lane[k]) ctx_release(lane[k], lane[k]->own_stream);
+    ctx_release(c0, s0);
+    return rc;
 }

@@ -162,6 +162,13 @@ Ctx* ctx_acquire(cudaStream_t use)
     return c;
 }
 
+Ctx* ctx_acquire_own()
+{
+    Ctx* c = ctx_acquire(nullptr);
+    if (c) cudaStreamWaitEvent(c->own_stream, c->idle, 0);
+    return c;
+}
+
 void ctx_release(Ctx* c, cudaStream_t used)
 {
     cudaEventRecord(c->idle, used);
