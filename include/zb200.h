@@ -31,6 +31,7 @@ extern "C" {
 #define ZB200_WRAP_RAW   0      /* windowBits < 0      (qcsrc/deflate.c:255-258) */
 #define ZB200_WRAP_ZLIB  1      /* windowBits 8..15    RFC 1950 */
 #define ZB200_WRAP_GZIP  2      /* windowBits + 16     RFC 1952 (qcsrc/deflate.c:259-264) */
+#define ZB200_WRAP_AUTO  3      /* inflate only: windowBits + 32, zlib or gzip by the first two bytes (qcsrc/inflate.c:596) */
 
 #define ZB200_CHUNK      131072u /* input bytes per independently parsed chunk */
 
@@ -96,7 +97,8 @@ int zb200_deflate_batch(const void *src, const uint64_t *src_off, size_t n,
  * dst[dst_off[i] .. dst_off[i+1]).  Per stream: dst_len[i] = bytes produced,
  * status[i] = Z_OK / Z_DATA_ERROR / Z_BUF_ERROR with uncompress()'s mapping
  * (qcsrc/uncompr.c:53-55).  Returns Z_OK if the batch ran, whatever the per-stream
- * statuses are. */
+ * statuses are.  wrap: ZB200_WRAP_RAW / _ZLIB / _GZIP / _AUTO; gzip members have their
+ * header fields skipped (FHCRC verified) and CRC-32 + ISIZE checked (qcsrc/inflate.c:634-759,1099-1112). */
 int zb200_inflate_batch(const void *src, const uint64_t *src_off, size_t n,
                         void *dst, const uint64_t *dst_off, uint64_t *dst_len,
                         int32_t *status, int wrap, void *stream);

@@ -127,3 +127,56 @@ def test_many_streams_device_resident(gpu_lib, oracle):
     assert int(d_st.abs().sum()) == 0
     assert bool((d_len == sz).all())
     assert np.array_equal(d_dst.cpu().numpy(), host)
+
+
+def _gzip_member(data, level=6, name=None, extra=None, comment=None, hcrc=False):
+    """A gzip member with any mix of optional header fields (RFC 1952), body from the system zlib."""
+    import struct
+    import zlib
+    flg = (4 if extra is not None else 0) | (8 if name is not None else 0) | (16 if comment is not None else 0) | (2 if hcrc else 0)
+    h = bytes([0x1f, 0x8b, 8, flg, 1, 2, 3, 4, 0, 3])
+    if extra is not None:
+        h += struct.pack("<H", len(extra)) + extra
+    if name is not None:
+        h += name + b"\0"
+    if comment is not None:
+        h += comment + b"\0"
+    if hcrc:
+        h += struct.pack("<H", zlib.crc32(h) & 0xffff)
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    body = co.compress(data) + co.flush()
+    return h + body + struct.pack("<II", zlib.crc32(data), len(data) & 0xffffffff)
+
+
+def test_gzip_members_batch(gpu_lib, oracle):
+    """windowBits+16 / +32 decoding (inflate.c:596-759, 1099-1112): header fields skipped, FHCRC, CRC-32 and ISIZE
+    verified; auto-detect takes zlib and gzip streams in one batch."""
+    import zlib
+    rng = random.Random(8)
+    datas = [zhelpers.corpus(rng.randrange(5), n, 700 + i) for i, n in enumerate([0, 1, 5, 300, 4096, 70000, 200000, 33333])]
+    members = [
+        _gzip_member(datas[0]), _gzip_member(datas[1], name=b"a.txt"), _gzip_member(datas[2], extra=b"\x01\x02\x03"),
+        _gzip_member(datas[3], comment=b"hello", hcrc=True), _gzip_member(datas[4], name=b"n", extra=b"", comment=b"", hcrc=True),
+        _gzip_member(datas[5], 1), _gzip_member(datas[6], 9, name=b"x" * 300), _gzip_member(datas[7]),
+    ]
+    for m, d in zip(members, datas):
+        assert zlib.decompress(m, 31) == d                       # the fixtures are valid for the system decoder
+    outs, st = gpu_lib.inflate_batch(members, [len(d) for d in datas], wrap=zb.WRAP_GZIP)
+    assert st == [0] * len(members) and outs == datas
+    # auto-detect: zlib streams and gzip members side by side
+    mixed = members[:4] + [oracle.deflate(d, 6) for d in datas[4:]]
+    outs, st = gpu_lib.inflate_batch(mixed, [len(d) for d in datas], wrap=3)
+    assert st == [0] * len(mixed) and outs == datas
+    # damage: CRC, ISIZE, header CRC, reserved flag bit, method, magic, truncation
+    def flip(b, i, v=0x01):
+        b = bytearray(b); b[i] ^= v; return bytes(b)
+    bad = [flip(members[5], len(members[5]) - 6), flip(members[5], len(members[5]) - 2), flip(members[3], 11),
+           flip(members[5], 3, 0x20), flip(members[5], 2, 0x01), flip(members[5], 1), members[5][:-3], members[5][:7]]
+    want = []
+    for z in bad:
+        try:
+            zlib.decompress(z, 31); want.append(0)
+        except zlib.error:
+            want.append(-3)
+    outs, st = gpu_lib.inflate_batch(bad, [len(datas[5])] * 6 + [len(datas[5])] * 2, wrap=zb.WRAP_GZIP)
+    assert st == want == [-3] * len(bad), (st, want)

@@ -129,3 +129,29 @@ def test_minizip_miniunz_both_directions(gpu_lib, tmp_path):
             assert (out / name).read_bytes() == data, (writer, reader, name)   # miniunz's exit code is not trusted
         import zipfile
         assert zipfile.ZipFile(arc).testzip() is None
+
+
+def test_gzip_stream_decoding(gpu_lib):
+    """inflateInit2(windowBits + 16 / + 32) through the streaming ABI in small pieces; strm->adler carries the CRC-32;
+    a damaged CRC is 'incorrect data check', a damaged ISIZE 'incorrect length check' (inflate.c:1099-1112)."""
+    import zlib
+    data = gpu_lib.synth(700000, kind=1, seed=9).tobytes()
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    z = co.compress(data) + co.flush()
+    for wbits in (31, 47):
+        rc, out, msg, tin = gpu_lib.inflate_stream(z, wbits=wbits, in_chunk=5000, out_chunk=30000)
+        assert rc == zb.Z_STREAM_END and out == data and tin == len(z)
+        assert gpu_lib.last_adler == zlib.crc32(data)
+    rc, out, msg, tin = gpu_lib.inflate_stream(zlib.compress(data, 6), wbits=47, in_chunk=7000, out_chunk=50000)
+    assert rc == zb.Z_STREAM_END and out == data                 # auto-detect also takes a zlib stream
+    bad = bytearray(z); bad[-6] ^= 4
+    rc, out, msg, tin = gpu_lib.inflate_stream(bytes(bad), wbits=31)
+    assert rc == zb.Z_DATA_ERROR and msg == "incorrect data check"
+    bad = bytearray(z); bad[-1] ^= 4
+    rc, out, msg, tin = gpu_lib.inflate_stream(bytes(bad), wbits=31)
+    assert rc == zb.Z_DATA_ERROR and msg == "incorrect length check"
+    # our own gzip output read back by our own gzip decoder
+    rc, zz = gpu_lib.deflate_stream(data, level=6, wbits=31)
+    assert rc == zb.Z_OK
+    rc, out, msg, tin = gpu_lib.inflate_stream(zz, wbits=31, in_chunk=1 << 20, out_chunk=1 << 20)
+    assert rc == zb.Z_STREAM_END and out == data

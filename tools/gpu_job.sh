@@ -1,1 +1,1 @@
-python -m pytest tests/test_checksum_gpu.py tests/test_deflate_gpu.py -m gpu -x -q 2>&1 | tail -12
+python -m pytest tests/test_inflate_gpu.py tests/test_stream_gpu.py -m gpu -x -q 2>&1 | tail -15

@@ -432,7 +432,7 @@ ZAPI int inflateInit2_(z_streamp strm, int windowBits, const char *version, int 
     if (windowBits < 0) { wrap = 0; windowBits = -windowBits; }
     else { wrap = (windowBits >> 4) + 1; if (windowBits < 48) windowBits &= 15; }
     if (windowBits < 8 || windowBits > 15) return Z_STREAM_ERROR;
-    if (wrap > 1) return Z_STREAM_ERROR;      /* gzip / auto-detect decoding: SURVEY.md 8(f) row 2, not built yet */
+    if (wrap > 3) return Z_STREAM_ERROR;      /* 2 = gzip (windowBits + 16), 3 = zlib or gzip (+ 32), inflate.c:159-167 */
     if (zb200_init(-1) != Z_OK) return Z_STREAM_ERROR;
     s = (zs *)strm->zalloc(strm->opaque, 1, (uInt)sizeof(zs));
     if (s == Z_NULL) return Z_MEM_ERROR;

@@ -270,7 +270,8 @@ k_checksum_final(const Partial* __restrict__ parts, uint32_t n_parts, const uint
 // Thread t runs the byte table over its contiguous stripe (crc32.c:244-252 DO1, adler32.c:66-70), then the CTA moves
 // every stripe's register to the end of the buffer and folds -- the combine tree of k_checksum_final, per buffer.
 // len == nullptr: buffer i is [off[i], off[i+1]).  expect != nullptr: out2 is not written; instead ok[i] is cleared
-// to Z_DATA_ERROR when the pair differs from expect[2i], expect[2i+1] (crc32, length mod 2^32: a gzip trailer).
+// to Z_DATA_ERROR when the pair differs from expect[3i], expect[3i+1] (crc32, length mod 2^32: a gzip trailer;
+// expect[3i+2] == 0 means buffer i has no such trailer).
 __global__ void __launch_bounds__(kStripeThreads)
 k_checksum_batch(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ lens,
                  uint32_t* __restrict__ crc_out, uint32_t* __restrict__ adler_out, const uint32_t* __restrict__ expect,
@@ -281,7 +282,7 @@ k_checksum_batch(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
     s_tab[threadIdx.x] = g_tab_byte[threadIdx.x];
     __syncthreads();
     const uint64_t i = blockIdx.x;
-    if (expect && ok[i] != 0) return;                         // nothing to verify for a stream that already failed
+    if (expect && (ok[i] != 0 || expect[3 * i + 2] == 0)) return;   // failed already, or not a gzip member
     const uint8_t* buf = base + off[i];
     const uint64_t len = lens ? lens[i] : off[i + 1] - off[i];
     const uint64_t stripe = (len + kStripeThreads - 1) / kStripeThreads;
@@ -321,7 +322,7 @@ k_checksum_batch(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
         const uint32_t s2 = (uint32_t)((len % kAdlerBase + b) % kAdlerBase);
         const uint32_t crc = ~reg, adl = (s2 << 16) | s1;
         if (expect) {
-            if (crc != expect[2 * i] || (uint32_t)len != expect[2 * i + 1]) ok[i] = ZB_DATA_ERROR;
+            if (crc != expect[3 * i] || (uint32_t)len != expect[3 * i + 1]) ok[i] = ZB_DATA_ERROR;
         } else {
             if (crc_out) crc_out[i] = crc;
             if (adler_out) adler_out[i] = adl;

@@ -384,7 +384,7 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
     b.total = in_len * 8;
     seek_bits(b, in, st->bit_off);
     Out o{out, 0, out_cap, st->hist};
-    const int wrap = st->wrap;
+    int wrap = st->wrap;                                        // 3 = zlib or gzip, decided by the first two bytes
     int mode = st->mode;
     int last = st->last;
     uint32_t s1 = st->s1, s2 = st->s2;
@@ -401,6 +401,12 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
     while (stop == kRunning) {
         const uint64_t mark = b.used;
         if (mode == kModeHead) {
+            if (wrap == kWrapAuto) {                  // inflate.c:596: gzip if the stream opens with 1f 8b
+                if (!have(b, 16)) { stop = kShortIn; continue; }
+                refill(b);
+                wrap = peek(b, 16) == 0x8b1fu ? ZB200_WRAP_GZIP : ZB200_WRAP_ZLIB;
+                if (lane == 0) st->wrap = wrap;
+            }
             if (wrap == ZB200_WRAP_ZLIB) {           // inflate.c:589-632
                 if (!have(b, 16)) { stop = kShortIn; continue; }
                 refill(b);
@@ -418,6 +424,46 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
                     st->dict_id = id;
                     mode = kModeDict; stop = kWantDict; continue;
                 }
+            } else if (wrap == ZB200_WRAP_GZIP) {    // inflate.c:596-602, 634-759; nothing is kept of the header fields
+                // bytes are read straight from the input: the header starts on a byte boundary
+                const uint64_t h0 = b.used >> 3;
+                const uint64_t avail = in_len - h0;
+                const uint8_t* hp = in + h0;
+                uint64_t need = 10;
+                int bad = 0;
+                bool shortin = avail < need;
+                uint32_t flg = 0;
+                if (!shortin) {
+                    if (hp[0] != 0x1f || hp[1] != 0x8b) bad = kMsgHeader;
+                    else if (hp[2] != 8) bad = kMsgMethod;
+                    else if (hp[3] & 0xe0) bad = kMsgFlags;
+                    flg = hp[3];
+                }
+                if (!shortin && !bad && (flg & 4)) {                          // FEXTRA: two length bytes, then the field
+                    if (avail < need + 2) shortin = true;
+                    else { need += 2 + ((uint64_t)hp[need] | ((uint64_t)hp[need + 1] << 8)); shortin = avail < need; }
+                }
+                for (int f = 8; f <= 16 && !shortin && !bad; f <<= 1) {       // FNAME, FCOMMENT: zero-terminated
+                    if (!(flg & f)) continue;
+                    while (need < avail && hp[need] != 0) need++;
+                    if (need >= avail) shortin = true; else need++;
+                }
+                if (!shortin && !bad && (flg & 2)) {                          // FHCRC: low 16 bits of the CRC-32 of the header so far
+                    if (avail < need + 2) shortin = true;
+                    else {
+                        uint32_t c = 0xffffffffu;
+                        for (uint64_t k = 0; k < need; k++) {
+                            c ^= hp[k];
+                            for (int j = 0; j < 8; j++) c = (c >> 1) ^ (kCrcPoly & (0u - (c & 1u)));
+                        }
+                        c = ~c;
+                        if ((c & 0xffffu) != ((uint32_t)hp[need] | ((uint32_t)hp[need + 1] << 8))) bad = kMsgHcrc;
+                        need += 2;
+                    }
+                }
+                if (bad) { st->msg = bad; stop = kError; continue; }
+                if (shortin) { stop = kShortIn; continue; }
+                seek_bits(b, in, (h0 + need) * 8);
             } else if (wrap != ZB200_WRAP_RAW) { st->msg = kMsgHeader; stop = kError; continue; }
             mode = kModeBlock;
         } else if (mode == kModeBlock) {
@@ -557,6 +603,15 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
                 adler_fold(s1, s2, o.p + folded, o.pos - folded);
                 folded = o.pos;
                 if (want != ((s2 << 16) | s1)) { st->msg = kMsgCheck; stop = kError; continue; }
+            } else if (wrap == ZB200_WRAP_GZIP) {     // inflate.c:1099-1112; the caller checks CRC-32 and length of the output
+                if (!have(b, pad + 64)) { stop = kShortIn; continue; }
+                drop(b, pad);
+                uint32_t w[2];
+                for (int k = 0; k < 2; k++) {
+                    w[k] = 0;
+                    for (int i = 0; i < 4; i++) { refill(b); w[k] |= peek(b, 8) << (8 * i); drop(b, 8); }
+                }
+                if (lane == 0) { st->crc = w[0]; st->isize = w[1]; st->flags |= kFlagGzipTrailer; }
             } else {
                 if (!have(b, pad)) { stop = kShortIn; continue; }
                 drop(b, pad);
@@ -602,7 +657,7 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
 __global__ void __launch_bounds__(kInfWarps * 32)
 k_inflate_batch(const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_off, uint64_t n,
                 uint8_t* __restrict__ dst, const uint64_t* __restrict__ dst_off,
-                uint64_t* __restrict__ dst_len, int32_t* __restrict__ status, int wrap)
+                uint64_t* __restrict__ dst_len, int32_t* __restrict__ status, int wrap, uint32_t* __restrict__ expect)
 {
     __shared__ WarpTables s_tab[kInfWarps];
     __shared__ InfState s_state[kInfWarps];
@@ -616,6 +671,11 @@ k_inflate_batch(const uint8_t* __restrict__ src, const uint64_t* __restrict__ sr
     __syncwarp();
     const uint64_t a = src_off[i], e = src_off[i + 1], oa = dst_off[i], oe = dst_off[i + 1];
     inflate_warp(src + a, e - a, dst + oa, oe - oa, false, st, &s_tab[warp], &dst_len[i], nullptr, &status[i], nullptr);
+    __syncwarp();
+    if (expect && lane == 0) {                                  // gzip members: {crc32, isize, 1} for the check that follows
+        const bool gz = (st->flags & kFlagGzipTrailer) != 0;
+        expect[3 * i] = st->crc; expect[3 * i + 1] = st->isize; expect[3 * i + 2] = gz ? 1u : 0u;
+    }
 }
 
 // One z_stream: a single warp continues from *st.
@@ -627,14 +687,21 @@ k_inflate_stream(const uint8_t* __restrict__ in, uint64_t in_len, uint8_t* __res
     inflate_warp(in, in_len, out, out_cap, true, st, &s_tab, &res->out_len, &res->in_used, &res->status, &res->msg);
 }
 
+// d_expect: n x 3 words of scratch, needed when wrap is gzip or auto (the CRC-32 / length check runs as a second launch)
 int inflate_batch_launch(const uint8_t* d_src, const uint64_t* d_src_off, size_t n, uint8_t* d_dst,
-                         const uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status, int wrap, cudaStream_t s)
+                         const uint64_t* d_dst_off, uint64_t* d_dst_len, int32_t* d_status, int wrap, uint32_t* d_expect,
+                         cudaStream_t s)
 {
     if (n == 0) return 0;
-    if (wrap != ZB200_WRAP_RAW && wrap != ZB200_WRAP_ZLIB) { set_error("inflate batch: wrap %d not supported", wrap); return ZB_STREAM_ERROR; }
+    if (wrap < 0 || wrap > kWrapAuto) { set_error("inflate batch: wrap %d not supported", wrap); return ZB_STREAM_ERROR; }
+    const bool gz = wrap == ZB200_WRAP_GZIP || wrap == kWrapAuto;
+    if (gz && !d_expect) { set_error("inflate batch: gzip needs check scratch"); return ZB_STREAM_ERROR; }
     const unsigned blocks = (unsigned)((n + kInfWarps - 1) / kInfWarps);
-    ZB_LAUNCH(k_inflate_batch, blocks, kInfWarps * 32, 0, s, d_src, d_src_off, (uint64_t)n, d_dst, d_dst_off, d_dst_len, d_status, wrap);
+    ZB_LAUNCH(k_inflate_batch, blocks, kInfWarps * 32, 0, s, d_src, d_src_off, (uint64_t)n, d_dst, d_dst_off, d_dst_len, d_status, wrap,
+              gz ? d_expect : nullptr);
     ZB_CHECK_LAUNCH();
+    // gzip trailer (inflate.c:1099-1112): CRC-32 and length of what was produced, for every member that decoded
+    if (gz) return checksum_batch_launch(d_dst, d_dst_off, d_dst_len, n, nullptr, nullptr, d_expect, d_status, s);
     return 0;
 }
 
@@ -681,7 +748,11 @@ struct zb200i_inflater {
     uint64_t hist = 0;
     int mode = kModeHead;
     uint32_t check = 1;
+    uint32_t crc = 0;                            // gzip: running CRC-32 and length of everything produced
+    uint64_t produced = 0;
 };
+
+extern "C" unsigned long crc32_combine(unsigned long crc1, unsigned long crc2, long len2);   // zapi_checksum.c
 
 static const char* const kInfMsgs[] = {
     nullptr, "incorrect header check", "unknown compression method", "invalid window size", "need dictionary",
@@ -702,7 +773,8 @@ static int inflater_write_state(zb200i_inflater* h, int wrap)
     st.wrap = wrap; st.mode = kModeHead; st.s1 = 1;
     ZB_CUDA(cudaMemcpyAsync(h->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, h->s));
     ZB_CUDA(cudaStreamSynchronize(h->s));
-    h->wrap = wrap; h->hist = 0; h->mode = kModeHead; h->check = 1; h->carry.clear();
+    h->wrap = wrap; h->hist = 0; h->mode = kModeHead; h->check = wrap >= ZB200_WRAP_GZIP ? 0u : 1u; h->carry.clear();
+    h->crc = 0; h->produced = 0;
     return 0;
 }
 
@@ -745,6 +817,7 @@ extern "C" int zb200i_inflate_clone(zb200i_inflater** out, const zb200i_inflater
     if (e == cudaSuccess) e = cudaMemcpy(h->d_arena, src->d_arena, kWindow32, cudaMemcpyDeviceToDevice);
     if (e != cudaSuccess) { zb200i_inflate_close(h); set_error("inflate state copy failed"); return ZB_MEM_ERROR; }
     h->carry = src->carry; h->hist = src->hist; h->mode = src->mode; h->check = src->check;
+    h->crc = src->crc; h->produced = src->produced;
     *out = h;
     return 0;
 }
@@ -811,6 +884,19 @@ extern "C" int zb200i_inflate_run(zb200i_inflater* h, const uint8_t* in, size_t 
         InfCallResult res;
         ZB_CUDA(cudaMemcpyAsync(&res, h->d_res, sizeof(res), cudaMemcpyDeviceToHost, h->s));
         ZB_CUDA(cudaStreamSynchronize(h->s));
+        if (res.out_len && h->wrap >= ZB200_WRAP_GZIP) {         // gzip (or undecided): CRC-32 of this window joins the running value
+            Ctx* c = ctx_acquire(h->s);
+            if (!c) return ZB_MEM_ERROR;
+            uint32_t piece[2] = {0, 0};
+            int rc2 = c->small.ensure(256);
+            if (!rc2) rc2 = checksum_launch(c, h->d_arena + kWindow32, res.out_len, c->small.as<uint32_t>(), h->s);
+            if (!rc2 && (cudaMemcpyAsync(piece, c->small.p, 8, cudaMemcpyDeviceToHost, h->s) != cudaSuccess ||
+                         cudaStreamSynchronize(h->s) != cudaSuccess)) { set_error("checksum readback failed"); rc2 = ZB_STREAM_ERROR; }
+            ctx_release(c, h->s);
+            if (rc2) return rc2;
+            h->crc = (uint32_t)crc32_combine(h->crc, piece[0], (long)res.out_len);
+            h->produced += res.out_len;
+        }
         if (res.out_len) {
             ZB_CUDA(cudaMemcpyAsync(out + produced, h->d_arena + kWindow32, res.out_len, cudaMemcpyDeviceToHost, h->s));
             ZB_LAUNCH(k_slide_history, 1, 1024, 0, h->s, h->d_arena, h->hist, res.out_len);
@@ -846,7 +932,13 @@ extern "C" int zb200i_inflate_run(zb200i_inflater* h, const uint8_t* in, size_t 
     InfState dst;
     ZB_CUDA(cudaMemcpy(&dst, h->d_state, sizeof(InfState) - sizeof(dst.lens), cudaMemcpyDeviceToHost));
     h->mode = dst.mode;
-    h->check = st == ZB_NEED_DICT ? dst.dict_id : ((dst.s2 << 16) | dst.s1);
+    if (h->wrap == kWrapAuto && dst.wrap != kWrapAuto) h->wrap = dst.wrap;      // the header settled zlib vs gzip
+    h->check = st == ZB_NEED_DICT ? dst.dict_id : h->wrap >= ZB200_WRAP_GZIP ? h->crc : ((dst.s2 << 16) | dst.s1);
+    if (st == ZB_STREAM_END && (dst.flags & kFlagGzipTrailer)) {                // inflate.c:1099-1112
+        if (dst.crc != h->crc) { st = ZB_DATA_ERROR; m = kMsgCheck; }
+        else if (dst.isize != (uint32_t)h->produced) { st = ZB_DATA_ERROR; m = kMsgLength; }
+        if (st == ZB_DATA_ERROR) h->mode = kModeBad;
+    }
     *in_used = taken; *out_len = produced; *status = st; *msg = m; *check = h->check;
     return 0;
 }
@@ -858,8 +950,16 @@ ZB_API int zb200_inflate_batch_dev(const void* d_src, const uint64_t* d_src_off,
 {
     int rc = ensure_init();
     if (rc) return rc;
-    return inflate_batch_launch((const uint8_t*)d_src, d_src_off, n, (uint8_t*)d_dst, d_dst_off, d_dst_len, d_status,
-                                wrap, (cudaStream_t)stream);
+    if (wrap != ZB200_WRAP_GZIP && wrap != kWrapAuto)
+        return inflate_batch_launch((const uint8_t*)d_src, d_src_off, n, (uint8_t*)d_dst, d_dst_off, d_dst_len, d_status,
+                                    wrap, nullptr, (cudaStream_t)stream);
+    Ctx* c = ctx_acquire((cudaStream_t)stream);                  // scratch for the trailer values
+    if (!c) return ZB_MEM_ERROR;
+    if ((rc = c->ws[0].ensure(n * 12 + 16)) == 0)
+        rc = inflate_batch_launch((const uint8_t*)d_src, d_src_off, n, (uint8_t*)d_dst, d_dst_off, d_dst_len, d_status,
+                                  wrap, c->ws[0].as<uint32_t>(), (cudaStream_t)stream);
+    ctx_release(c, (cudaStream_t)stream);
+    return rc;
 }
 
 ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t n, void* dst, const uint64_t* dst_off,
@@ -881,8 +981,8 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             if ((rc = c->out.ensure(dst_total + 16)) != 0) break;
             d_dst = c->out.as<uint8_t>();
         }
-        // descriptors: [src_off n+1][dst_off n+1][dst_len n][status n]
-        const size_t desc_bytes = (size_t)(3 * n + 2) * 8 + n * 4;
+        // descriptors: [src_off n+1][dst_off n+1][dst_len n][status n][gzip trailer values 3n]
+        const size_t desc_bytes = (size_t)(3 * n + 2) * 8 + n * 4 + n * 12;
         if ((rc = c->ws[0].ensure(desc_bytes)) != 0) break;
         uint64_t* d_src_off = c->ws[0].as<uint64_t>();
         uint64_t* d_dst_off = d_src_off + (n + 1);
@@ -891,7 +991,7 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
         cudaError_t e = cudaMemcpyAsync(d_src_off, src_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst_off, dst_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { set_error("descriptor upload failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
-        if ((rc = inflate_batch_launch(d_src, d_src_off, n, d_dst, d_dst_off, d_len, d_status, wrap, s)) != 0) break;
+        if ((rc = inflate_batch_launch(d_src, d_src_off, n, d_dst, d_dst_off, d_len, d_status, wrap, (uint32_t*)(d_status + n), s)) != 0) break;
         e = cudaMemcpyAsync(dst_len, d_len, n * 8, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess && dst_on_host) e = cudaMemcpyAsync(dst, d_dst, dst_total, cudaMemcpyDeviceToHost, s);

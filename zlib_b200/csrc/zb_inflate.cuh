@@ -13,6 +13,9 @@ enum InfMsg { kMsgNone = 0, kMsgHeader, kMsgMethod, kMsgWindow, kMsgNeedDict, kM
               kMsgTooMany, kMsgCodeLens, kMsgRepeat, kMsgLitSet, kMsgDistSet, kMsgBadLit, kMsgBadDist,
               kMsgFar, kMsgCheck, kMsgLength, kMsgFlags, kMsgHcrc };
 
+constexpr int kWrapAuto = 3;             // windowBits + 32: zlib or gzip, detected from the header (inflate.c:596)
+constexpr uint32_t kFlagGzipTrailer = 1;   // InfState::flags: crc / isize hold a gzip trailer that is still to be checked
+
 // Per-call outcome codes of the streaming kernel (beyond zlib's own codes).
 enum { kNeedInput = 100, kNeedOutput = 101 };
 
