@@ -92,6 +92,15 @@ int zb200_deflate_batch(const void *src, const uint64_t *src_off, size_t n,
                         uint32_t *crc, uint32_t *adler, int32_t *status,
                         int level, int wrap, void *stream);
 
+/* ---- ZIP32 archive of n files compressed in one batch (qcsrc/zip.c:902-1128 member by member) ----
+ * names[i] is the member name, file i is src[src_off[i] .. src_off[i+1]) (host memory).  The archive is written
+ * to dst (host memory); *dst_len: in = capacity, out = archive size (the size needed when Z_BUF_ERROR is
+ * returned).  dos_datetime = MS-DOS time in the low and date in the high 16 bits, as in zip.c's dosDate.
+ * Z_STREAM_ERROR beyond ZIP32 (65535 members, sizes and offsets below 4 GiB). */
+size_t zb200_zip_bound(const char *const *names, const uint64_t *src_off, size_t n);
+int zb200_zip_build(const char *const *names, const void *src, const uint64_t *src_off, size_t n,
+                    int level, uint32_t dos_datetime, void *dst, size_t *dst_len);
+
 /* ---- inflate: n independent streams (qcsrc/uncompr.c:26 uncompress, batched) ----
  * Stream i occupies src[src_off[i] .. src_off[i+1]) and is decoded into
  * dst[dst_off[i] .. dst_off[i+1]).  Per stream: dst_len[i] = bytes produced,

@@ -155,3 +155,29 @@ def test_gzip_stream_decoding(gpu_lib):
     assert rc == zb.Z_OK
     rc, out, msg, tin = gpu_lib.inflate_stream(zz, wbits=31, in_chunk=1 << 20, out_chunk=1 << 20)
     assert rc == zb.Z_STREAM_END and out == data
+
+
+def test_zip_archive_from_one_gpu_batch(gpu_lib, tmp_path):
+    """BASELINE config 5 in small: many files compressed by ONE zb200_deflate_batch call and laid out as a ZIP32
+    archive by zb200_zip_build; the reference's miniunz extracts every member bit-exact, Python's zipfile agrees."""
+    import random
+    import zipfile
+    rng = random.Random(31)
+    files = {}
+    for i in range(120):
+        n = int(4096 * (2 ** rng.uniform(0, 9)))                 # 4 KiB .. 2 MiB, log-uniform
+        if i in (3, 4):
+            n = i - 3                                            # an empty and a one-byte member
+        files[f"f{i:05d}.bin"] = zhelpers.corpus(rng.choice([0, 1, 1, 3, 3, 4]), n, 900 + i)
+    arc = gpu_lib.zip_build(files, level=6)
+    path = tmp_path / "batch.zip"
+    path.write_bytes(arc)
+    zf = zipfile.ZipFile(path)
+    assert zf.testzip() is None and len(zf.namelist()) == len(files)
+    assert sum(i.compress_size for i in zf.infolist()) < 0.8 * sum(len(v) for v in files.values())
+    out = tmp_path / "x"
+    out.mkdir()
+    p = subprocess.run([_need(os.path.join(REFDIR, "miniunz")), "-o", str(path)], cwd=out, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    for name, data in files.items():
+        assert (out / name).read_bytes() == data, name

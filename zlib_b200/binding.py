@@ -112,6 +112,8 @@ class Lib:
             "zb200_deflate": (C.c_int, [vp, sz, vp, C.POINTER(sz), C.c_int, C.c_int, vp]),
             "zb200_deflate_shard": (C.c_int, [vp, sz, vp, sz, vp, C.POINTER(sz), C.c_int, C.c_int, C.c_int, u32p, u32p, vp]),
             "zb200_deflate_batch": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
+            "zb200_zip_bound": (sz, [vp, vp, sz]),
+            "zb200_zip_build": (C.c_int, [vp, vp, vp, sz, C.c_int, C.c_uint32, vp, C.POINTER(sz)]),
             "zb200_inflate_batch": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
             "zb200_inflate_batch_dev": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
             "zb200_kernel_launches": (C.c_uint64, []),
@@ -238,6 +240,22 @@ class Lib:
                                                  level, wrap, _stream(stream)), "zb200_deflate_batch")
         outs = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + int(dst_len[i])]) if status[i] == 0 else b"" for i in range(n)]
         return outs, [int(x) for x in status[:n]], [int(x) for x in crc[:n]], [int(x) for x in adl[:n]]
+
+    def zip_build(self, files, level: int = 6, dos_datetime: int = (46 << 25 | 10 << 21 | 18 << 16)):
+        """zb200_zip_build over {name: bytes} -> archive bytes."""
+        import numpy as np
+        names = list(files)
+        n = len(names)
+        arr = (C.c_char_p * max(n, 1))(*[nm.encode() for nm in names])
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(files[nm]) for nm in names], dtype=np.uint64)
+        src = np.frombuffer(b"".join(files[nm] for nm in names) + b"\0" * 8, dtype=np.uint8)
+        cap = self.dll.zb200_zip_bound(arr, off.ctypes.data, n)
+        out = C.create_string_buffer(max(cap, 1))
+        ol = C.c_size_t(cap)
+        self._check(self.dll.zb200_zip_build(arr, src.ctypes.data, off.ctypes.data, n, level, dos_datetime, out, C.byref(ol)),
+                    "zb200_zip_build")
+        return out.raw[:ol.value]
 
     def inflate_batch(self, streams, caps, wrap: int = WRAP_ZLIB, stream=None):
         """zb200_inflate_batch over a list of bytes objects; returns (outputs, statuses)."""
