@@ -237,6 +237,7 @@ __device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, c
     uint32_t hq = lds32u(s_mem, o + qoff);
     do {
         if (acc > kWindow) break;
+        const uint32_t d = *(dp - acc);                         // next link: issued before the compare so the L2 trip overlaps it
         const uint32_t co = o - acc;
         const uint32_t x = lds32u(s_mem, co + qoff) ^ hq;
         if ((x & qmask) == 0) {
@@ -259,7 +260,6 @@ __device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, c
                 hq = lds32u(s_mem, o + qoff);
             }
         }
-        const uint32_t d = *(dp - acc);
         if (d == 0) break;
         acc += d;
     } while (--chain > 0);
