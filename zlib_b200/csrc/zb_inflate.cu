@@ -296,21 +296,35 @@ __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t*
     const uint64_t room64 = o.cap - o.pos, back64 = o.pos + o.hist;
     const uint32_t room = room64 > 0x7fffffffu ? 0x7fffffffu : (uint32_t)room64;
     const uint32_t back = back64 > 0x7fffffffu ? 0x7fffffffu : (uint32_t)back64;   // bytes behind p at entry
-    uint32_t consumed = 0, produced = 0, mark = 0;
+    if (room < 260 || nwords < 3) return kRunning;
+    // a symbol may start while nextw <= w_lim (>= 72 valid bits ahead) and produced <= p_lim (>= 260 bytes of room);
+    // the bit position is nextw * 32 - cnt, kept in 32 bits: the loop returns before 2^28 bits go by
+    const uint32_t w_lim = min(nwords - 3, nextw + (1u << 23));
+    const uint32_t p_lim = room - 260;
+    const uint32_t entry32 = nextw * 32u - (uint32_t)cnt;
+    uint32_t produced = 0, mark32 = entry32;
     bool rewind = false;
     Stop result = kRunning;
     for (;;) {
-        if (nextw + 3 > nwords || produced + 258 > room) break;
-        mark = consumed;
-        if (cnt <= 32) { buf |= (uint64_t)__ldg(words + nextw) << cnt; nextw++; cnt += 32; }
+        if (nextw > w_lim || produced > p_lim) break;
+        mark32 = nextw * 32u - (uint32_t)cnt;
+        if (__builtin_expect(cnt <= 32, 0)) { buf |= (uint64_t)__ldg(words + nextw) << cnt; nextw++; cnt += 32; }
         const uint32_t e = t->lit[(uint32_t)buf & (kLitSize - 1)];
         const uint32_t len = e & 15u;
         if (len == 0) { rewind = true; break; }
-        buf >>= len; cnt -= (int)len; consumed += len;
+        buf >>= len; cnt -= (int)len;
         const uint32_t kind = (e >> 8) & 3u;
         if (kind == kLit) {
-            if (lane == 0) p[produced] = (uint8_t)(e >> 16);
+            // literals come in runs: try the next symbol too -- at least 18 bits are left, enough for any code
+            const uint32_t e2 = t->lit[(uint32_t)buf & (kLitSize - 1)];
+            const uint32_t len2 = e2 & 15u;
+            const bool lit2 = len2 != 0 && ((e2 >> 8) & 3u) == kLit;
+            if (lane == 0) {
+                p[produced] = (uint8_t)(e >> 16);
+                if (lit2) p[produced + 1] = (uint8_t)(e2 >> 16);
+            }
             produced++;
+            if (lit2) { buf >>= len2; cnt -= (int)len2; produced++; }
             continue;
         }
         if (kind != kBase) {
@@ -319,15 +333,15 @@ __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t*
         }
         const uint32_t xl = (e >> 4) & 15u;
         const uint32_t mlen = (e >> 16) + ((uint32_t)buf & ((1u << xl) - 1u));
-        buf >>= xl; cnt -= (int)xl; consumed += xl;
+        buf >>= xl; cnt -= (int)xl;
         if (cnt <= 32) { buf |= (uint64_t)__ldg(words + nextw) << cnt; nextw++; cnt += 32; }
         const uint32_t de = t->dist[(uint32_t)buf & (kDistSize - 1)];
         const uint32_t dl = de & 15u;
         if (dl == 0 || ((de >> 8) & 3u) != kBase) { rewind = true; break; }
-        buf >>= dl; cnt -= (int)dl; consumed += dl;
+        buf >>= dl; cnt -= (int)dl;
         const uint32_t xd = (de >> 4) & 15u;
         const uint32_t dist = (de >> 16) + ((uint32_t)buf & ((1u << xd) - 1u));
-        buf >>= xd; cnt -= (int)xd; consumed += xd;
+        buf >>= xd; cnt -= (int)xd;
         if (dist > back + produced) { rewind = true; break; }
         uint8_t* d = p + produced;
         const uint8_t* s = d - dist;
@@ -342,9 +356,10 @@ __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t*
     }
     o.pos += produced;
     if (rewind) {
-        seek_bits(b, in, b.used + mark);
+        seek_bits(b, in, b.used + (uint32_t)(mark32 - entry32));
     } else {
-        b.buf = buf; b.cnt = cnt; b.nextw = nextw; b.used += consumed;
+        b.used += (uint32_t)(nextw * 32u - (uint32_t)cnt - entry32);
+        b.buf = buf; b.cnt = cnt; b.nextw = nextw;
     }
     return result;
 }
