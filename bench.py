@@ -49,37 +49,61 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  NVML when importable (a sample
+    every 2 ms: the timed region is ~0.1 s), else the nvidia-smi query of the profiling recipe."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:   # noqa: BLE001
+            self.nvml = None
+
+    def _nvml_row(self):
+        n = self.nvml
+        mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [bool(r & n.nvmlClocksThrottleReasonHwSlowdown), bool(r & n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 bool(r & n.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & n.nvmlClocksThrottleReasonSwPowerCap)]
+        return [str(mhz), str(self.max_mhz)] + ["Active" if f else "Not Active" for f in flags]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():
             try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._nvml_row())
+                else:
+                    o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                       capture_output=True, text=True, timeout=5).stdout.strip()
+                    if o:
+                        self.rows.append([x.strip() for x in o.split(",")])
             except Exception:   # noqa: BLE001
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.002 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for i, nme in enumerate(names):
+            for i, nme in enumerate(self.NAMES):
                 if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
                     reasons.add(nme)
         mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------- reference arm

@@ -781,19 +781,36 @@ __global__ void __launch_bounds__(1024) k_scan(uint64_t nchunks, ChunkMeta* __re
 // K3: bit packing
 // ------------------------------------------------------------------------------------------
 constexpr int kPackThreads = 256;
-constexpr int kStageWords = (kPackThreads * 48 + 64) / 32 + 4;
+constexpr int kStageWords = (kPackThreads * 96 + 64) / 32 + 4;  // two symbols of <= 48 bits per thread and round
 
 struct Packer {
-    uint32_t* stage;                                            // shared staging window, bit 0 = first unwritten bit of byte `bytepos`
+    uint32_t* stage;                                            // two shared staging windows, used alternately; bit 0 of the
+    uint32_t par;                                               // current one (0/1) = first unwritten bit of byte `bytepos`
     uint32_t* warp_sums;                                        // shared, kPackThreads/32 entries
     uint8_t* dst;                                               // chunk output
     uint64_t bytepos;                                           // bytes already written to dst
-    uint32_t carry_bits;                                        // bits pending in stage[0] (0..7)
+    uint32_t carry_bits;                                        // bits pending in word 0 of the current window (0..7)
+    uint32_t prev_words;                                        // words of the other window that the previous round dirtied
 
-    // every thread contributes (value, nbits <= 48); bits are appended in thread order
-    __device__ void round(uint64_t value, uint32_t nbits)
+    __device__ __forceinline__ void put(uint32_t* st, uint32_t off, uint64_t value)
+    {
+        const uint32_t sh = off & 31, wi = off >> 5;
+        const uint64_t lo = value << sh;
+        atomicOr(&st[wi], (uint32_t)lo);
+        const uint32_t mid = (uint32_t)(lo >> 32);
+        if (mid) atomicOr(&st[wi + 1], mid);
+        if (sh) { const uint32_t hi = (uint32_t)(value >> (64 - sh)); if (hi) atomicOr(&st[wi + 2], hi); }
+    }
+
+    // Every thread contributes two symbols (value, nbits <= 48 each); bits are appended in thread order, a thread's
+    // first symbol before its second.  Two barriers per round: the window written in this round is drained after
+    // the second one, and the other window (drained one round ago) is cleared for the next round meanwhile.
+    __device__ void round(uint64_t v0, uint32_t n0, uint64_t v1 = 0, uint32_t n1 = 0)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t* cur = stage + par * kStageWords;
+        uint32_t* oth = stage + (par ^ 1u) * kStageWords;
+        const uint32_t nbits = n0 + n1;
         uint32_t x = nbits;
 #pragma unroll
         for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(kFullMask, x, k); if (lane >= k) x += y; }
@@ -803,24 +820,17 @@ struct Packer {
 #pragma unroll
         for (int w = 0; w < kPackThreads / 32; w++) { const uint32_t s = warp_sums[w]; if (w < warp) before += s; total += s; }
         const uint32_t off = carry_bits + before + x - nbits;
-        if (nbits) {
-            const uint32_t sh = off & 31, wi = off >> 5;
-            const uint64_t lo = value << sh;
-            atomicOr(&stage[wi], (uint32_t)lo);
-            const uint32_t mid = (uint32_t)(lo >> 32);
-            if (mid) atomicOr(&stage[wi + 1], mid);
-            if (sh) { const uint32_t hi = (uint32_t)(value >> (64 - sh)); if (hi) atomicOr(&stage[wi + 2], hi); }
-        }
+        if (n0) put(cur, off, v0);
+        if (n1) put(cur, off + n0, v1);
         __syncthreads();
         const uint32_t tbits = carry_bits + total, nbytes = tbits >> 3;
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage);
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(cur);
         for (uint32_t i = threadIdx.x; i < nbytes; i += kPackThreads) dst[bytepos + i] = sb[i];
         const uint32_t tail = (tbits & 7) ? sb[nbytes] : 0u;
-        __syncthreads();
-        const uint32_t used_words = (tbits + 31) / 32 + 1;
-        for (uint32_t i = threadIdx.x; i < used_words && i < (uint32_t)kStageWords; i += kPackThreads) stage[i] = i == 0 ? tail : 0u;
-        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < prev_words; i += kPackThreads) oth[i] = i == 0 ? tail : 0u;   // word 0 carries the pending bits over
+        prev_words = min((tbits + 31) / 32 + 1, (uint32_t)kStageWords);
         bytepos += nbytes; carry_bits = tbits & 7;
+        par ^= 1;
     }
 };
 
@@ -831,7 +841,7 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
             const ChunkMeta* __restrict__ chunks, uint8_t* __restrict__ out, uint64_t cap, int last_is_final,
             int force_mark, uint32_t* __restrict__ err)
 {
-    __shared__ uint32_t s_stage[kStageWords];
+    __shared__ uint32_t s_stage[2][kStageWords];
     __shared__ uint32_t s_sums[kPackThreads / 32];
     __shared__ uint32_t s_codes[kHistSize];
     const uint64_t c = blockIdx.x;
@@ -862,9 +872,9 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
         return;
     }
 
-    for (int i = threadIdx.x; i < kStageWords; i += kPackThreads) s_stage[i] = 0;
+    for (int i = threadIdx.x; i < 2 * kStageWords; i += kPackThreads) (&s_stage[0][0])[i] = 0;
     __syncthreads();
-    Packer pk{s_stage, s_sums, dst, 0, 0};
+    Packer pk{&s_stage[0][0], 0, s_sums, dst, 0, 0, 1};
     bool ends_stored = false;
     for (uint32_t j = 0; j < cm.nblocks; j++) {
         const uint64_t b = c * kBlocksPerChunk + j;
@@ -903,11 +913,10 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
         }
         const uint32_t* t = tok + b * kBlockBytes;
         const uint32_t cnt = blk_ntok[b];
-        for (uint32_t i0 = 0; i0 <= cnt; i0 += kPackThreads) {
-            const uint32_t i = i0 + threadIdx.x;
-            uint64_t v = 0; uint32_t nb = 0;
+        auto encode = [&](uint32_t i, uint32_t tk, uint64_t& v, uint32_t& nb) {   // symbol i of the block: token, or end-of-block
+            v = 0; nb = 0;
             if (i < cnt) {
-                const uint32_t tk = t[i], dist = tk >> 16;
+                const uint32_t dist = tk >> 16;
                 if (dist == 0) {
                     const uint32_t e = s_codes[tk & 0xff];
                     v = e & 0xffffu; nb = e >> 16;
@@ -925,7 +934,16 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
                 const uint32_t e = s_codes[256];                // end of block
                 v = e & 0xffffu; nb = e >> 16;
             }
-            pk.round(v, nb);
+        };
+        for (uint32_t i0 = 0; i0 <= cnt; i0 += 2 * kPackThreads) {
+            const uint32_t i = i0 + 2 * threadIdx.x;
+            uint2 tk = make_uint2(0, 0);
+            if (i + 1 < cnt) tk = *reinterpret_cast<const uint2*>(t + i);   // the block's token array is 8-byte aligned
+            else if (i < cnt) tk.x = t[i];
+            uint64_t v0, v1; uint32_t n0, n1;
+            encode(i, tk.x, v0, n0);
+            encode(i + 1, tk.y, v1, n1);
+            pk.round(v0, n0, v1, n1);
         }
     }
     // end of chunk: final -> pad; otherwise empty stored block unless already byte-aligned by a stored block
