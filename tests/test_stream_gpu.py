@@ -181,3 +181,26 @@ def test_zip_archive_from_one_gpu_batch(gpu_lib, tmp_path):
     assert p.returncode == 0, p.stdout + p.stderr
     for name, data in files.items():
         assert (out / name).read_bytes() == data, name
+
+
+def test_strategies(gpu_lib, oracle):
+    """deflateInit2 strategies (deflate.c:1485-1494, 1594-1612, trees.c:986): every one decodes; Z_RLE only emits
+    distance-1 matches, Z_HUFFMAN_ONLY none, Z_FIXED only fixed blocks; sizes order like the reference's."""
+    import zlib
+    data = (zhelpers.corpus(1, 200000, 5) + bytes(50000) + zhelpers.corpus(3, 100000, 6) + b"ab" * 30000)
+    sizes = {}
+    for strategy in (0, 1, 2, 3, 4):
+        for level in (1, 6):
+            rc, z = gpu_lib.deflate_stream(data, level=level, wbits=15, strategy=strategy)
+            assert rc == zb.Z_OK
+            assert zlib.decompress(z) == data
+            rc2, out, used = oracle.inflate(z, len(data))
+            assert rc2 == 0 and out == data
+            sizes[(strategy, level)] = len(z)
+            ref = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+            want = len(ref.compress(data) + ref.flush())
+            assert len(z) <= 1.03 * want + 64, (strategy, level, len(z), want)
+            if strategy >= 2:
+                assert (z[1] >> 6) == 0                               # FLEVEL = fastest (deflate.c:628)
+    assert sizes[(2, 6)] > sizes[(3, 6)] > sizes[(0, 6)]              # Huffman only > RLE > default
+    assert sizes[(1, 6)] >= sizes[(0, 6)]

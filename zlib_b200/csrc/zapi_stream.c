@@ -223,7 +223,7 @@ static int zs_compress(z_streamp strm, int level, int final, int force_mark)
     int rc, flags = ZB200_DEFLATE_NO_HEADER | ZB200_DEFLATE_NO_TRAILER;
     if (!final) flags |= ZB200_DEFLATE_NOT_LAST;
     if (force_mark) flags |= ZB200I_DEFLATE_FORCE_MARK;
-    if (s->strategy == Z_HUFFMAN_ONLY || s->strategy == Z_FIXED || s->strategy == Z_RLE) flags |= (s->strategy << 8);
+    if (s->strategy != Z_DEFAULT_STRATEGY) flags |= (s->strategy << 8);       /* Z_FILTERED, Z_HUFFMAN_ONLY, Z_RLE, Z_FIXED */
     cap = (size_t)compressBound((uLong)s->in_len) + 64;
     if (s->out_pos == s->out_len) s->out_pos = s->out_len = 0;
     if (zs_reserve(&s->out, &s->out_cap, s->out_len + cap)) return Z_MEM_ERROR;

@@ -266,10 +266,28 @@ __device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, c
     return f;
 }
 
+// Z_RLE (deflate.c:1485-1494, 1594-1598): the only candidate is the previous byte, i.e. a match is a run.
+__device__ __forceinline__ Found walk_search_rle(const uint8_t* s_mem, uint32_t o, bool has_prev, uint32_t maxlen, uint32_t prev_len)
+{
+    Found f{kMinMatch - 1, 0};
+    if (prev_len > f.len) f.len = prev_len;
+    if (!has_prev) return f;
+    uint32_t len = 0;
+    while (len < maxlen) {
+        const uint32_t y = lds32u(s_mem, o + len) ^ lds32u(s_mem, o - 1 + len);
+        if (y) { len += (uint32_t)(__ffs(y) - 1) >> 3; break; }
+        len += 4;
+    }
+    len = min(len, maxlen);
+    if (len > f.len) { f.len = len; f.dist = 1; }
+    return f;
+}
+
 __global__ void __launch_bounds__(kWalkThreads, 2)
 k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
           uint32_t* __restrict__ tok_tmp, uint32_t* __restrict__ tok, uint32_t* __restrict__ blk_ntok,
-          uint32_t* __restrict__ blk_hist, int kind, int max_chain, uint32_t nice, uint32_t max_lazy, uint32_t good)
+          uint32_t* __restrict__ blk_hist, int kind, int max_chain, uint32_t nice, uint32_t max_lazy, uint32_t good,
+          int strategy)
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
     __shared__ uint32_t s_hist[kHistSize];
@@ -309,8 +327,10 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
             while (pos < s1) {
                 const uint32_t maxlen = min(kMaxMatch, blk_end - pos);
                 Found f{0, 0};
-                if (maxlen >= kMinMatch && max_chain > 0)
-                    f = walk_search(s_mem, sm_off + pos - win_beg, dist16 + pos, maxlen, max_chain, min(nice, maxlen), 0);
+                if (maxlen >= kMinMatch && max_chain > 0) {
+                    if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, 0);
+                    else f = walk_search(s_mem, sm_off + pos - win_beg, dist16 + pos, maxlen, max_chain, min(nice, maxlen), 0);
+                }
                 if (f.len >= kMinMatch) { mine[ntok++] = (f.dist << 16) | (f.len - kMinMatch); pos += f.len; }
                 else { mine[ntok++] = byte_at(pos); pos++; }
             }
@@ -325,9 +345,10 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                     const uint32_t maxlen = blk_end - pos < kMaxMatch ? blk_end - pos : kMaxMatch;
                     if (maxlen >= kMinMatch && prev_len < max_lazy) {
                         const int chain = prev_len >= good ? max(max_chain >> 2, 1) : max_chain;
-                        f = walk_search(s_mem, sm_off + pos - win_beg, dist16 + pos, maxlen, chain, min(nice, maxlen), prev_len);
+                        if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, prev_len);
+                        else f = walk_search(s_mem, sm_off + pos - win_beg, dist16 + pos, maxlen, chain, min(nice, maxlen), prev_len);
                         if (f.dist == 0) f.len = kMinMatch - 1;                  // nothing longer than the pending match
-                        if (f.len == kMinMatch && f.dist > kTooFar) f.len = kMinMatch - 1;
+                        if (f.len <= 5 && (strategy == 1 || (f.len == kMinMatch && f.dist > kTooFar))) f.len = kMinMatch - 1;   // Z_FILTERED, TOO_FAR
                     }
                 }
                 if (prev_len >= kMinMatch && f.len <= prev_len) {               // the pending match wins
@@ -967,6 +988,7 @@ __global__ void k_frame(uint8_t* __restrict__ out, uint64_t cap, uint64_t hdr_le
                         const uint32_t* __restrict__ sums, uint64_t n, int level, int wrap, int flags, uint64_t* __restrict__ total_out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int strat = (flags >> 8) & 7;                         // Z_HUFFMAN_ONLY and above report the fastest level
     uint64_t pos = d_end[0];                                    // header + every slab's payload
     uint8_t trailer[8]; int tl = 0;
     if (!(flags & (ZB200_DEFLATE_NO_TRAILER | ZB200_DEFLATE_NOT_LAST))) {
@@ -984,12 +1006,12 @@ __global__ void k_frame(uint8_t* __restrict__ out, uint64_t cap, uint64_t hdr_le
     if (pos + tl > cap) return;
     if (hdr_len) {
         if (wrap == ZB200_WRAP_ZLIB) {
-            const uint32_t fl = level < 2 ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;
+            const uint32_t fl = (level < 2 || strat >= 2) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;   // deflate.c:628-636
             uint32_t h = (0x78u << 8) | (fl << 6);
             h += 31 - h % 31;
             out[0] = h >> 8; out[1] = h;
         } else if (wrap == ZB200_WRAP_GZIP) {
-            const uint8_t g[10] = {31, 139, 8, 0, 0, 0, 0, 0, (uint8_t)(level == 9 ? 2 : level < 2 ? 4 : 0), 3};
+            const uint8_t g[10] = {31, 139, 8, 0, 0, 0, 0, 0, (uint8_t)(level == 9 ? 2 : (level < 2 || strat >= 2) ? 4 : 0), 3};   // deflate.c:590-593
             for (int i = 0; i < 10; i++) out[i] = g[i];
         }
     }
@@ -1048,13 +1070,13 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
         d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
         d_ntok = c->ws[10].as<uint32_t>();
         const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
-        if (cfg.chain != 0) {
+        if (cfg.chain != 0 && P.strategy != 3) {                // Z_RLE needs no chains
             // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
             if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
             else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
         }
         ZB_LAUNCH(k_lz_walk, (unsigned)nblocks, kWalkThreads, kWalkSmem, s, d_buf, (uint32_t)total, (uint32_t)dict, d_dist, d_tmp,
-                  d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy, (uint32_t)cfg.good);
+                  d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy, (uint32_t)cfg.good, P.strategy);
         ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, n, d_blk, d_hist,
                   d_codes, d_hdr, P.strategy == 4 ? 1 : 0);
     }
