@@ -283,7 +283,7 @@ __device__ __forceinline__ Found walk_search_rle(const uint8_t* s_mem, uint32_t 
     return f;
 }
 
-__global__ void __launch_bounds__(kWalkThreads, 2)
+__global__ void __launch_bounds__(kWalkThreads, 3)
 k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
           uint32_t* __restrict__ tok_tmp, uint32_t* __restrict__ tok, uint32_t* __restrict__ blk_ntok,
           uint32_t* __restrict__ blk_hist, int kind, int max_chain, uint32_t nice, uint32_t max_lazy, uint32_t good,

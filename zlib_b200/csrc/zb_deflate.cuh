@@ -5,7 +5,7 @@
 namespace zb {
 
 constexpr uint32_t kChunk = ZB200_CHUNK;         // input bytes linked by one CTA / packed by one CTA; ends byte-aligned
-constexpr uint32_t kBlockBytes = 65536;          // input bytes per DEFLATE block = per CTA of the walk kernel (the reference
+constexpr uint32_t kBlockBytes = 32768;          // input bytes per DEFLATE block = per CTA of the walk kernel (the reference
 constexpr uint32_t kBlocksPerChunk = kChunk / kBlockBytes;   // closes a block every 16 Ki symbols, 45-60 KiB of text, deflate.c:291)
 constexpr uint32_t kWindow = 32768;              // DEFLATE history (h/zconf.h MAX_WBITS = 15)
 constexpr uint32_t kMinMatch = 3, kMaxMatch = 258;
