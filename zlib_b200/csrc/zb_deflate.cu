@@ -1042,7 +1042,8 @@ struct DeflateParams {
 // out[(*d_start or 0) + start_add]; *d_end receives where the next slab starts.  Everything is asynchronous on s.
 static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint64_t n, uint8_t* d_out, uint64_t cap,
                                const DeflateParams& P, int last_is_final, int force_mark, const uint64_t* d_start,
-                               uint64_t start_add, uint64_t* d_end, uint32_t* d_err, cudaStream_t s)
+                               uint64_t start_add, uint64_t* d_end, uint32_t* d_err, cudaStream_t s,
+                               cudaEvent_t prev_scanned = nullptr, cudaEvent_t scanned = nullptr)
 {
     const LevelCfg& cfg = P.cfg;
     const uint64_t total = dict + n;
@@ -1081,7 +1082,11 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
                   d_codes, d_hdr, P.strategy == 4 ? 1 : 0);
     }
     ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0, force_mark);
+    // Slabs alternate between two streams; only the running output offset links them: this slab's offsets need the
+    // end of the previous slab, everything before this point (link, walk, codes, plan) does not.
+    if (prev_scanned) ZB_CUDA(cudaStreamWaitEvent(s, prev_scanned, 0));
     ZB_LAUNCH(k_scan, 1, 1024, 0, s, nchunks, d_chunks, d_start, start_add, d_end);
+    if (scanned) ZB_CUDA(cudaEventRecord(scanned, s));
     ZB_LAUNCH(k_huff_pack, (unsigned)nchunks, kPackThreads, 0, s, d_src, n, d_tok, d_ntok, d_blk, d_codes, d_hdr, d_chunks, d_out, cap,
               last_is_final, force_mark, d_err);
     ZB_CHECK_LAUNCH();
@@ -1161,16 +1166,25 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
 
     Ctx* c = ctx_acquire((cudaStream_t)stream);
     if (!c) return ZB_MEM_ERROR;
+    Ctx* c2 = nullptr;
     cudaStream_t s = pick_stream(c, stream);
     const size_t cap = *dst_len;
     do {
         const bool src_on_host = n != 0 && classify(src) != kDevice;
         const bool dst_on_host = classify(dst) != kDevice;
-        if ((rc = c->ensure_aux((int)(2 * nslabs + 2))) != 0) break;
+        if ((rc = c->ensure_aux((int)(3 * nslabs + 4))) != 0) break;
         cudaStream_t s_in = c->aux[0], s_out = c->aux[1];
         cudaEvent_t* ev_in = c->evs;
         cudaEvent_t* ev_done = c->evs + nslabs;
+        cudaEvent_t* ev_scan = c->evs + 2 * nslabs;
+        cudaEvent_t ev_start = c->evs[3 * nslabs + 1], ev_join = c->evs[3 * nslabs + 2];
         cudaError_t e = cudaSuccess;
+        // Odd slabs run on a second context and stream: the walk kernel is latency bound and leaves issue slots and
+        // some shared memory free, which the pack / code kernels of the neighbouring slab can use.
+        if (nslabs > 1 && !c2 && !g_profile) {                  // per-kernel timing (zb200_profile) wants the slabs serialized
+            c2 = ctx_acquire_own();
+            if (!c2) { rc = ZB_MEM_ERROR; break; }
+        }
         // ---- [dict][src] as one contiguous device range ----
         const uint8_t* d_buf;
         bool stage_slabs = false;                               // source slabs still have to be copied in
@@ -1186,8 +1200,8 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
             stage_slabs = true;
             cudaStreamWaitEvent(s_in, c->idle, 0);              // the staging buffer may still be read by the previous borrower
             if (!src_on_host) {                                 // device source produced on the caller's stream
-                cudaEventRecord(c->evs[2 * nslabs], s);
-                cudaStreamWaitEvent(s_in, c->evs[2 * nslabs], 0);
+                cudaEventRecord(c->evs[3 * nslabs], s);
+                cudaStreamWaitEvent(s_in, c->evs[3 * nslabs], 0);
             }
             if (dict_len) {
                 e = cudaMemcpyAsync(c->in.p, dict, dict_len, cudaMemcpyDefault, s_in);
@@ -1209,6 +1223,10 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
         uint64_t* h_res = (uint64_t*)c->pinned;                 // [0..3] result words, [4..] slab ends
         uint64_t* h_pos = h_res + 4;
         if ((e = cudaMemsetAsync(d_err, 0, 4, s)) != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        if (c2) {                                               // the second stream starts where the caller's stream is now
+            cudaEventRecord(ev_start, s);
+            cudaStreamWaitEvent(c2->own_stream, ev_start, 0);
+        }
 
         // ---- slabs: copy in (own stream) -> kernels (s) -> slab end to the host ----
         const uint8_t* d_src = d_buf + dict_len;
@@ -1217,22 +1235,30 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
         }
         for (uint64_t i = 0; i < nslabs; i++) {
             const uint64_t off = i * slab, len = n - off < slab ? n - off : slab;
+            Ctx* cl = (c2 && (i & 1)) ? c2 : c;
+            cudaStream_t sl = (c2 && (i & 1)) ? c2->own_stream : s;
             if (stage_slabs) {
                 e = cudaMemcpyAsync((uint8_t*)d_src + off, (const uint8_t*)src + off, len, cudaMemcpyDefault, s_in);
                 if (e == cudaSuccess) e = cudaEventRecord(ev_in[i], s_in);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev_in[i], 0);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(sl, ev_in[i], 0);
+                if (e == cudaSuccess && c2 && i + 1 < nslabs) e = cudaStreamWaitEvent((i & 1) ? s : c2->own_stream, ev_in[i], 0);   // its tail is the next slab's dictionary
                 if (e != cudaSuccess) { set_error("input staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
             }
             const uint64_t dlen = i == 0 ? dict_len : kWindow;  // later slabs see the tail of the previous one
             const bool last = i == nslabs - 1;
-            rc = deflate_slab_launch(c, d_src + off - dlen, dlen, len, d_out, cap, P, last && last_is_final, last ? force_mark : 0,
-                                     i ? d_pos + i - 1 : nullptr, i ? 0 : hdr_len, d_pos + i, d_err, s);
+            rc = deflate_slab_launch(cl, d_src + off - dlen, dlen, len, d_out, cap, P, last && last_is_final, last ? force_mark : 0,
+                                     i ? d_pos + i - 1 : nullptr, i ? 0 : hdr_len, d_pos + i, d_err, sl,
+                                     i ? ev_scan[i - 1] : nullptr, last ? nullptr : ev_scan[i]);
             if (rc) break;
             if (dst_on_host && !last) {
-                e = cudaMemcpyAsync(h_pos + i, d_pos + i, 8, cudaMemcpyDeviceToHost, s);
-                if (e == cudaSuccess) e = cudaEventRecord(ev_done[i], s);
+                e = cudaMemcpyAsync(h_pos + i, d_pos + i, 8, cudaMemcpyDeviceToHost, sl);
+                if (e == cudaSuccess) e = cudaEventRecord(ev_done[i], sl);
                 if (e != cudaSuccess) { set_error("slab bookkeeping failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
             }
+        }
+        if (c2) {                                               // join the second stream
+            cudaEventRecord(ev_join, c2->own_stream);
+            cudaStreamWaitEvent(s, ev_join, 0);
         }
         if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(s_in); break; }
         // ---- checksums of the uncompressed data (read_buf, deflate.c:956-981), header, trailer ----
@@ -1274,6 +1300,7 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
             if (e != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         }
     } while (0);
+    if (c2) ctx_release(c2, c2->own_stream);
     ctx_release(c, s);
     return rc;
 }
