@@ -13,13 +13,13 @@
 //              barriers.  Output: for every position the distance to the previous position with the same
 //              3-byte hash (the reference's prev[] chain, stored as deltas so chains cross chunk boundaries
 //              and the 32 KiB of history in front of a chunk needs no copy -- it is simply there).
-//   K1b walk   one CTA per 64 KiB block, window staged in shared memory, one thread per 128-byte sub-unit
+//   K1b walk   one CTA per 32 KiB block, window staged in shared memory, one thread per 64-byte sub-unit
 //              running the reference's own search-emit-skip loop (deflate_fast, or deflate_slow with max_lazy,
 //              good_match and TOO_FAR, deflate.c:1448-1674): chain candidates up to max_chain
 //              (configuration_table, deflate.c:137-149), quick reject on the word a longer match must reach,
 //              nice_match.  Sub-unit boundaries are reconciled afterwards (prefix maximum of end positions);
 //              tokens are compacted per block and tallied into the block histogram.
-//   K2 codes   one warp per block (64 KiB of input) builds the three length-limited canonical
+//   K2 codes   one warp per block (32 KiB of input) builds the three length-limited canonical
 //              codes (sort + two-queue merge, the reference's overflow repair), prices stored / fixed /
 //              dynamic with the reference's rule (trees.c:955-1001) and serialises the dynamic header.
 //   plan+scan  exact compressed size of every chunk -> exclusive prefix sum -> byte offsets.
@@ -186,14 +186,14 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// K1b: match search + parse, one thread per 128-byte sub-unit, window staged in shared memory
+// K1b: match search + parse, one thread per 64-byte sub-unit, window staged in shared memory
 // ------------------------------------------------------------------------------------------
 // A parse only needs a match where a token starts (one position in three on text), and a kernel with one thread per
 // position both searches everywhere and leaves lanes idle while a neighbour extends a match (round 1 measured it:
 // 4x the instructions of this kernel).  This kernel works the way deflate_fast / deflate_slow do -- search, emit,
-// skip the matched bytes (deflate.c:1448-1674) -- with one thread per 128-byte sub-unit, so every lane is always
+// skip the matched bytes (deflate.c:1448-1674) -- with one thread per 64-byte sub-unit, so every lane is always
 // searching a position that matters.
-//   * One CTA per 64 KiB block: the block, the 32 KiB in front of it and 272 bytes of lookahead are staged in
+//   * One CTA per 32 KiB block (3 CTAs per SM): the block, the 32 KiB in front of it and 272 bytes of lookahead are staged in
 //     shared memory once (16-byte loads); every candidate comparison then reads shared memory.  Only the chain
 //     links (dist16) come from global memory; they are L2 hits because the CTAs in flight cover a few tens of MiB.
 //   * Sub-units start parsing at their boundary without knowing where the previous sub-unit's last token ends.
@@ -204,13 +204,12 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
 //   * Tokens go to a private region per thread, then each warp copies its 32 regions into the block's contiguous
 //     token array with coalesced stores and tallies the block histogram on the way (dense shared-memory atomics).
 constexpr int kWalkThreads = 512;
-constexpr uint32_t kSub = kBlockBytes / kWalkThreads;           // 128 input bytes per thread
+constexpr uint32_t kSub = kBlockBytes / kWalkThreads;           // 64 input bytes per thread
 constexpr uint32_t kSubSlots = kSub + 2;                        // token slots per thread; two spare in front for the fix-up
 constexpr uint32_t kWalkPad = 272;                              // lookahead behind the block (kMaxMatch + word slack)
 // Shared-memory image of the window: rows of 128 bytes followed by one pad word that repeats the first word of
-// the next row.  The lanes of a warp sit 128 bytes apart (one sub-unit each); with 132-byte rows their words fall
-// into 32 different banks, and an unaligned 4-byte read that starts in the last bytes of a row still finds its
-// continuation in the pad word.
+// the next row.  The lanes of a warp sit 64 bytes apart (one sub-unit each): without the skew they would share two
+// banks; with 132-byte rows a pair of lanes shifts by one bank per row and the 32 lanes cover all 32 banks.  An unaligned 4-byte read that starts in the last bytes of a row still finds its continuation in the pad word.
 constexpr uint32_t kWalkRows = (kWindow + kBlockBytes + kWalkPad + 16 + 127) / 128 + 1;
 constexpr uint32_t kWalkSmem = kWalkRows * 132;
 __device__ __forceinline__ uint32_t smap(uint32_t off) { return off + ((off >> 7) << 2); }
@@ -689,7 +688,7 @@ k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict
         uint32_t opt_lenb = (opt_len + 3 + 7) >> 3;
         const uint32_t static_lenb = (static_len + 3 + 7) >> 3;
         if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
-        // a stored block holds at most 65535 bytes: a full 64 KiB block goes out as two (5 more bytes)
+        // a stored block holds at most 65535 bytes: a block of 64 KiB or more would go out as two (5 more bytes)
         if (in_len + 4 + (in_len > 65535u ? 5u : 0u) <= opt_lenb && !force_fixed) { type = 0; body = 0; }
         else if (static_lenb == opt_lenb || force_fixed) { type = 1; body = static_len; }
         else {
