@@ -203,15 +203,20 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
 //     bytes, turned into literals.
 //   * Tokens go to a private region per thread, then each warp copies its 32 regions into the block's contiguous
 //     token array with coalesced stores and tallies the block histogram on the way (dense shared-memory atomics).
-constexpr int kWalkThreads = 512;
-constexpr uint32_t kSub = kBlockBytes / kWalkThreads;           // 64 input bytes per thread
-constexpr uint32_t kSubSlots = kSub + 2;                        // token slots per thread; two spare in front for the fix-up
+// Two shapes: greedy levels run 512 threads (64-byte sub-units) at 3 CTAs per SM with the chain links read from
+// global memory (L2); lazy levels walk up to 4096 candidates per search, where every link is a dependent load, so
+// they also stage the links of the window (128 KiB more shared memory, one CTA per SM) and run 1024 threads
+// (32-byte sub-units).
+constexpr int kWalkThreadsFast = 512, kWalkThreadsLazy = 1024;
+constexpr uint32_t kSubSlotsMax = 66;                           // token slots per sub-unit incl. two spare in front: max over both shapes
+constexpr uint32_t kTmpPerBlock = 1024 * 34 > 512 * 66 ? 1024 * 34 : 512 * 66;   // private token slots per block
 constexpr uint32_t kWalkPad = 272;                              // lookahead behind the block (kMaxMatch + word slack)
 // Shared-memory image of the window: rows of 128 bytes followed by one pad word that repeats the first word of
 // the next row.  The lanes of a warp sit 64 bytes apart (one sub-unit each): without the skew they would share two
 // banks; with 132-byte rows a pair of lanes shifts by one bank per row and the 32 lanes cover all 32 banks.  An unaligned 4-byte read that starts in the last bytes of a row still finds its continuation in the pad word.
 constexpr uint32_t kWalkRows = (kWindow + kBlockBytes + kWalkPad + 16 + 127) / 128 + 1;
 constexpr uint32_t kWalkSmem = kWalkRows * 132;
+constexpr uint32_t kWalkLinkSmem = (kWindow + kBlockBytes + 16) * 2;   // image of dist16 over the window and the block
 __device__ __forceinline__ uint32_t smap(uint32_t off) { return off + ((off >> 7) << 2); }
 
 __device__ __forceinline__ uint32_t lds32u(const uint8_t* s_mem, uint32_t off)   // 4 bytes at any window-image offset
@@ -225,7 +230,7 @@ struct Found { uint32_t len, dist; };
 
 // longest_match (deflate.c:1027-1168) at window offset `o` (= absolute position gp): candidates from the dist16 chain,
 // quick reject on the word that ends at the byte a better match must reach, strictly longer wins, stop at nice.
-__device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, const uint16_t* __restrict__ dp, uint32_t maxlen,
+__device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, const uint16_t* dp, uint32_t maxlen,
                                              int chain, uint32_t nice_eff, uint32_t prev_len)
 {
     Found f{kMinMatch - 1, 0};
@@ -282,7 +287,8 @@ __device__ __forceinline__ Found walk_search_rle(const uint8_t* s_mem, uint32_t 
     return f;
 }
 
-__global__ void __launch_bounds__(kWalkThreads, 3)
+template <int kT, bool kSmemLinks>
+__global__ void __launch_bounds__(kT, kSmemLinks ? 1 : 3)
 k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
           uint32_t* __restrict__ tok_tmp, uint32_t* __restrict__ tok, uint32_t* __restrict__ blk_ntok,
           uint32_t* __restrict__ blk_hist, int kind, int max_chain, uint32_t nice, uint32_t max_lazy, uint32_t good,
@@ -290,10 +296,11 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
     __shared__ uint32_t s_hist[kHistSize];
-    __shared__ uint32_t s_end[kWalkThreads];                    // end position of each thread's walk, then its prefix maximum
-    __shared__ uint32_t s_cnt[kWalkThreads];                    // kept tokens per thread, then their exclusive prefix sum
-    __shared__ uint32_t s_first[kWalkThreads];
-    __shared__ uint32_t s_wsum[kWalkThreads / 32];
+    constexpr uint32_t kSub = kBlockBytes / kT, kSubSlots = kSub + 2;   // input bytes / private token slots per thread
+    __shared__ uint32_t s_end[kT];                    // end position of each thread's walk, then its prefix maximum
+    __shared__ uint32_t s_cnt[kT];                    // kept tokens per thread, then their exclusive prefix sum
+    __shared__ uint32_t s_first[kT];
+    __shared__ uint32_t s_wsum[kT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t b = blockIdx.x;
     const uint32_t blk_beg = dict + b * kBlockBytes;            // absolute positions in buf
@@ -304,22 +311,33 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     const uintptr_t g_lo = (uintptr_t)(buf + win_beg) & ~(uintptr_t)15;
     const uint32_t mis = (uint32_t)((uintptr_t)(buf + win_beg) - g_lo);     // window offset w lives at s_mem[w + mis]
     const uint32_t nvec = (mis + (stage_end - win_beg) + 15) >> 4;
-    for (uint32_t i = tid; i < nvec; i += kWalkThreads) {
+    for (uint32_t i = tid; i < nvec; i += kT) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(g_lo) + i);
         uint32_t* d = reinterpret_cast<uint32_t*>(s_mem + smap(i * 16));    // a 16-byte vector never straddles a row
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
-    for (int i = tid; i < (int)kHistSize; i += kWalkThreads) s_hist[i] = 0;
+    for (int i = tid; i < (int)kHistSize; i += kT) s_hist[i] = 0;
     __syncthreads();
-    for (uint32_t r = tid; r + 1 < kWalkRows; r += kWalkThreads)            // pad word = first word of the next row
+    for (uint32_t r = tid; r + 1 < kWalkRows; r += kT)            // pad word = first word of the next row
         reinterpret_cast<uint32_t*>(s_mem)[r * 33 + 32] = reinterpret_cast<const uint32_t*>(s_mem)[(r + 1) * 33];
     __syncthreads();
     const uint32_t sm_off = mis;                                 // image offset of window offset 0
+    const uint16_t* links = dist16 + win_beg;                    // links[q - win_beg] = dist16[q]
+    if (kSmemLinks) {
+        uint16_t* sl = reinterpret_cast<uint16_t*>(s_mem + kWalkSmem);
+        const uintptr_t l_lo = (uintptr_t)(dist16 + win_beg) & ~(uintptr_t)15;
+        const uint32_t lmis = (uint32_t)(((uintptr_t)(dist16 + win_beg) - l_lo) >> 1);
+        const uint32_t lvec = (lmis + (blk_end - win_beg) + 7) >> 3;
+        for (uint32_t i = tid; i < lvec; i += kT)
+            reinterpret_cast<uint4*>(sl)[i] = __ldg(reinterpret_cast<const uint4*>(l_lo) + i);
+        __syncthreads();
+        links = sl + lmis;
+    }
     auto byte_at = [&](uint32_t q) { return (uint32_t)s_mem[smap(sm_off + q - win_beg)]; };   // buf[q]
 
     // ---- walk this thread's sub-unit ----
     const uint32_t s0 = blk_beg + tid * kSub, s1 = min(s0 + kSub, blk_end);
-    uint32_t* mine = tok_tmp + ((size_t)b * kWalkThreads + tid) * kSubSlots + 2;
+    uint32_t* mine = tok_tmp + (size_t)b * kTmpPerBlock + (size_t)tid * kSubSlots + 2;
     uint32_t ntok = 0, pos = s0;
     if (s0 < blk_end) {
         if (kind == 1) {                                        // deflate_fast, deflate.c:1448-1546
@@ -328,7 +346,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                 Found f{0, 0};
                 if (maxlen >= kMinMatch && max_chain > 0) {
                     if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, 0);
-                    else f = walk_search(s_mem, sm_off + pos - win_beg, dist16 + pos, maxlen, max_chain, min(nice, maxlen), 0);
+                    else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), maxlen, max_chain, min(nice, maxlen), 0);
                 }
                 if (f.len >= kMinMatch) { mine[ntok++] = (f.dist << 16) | (f.len - kMinMatch); pos += f.len; }
                 else { mine[ntok++] = byte_at(pos); pos++; }
@@ -345,7 +363,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                     if (maxlen >= kMinMatch && prev_len < max_lazy) {
                         const int chain = prev_len >= good ? max(max_chain >> 2, 1) : max_chain;
                         if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, prev_len);
-                        else f = walk_search(s_mem, sm_off + pos - win_beg, dist16 + pos, maxlen, chain, min(nice, maxlen), prev_len);
+                        else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), maxlen, chain, min(nice, maxlen), prev_len);
                         if (f.dist == 0) f.len = kMinMatch - 1;                  // nothing longer than the pending match
                         if (f.len <= 5 && (strategy == 1 || (f.len == kMinMatch && f.dist > kTooFar))) f.len = kMinMatch - 1;   // Z_FILTERED, TOO_FAR
                     }
@@ -377,7 +395,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
         __syncthreads();
         uint32_t prevmax = 0;
 #pragma unroll
-        for (int w = 0; w < kWalkThreads / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp && v > prevmax) prevmax = v; }
+        for (int w = 0; w < kT / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp && v > prevmax) prevmax = v; }
         s_end[tid] = m > prevmax ? m : prevmax;
         __syncthreads();
     }
@@ -412,7 +430,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     __syncthreads();
     uint32_t before = 0, all = 0;
 #pragma unroll
-    for (int w = 0; w < kWalkThreads / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; all += v; }
+    for (int w = 0; w < kT / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; all += v; }
     s_cnt[tid] = before + x - keep;
     s_first[tid] = (uint32_t)(first + 2);                       // relative to the region base (2 spare slots in front)
     s_end[tid] = keep;
@@ -422,7 +440,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     for (int r = 0; r < 32; r++) {
         const int t = warp * 32 + r;
         const uint32_t cnt = s_end[t], off = s_cnt[t];
-        const uint32_t* srcp = tok_tmp + ((size_t)b * kWalkThreads + t) * kSubSlots + s_first[t];
+        const uint32_t* srcp = tok_tmp + (size_t)b * kTmpPerBlock + (size_t)t * kSubSlots + s_first[t];
         for (uint32_t k = lane; k < cnt; k += 32) {
             const uint32_t v = srcp[k];
             out[off + k] = v;
@@ -435,7 +453,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
         }
     }
     __syncthreads();
-    for (int i = tid; i < (int)kHistSize; i += kWalkThreads) blk_hist[(size_t)b * kHistSize + i] = s_hist[i];
+    for (int i = tid; i < (int)kHistSize; i += kT) blk_hist[(size_t)b * kHistSize + i] = s_hist[i];
     if (tid == 0) blk_ntok[b] = all;
 }
 
@@ -1056,7 +1074,7 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
     uint32_t *d_hist = nullptr, *d_codes = nullptr, *d_hdr = nullptr, *d_tok = nullptr, *d_ntok = nullptr;
     if (cfg.kind != 0) {
         if ((rc = c->ws[3].ensure(total * 2 + 64)) != 0) return rc;          // dist16
-        if ((rc = c->ws[4].ensure(nblocks * kWalkThreads * kSubSlots * 4 + 64)) != 0) return rc;   // private token regions
+        if ((rc = c->ws[4].ensure(nblocks * kTmpPerBlock * 4 + 64)) != 0) return rc;               // private token regions
         if ((rc = c->ws[5].ensure(nblocks * kBlockBytes * 4 + 64)) != 0) return rc;               // tokens, contiguous per block
         if ((rc = c->ws[6].ensure(nblocks * sizeof(BlockMeta))) != 0) return rc;
         if ((rc = c->ws[7].ensure(nblocks * kHistSize * 4)) != 0) return rc;
@@ -1075,8 +1093,14 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
             if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
             else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
         }
-        ZB_LAUNCH(k_lz_walk, (unsigned)nblocks, kWalkThreads, kWalkSmem, s, d_buf, (uint32_t)total, (uint32_t)dict, d_dist, d_tmp,
-                  d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy, (uint32_t)cfg.good, P.strategy);
+        if (cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3)
+            ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), (unsigned)nblocks, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_buf, (uint32_t)total,
+                      (uint32_t)dict, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
+                      (uint32_t)cfg.good, P.strategy);
+        else
+            ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), (unsigned)nblocks, kWalkThreadsFast, kWalkSmem, s, d_buf, (uint32_t)total,
+                      (uint32_t)dict, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
+                      (uint32_t)cfg.good, P.strategy);
         ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, n, d_blk, d_hist,
                   d_codes, d_hdr, P.strategy == 4 ? 1 : 0);
     }
@@ -1130,7 +1154,8 @@ static int deflate_params(DeflateParams& P, int level, int wrap, int flags)
     if (!attr) {
         ZB_CUDA(cudaFuncSetAttribute(k_lz_link<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
         ZB_CUDA(cudaFuncSetAttribute(k_lz_link<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem));
+        ZB_CUDA(cudaFuncSetAttribute(k_lz_walk<kWalkThreadsFast, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem));
+        ZB_CUDA(cudaFuncSetAttribute(k_lz_walk<kWalkThreadsLazy, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem + kWalkLinkSmem));
         attr = true;
     }
     if (level < 0) level = 6;
