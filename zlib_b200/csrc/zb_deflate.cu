@@ -37,6 +37,8 @@
 #include "zb_deflate.cuh"
 #include "zb200_internal.h"
 #include <stdlib.h>
+#include <algorithm>
+#include <vector>
 
 namespace zb {
 
@@ -1116,6 +1118,27 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
     return 0;
 }
 
+// Slab boundaries (byte offsets, cut[0] = 0 .. cut.back() = n).  Device-resident data: uniform slabs.  Host buffers:
+// the first and last slabs are a quarter and a half slab, so that the first kernels start after 28 MiB of H2D instead
+// of 111 MiB and only 28 MiB of work and its D2H copy trail the last H2D.
+static void plan_slabs(uint64_t n, bool ramp, std::vector<uint64_t>& cut)
+{
+    cut.assign(1, 0);
+    if (n == 0) return;
+    const uint64_t C = (n + kChunk - 1) / kChunk, full = kSlabChunks, h = full / 2, q = full / 4;
+    std::vector<uint64_t> sizes;
+    if (!ramp || C <= 4 * full) {
+        for (uint64_t c = 0; c < C; c += full) sizes.push_back(std::min<uint64_t>(full, C - c));
+    } else {
+        const uint64_t mid = C - 2 * (q + h);
+        sizes.push_back(q); sizes.push_back(h);
+        for (uint64_t c = 0; c < mid; c += full) sizes.push_back(std::min<uint64_t>(full, mid - c));
+        sizes.push_back(h); sizes.push_back(q);
+    }
+    uint64_t c = 0;
+    for (uint64_t z : sizes) { c += z; cut.push_back(std::min<uint64_t>(n, c * kChunk)); }
+}
+
 // A whole device-resident job, asynchronous on s with the scratch of context c: slabs, checksums of the input,
 // header and trailer.  d_res (device, 32 bytes): u64 total length, then u32 crc32, adler32, error count.
 static int deflate_enqueue_dev(Ctx* c, cudaStream_t s, const uint8_t* d_buf, uint64_t dict_len, uint64_t n, uint8_t* d_out,
@@ -1124,8 +1147,9 @@ static int deflate_enqueue_dev(Ctx* c, cudaStream_t s, const uint8_t* d_buf, uin
     const int force_mark = (P.flags & ZB200I_DEFLATE_FORCE_MARK) ? 1 : 0;
     const int last_is_final = (P.flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
     const uint64_t hdr_len = (P.flags & ZB200_DEFLATE_NO_HEADER) ? 0 : P.wrap == ZB200_WRAP_ZLIB ? 2 : P.wrap == ZB200_WRAP_GZIP ? 10 : 0;
-    const uint64_t slab = (uint64_t)kSlabChunks * kChunk;
-    const uint64_t nslabs = n ? (n + slab - 1) / slab : 0;
+    std::vector<uint64_t> cut;
+    plan_slabs(n, false, cut);
+    const uint64_t nslabs = cut.size() - 1;
     int rc;
     if ((rc = c->ws[1].ensure((nslabs + 2) * 8)) != 0) return rc;
     uint64_t* d_pos = c->ws[1].as<uint64_t>();
@@ -1136,7 +1160,7 @@ static int deflate_enqueue_dev(Ctx* c, cudaStream_t s, const uint8_t* d_buf, uin
     const uint8_t* d_src = d_buf + dict_len;
     if (n == 0) ZB_LAUNCH(k_empty_payload, 1, 32, 0, s, d_out, cap, hdr_len, !last_is_final, force_mark, d_pos);
     for (uint64_t i = 0; i < nslabs; i++) {
-        const uint64_t off = i * slab, len = n - off < slab ? n - off : slab;
+        const uint64_t off = cut[i], len = cut[i + 1] - cut[i];
         const uint64_t dlen = i == 0 ? dict_len : kWindow;
         const bool last = i == nslabs - 1;
         if ((rc = deflate_slab_launch(c, d_src + off - dlen, dlen, len, d_out, cap, P, last && last_is_final, last ? force_mark : 0,
@@ -1185,8 +1209,9 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
     const int last_is_final = (flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
     const uint64_t hdr_len = (flags & ZB200_DEFLATE_NO_HEADER) ? 0 : wrap == ZB200_WRAP_ZLIB ? 2 : wrap == ZB200_WRAP_GZIP ? 10 : 0;
     const uint64_t n = src_len;
-    const uint64_t slab = (uint64_t)kSlabChunks * kChunk;
-    const uint64_t nslabs = n ? (n + slab - 1) / slab : 0;
+    std::vector<uint64_t> cut;
+    plan_slabs(n, (n != 0 && classify(src) != kDevice) || classify(dst) != kDevice, cut);
+    const uint64_t nslabs = cut.size() - 1;
 
     Ctx* c = ctx_acquire((cudaStream_t)stream);
     if (!c) return ZB_MEM_ERROR;
@@ -1258,7 +1283,7 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
             ZB_LAUNCH(k_empty_payload, 1, 32, 0, s, d_out, cap, hdr_len, !last_is_final, force_mark, d_pos);
         }
         for (uint64_t i = 0; i < nslabs; i++) {
-            const uint64_t off = i * slab, len = n - off < slab ? n - off : slab;
+            const uint64_t off = cut[i], len = cut[i + 1] - cut[i];
             Ctx* cl = (c2 && (i & 1)) ? c2 : c;
             cudaStream_t sl = (c2 && (i & 1)) ? c2->own_stream : s;
             if (stage_slabs) {
