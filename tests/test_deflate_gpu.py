@@ -195,3 +195,28 @@ def test_deflate_batch_independent_streams(gpu_lib, oracle):
     outs, st, _, _ = gpu_lib.deflate_batch(bufs, 6, zb.WRAP_ZLIB, caps=caps)
     assert st[7] == zb.Z_BUF_ERROR and all(s == 0 for i, s in enumerate(st) if i != 7)
     assert zlib.decompress(outs[8]) == bufs[8]
+
+
+def test_concurrent_host_threads(gpu_lib, oracle):
+    """The library is re-entrant like the reference (qcsrc/readme.txt:3-4): different streams from different threads at
+    once.  Contexts (stream + scratch) come from a pool, one per call in flight."""
+    import threading
+    datas = [gpu_lib.synth((3 << 20) + 1000 * i, kind=i % 2, seed=40 + i).tobytes() for i in range(6)]
+    results = [None] * len(datas)
+
+    def work(i):
+        ok = True
+        for rep in range(3):
+            rc, z = gpu_lib.compress2(datas[i], 1 if (i + rep) % 2 else 6)
+            ok = ok and rc == 0 and zlib.decompress(z) == datas[i]
+            rc, out = gpu_lib.uncompress(z, len(datas[i]))
+            ok = ok and rc == 0 and out == datas[i]
+            ok = ok and gpu_lib.crc32(datas[i]) == oracle.crc32(datas[i])
+        results[i] = ok
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(datas))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert results == [True] * len(datas)
