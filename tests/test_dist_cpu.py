@@ -93,3 +93,58 @@ def test_shard_ranges_and_adler_join():
     for _ in range(200):
         x, y = rng.randbytes(rng.randint(0, 70000)), rng.randbytes(rng.randint(0, 70000))
         assert zd.adler_join(zlib.adler32(x), zlib.adler32(y), len(y)) == zlib.adler32(x + y)
+
+
+def _worker_c3_c4(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import random
+        import zhelpers
+        from zlib_b200 import dist as zd, load
+        lib = load()
+        # config 4: one buffer, a slice per rank, combine in rank order (stand-in checksum: system zlib)
+        data = zhelpers.corpus(0, 777_777, 9)
+        a, b = zd.shard_ranges(len(data), world)[rank]
+        mine = torch.frombuffer(bytearray(data[a:b]), dtype=torch.uint8) if b > a else torch.empty(0, dtype=torch.uint8)
+        crc, adl, total = zd.checksum_sharded(lib, mine, checksum_fn=lambda t: (zlib.crc32(bytes(t.numpy())), zlib.adler32(bytes(t.numpy()))))
+        assert (crc, adl, total) == (zlib.crc32(data), zlib.adler32(data), len(data))
+        # config 3: streams sharded by compressed size; statuses and lengths known everywhere afterwards
+        rng = random.Random(3)
+        plain = [zhelpers.corpus(rng.randrange(5), rng.randint(0, 40000), 100 + i) for i in range(37)]
+        zs = [zlib.compress(p, 6) for p in plain]
+        zs[5] = zs[5][:-3]                                         # one damaged stream
+        def standin(zz, caps):
+            outs, st = [], []
+            for z in zz:
+                try:
+                    outs.append(zlib.decompress(z)); st.append(0)
+                except zlib.error:
+                    outs.append(b""); st.append(-3)
+            return outs, st
+        idx, outs, st, lens = zd.inflate_sharded(lib, zs, [len(p) for p in plain], inflate_fn=standin)
+        assert st == [0 if i != 5 else -3 for i in range(len(zs))]
+        assert lens == [len(p) if i != 5 else 0 for i, p in enumerate(plain)]
+        assert all(outs[k] == plain[i] for k, i in enumerate(idx) if i != 5)
+        parts = zd.balance_streams([len(z) for z in zs], world)
+        assert [i for p in parts for i in p] == list(range(len(zs)))
+        q.put((rank, "ok"))
+    except Exception:          # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_checksum_and_inflate(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_c3_c4, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert all(m == "ok" for _, m in res), res

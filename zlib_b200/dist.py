@@ -143,3 +143,76 @@ def deflate_sharded(lib, data, halo, level: int = 6, wrap: int = zb.WRAP_ZLIB, g
     plan = plan_stream(metas, level, wrap, lib.crc32_combine)
     assembled = gather_stream(out, clen, plan, root, group) if assemble else None
     return plan, out, clen, assembled
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4: crc32 / adler32 of one buffer spread over the ranks
+# ---------------------------------------------------------------------------------------------
+def checksum_sharded(lib, data, group=None, checksum_fn: Optional[Callable] = None, stream=None) -> Tuple[int, int, int]:
+    """crc32 / adler32 of the concatenation of every rank's slice, in rank order.
+
+    Each rank runs the fused checksum kernel over its own slice; the exchange is one all-gather of
+    {crc32, adler32, length} per rank, and every rank folds the triples in rank order with
+    crc32_combine (qcsrc/crc32.c:370) and the Adler join -- the combine is not commutative, so a
+    reduction collective cannot do it.  Returns (crc32, adler32, total length).
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = data.numel()
+    if checksum_fn is None:
+        crc, adl = lib.checksum(data.data_ptr(), n, stream) if n else (0, 1)
+    else:
+        crc, adl = checksum_fn(data)
+    mine = torch.tensor([crc, adl, n], dtype=torch.int64, device=data.device)
+    out = torch.empty(world * 3, dtype=torch.int64, device=data.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    crc_all, adl_all, total = 0, 1, 0
+    for c, a, m in out.view(world, 3).cpu().tolist():
+        if m:
+            crc_all = lib.crc32_combine(crc_all, c, m)
+            adl_all = adler_join(adl_all, a, m)
+        total += m
+    return crc_all, adl_all, total
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 3: batch inflate of independent streams, sharded by stream (SURVEY.md 8(e))
+# ---------------------------------------------------------------------------------------------
+def balance_streams(sizes: Sequence[int], world: int) -> List[List[int]]:
+    """Contiguous ranges of stream indices per rank with nearly equal compressed bytes (streams stay in order, so
+    outputs concatenate in rank order).  Returns world lists of indices."""
+    total = sum(sizes)
+    out, i, acc = [], 0, 0
+    for r in range(world):
+        want = total * (r + 1) / world
+        j = i
+        while j < len(sizes) and (r == world - 1 or acc + sizes[j] / 2 <= want):
+            acc += sizes[j]
+            j += 1
+        out.append(list(range(i, j)))
+        i = j
+    return out
+
+
+def inflate_sharded(lib, streams: Sequence[bytes], caps: Sequence[int], wrap: int = zb.WRAP_ZLIB, group=None,
+                    inflate_fn: Optional[Callable] = None):
+    """Every rank decodes its share of the streams; nothing but {status, length} per stream is exchanged.
+
+    Returns (my_indices, my_outputs, statuses_of_all_streams, lengths_of_all_streams)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    parts = balance_streams([len(z) for z in streams], world)
+    mine = parts[rank]
+    fn = inflate_fn or (lambda zs, cs: lib.inflate_batch(zs, cs, wrap))
+    outs, st = fn([streams[i] for i in mine], [caps[i] for i in mine]) if mine else ([], [])
+    n = len(streams)
+    local = torch.full((n, 2), -100, dtype=torch.int64)          # below every zlib status (>= -6) and every length
+    for k, i in enumerate(mine):
+        local[i, 0], local[i, 1] = st[k], len(outs[k])
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    local = local.to(dev)
+    dist.all_reduce(local, op=dist.ReduceOp.MAX, group=group)     # every stream has exactly one owner; the rest hold -100
+    res = local.cpu().tolist()
+    return mine, outs, [int(r[0]) for r in res], [int(r[1]) for r in res]
