@@ -1,1 +1,1 @@
-python -m pytest tests/test_deflate_gpu.py -m gpu -x -q -k concurrent 2>&1 | tail -8
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dist_check.py 2>&1 | tail -5
