@@ -433,25 +433,23 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     uint32_t before = 0, all = 0;
 #pragma unroll
     for (int w = 0; w < kT / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; all += v; }
-    s_cnt[tid] = before + x - keep;
-    s_first[tid] = (uint32_t)(first + 2);                       // relative to the region base (2 spare slots in front)
-    s_end[tid] = keep;
+    // region descriptor for the copy: {first kept slot (index into this block's private slots), output offset | count << 16}
+    s_first[tid] = (uint32_t)tid * kSubSlots + (uint32_t)(first + 2);
+    s_cnt[tid] = (before + x - keep) | (keep << 16);             // a block holds at most 32768 tokens, a sub-unit at most 66
     __syncthreads();
     // ---- each warp moves its 32 regions, coalesced, and tallies ----
     uint32_t* out = tok + (size_t)b * kBlockBytes;
+    const uint32_t* tmp_blk = tok_tmp + (size_t)b * kTmpPerBlock;
     for (int r = 0; r < 32; r++) {
         const int t = warp * 32 + r;
-        const uint32_t cnt = s_end[t], off = s_cnt[t];
-        const uint32_t* srcp = tok_tmp + (size_t)b * kTmpPerBlock + (size_t)t * kSubSlots + s_first[t];
+        const uint32_t dsc = s_cnt[t], src0 = s_first[t];
+        const uint32_t cnt = dsc >> 16, off = dsc & 0xffffu;
         for (uint32_t k = lane; k < cnt; k += 32) {
-            const uint32_t v = srcp[k];
+            const uint32_t v = tmp_blk[src0 + k];
             out[off + k] = v;
-            if (v >> 16) {
-                atomicAdd(&s_hist[257 + len_code(v & 0xffffu)], 1u);
-                atomicAdd(&s_hist[288 + dist_code((v >> 16) - 1)], 1u);
-            } else {
-                atomicAdd(&s_hist[v], 1u);
-            }
+            const bool is_match = (v >> 16) != 0;
+            atomicAdd(&s_hist[is_match ? 257 + len_code(v & 0xffffu) : v], 1u);
+            if (is_match) atomicAdd(&s_hist[288 + dist_code((v >> 16) - 1)], 1u);
         }
     }
     __syncthreads();
