@@ -20,6 +20,7 @@ A step = one pass of the hot path over the 1 GiB batch (per GPU: weak scaling).
 import argparse
 import ctypes as C
 import json
+import re
 import os
 import subprocess
 import sys
@@ -258,6 +259,9 @@ def main():
     step_deflate(1)
     prof = lib.profile_report()
     lib.profile(False)
+    def kname(k):                                        # "(k_lz_walk<kWalkThreadsFast, false>)" -> "k_lz_walk"
+        return re.sub(r"<.*>|[()]|zb::", "", k).strip()
+    prof = {kname(k): v for k, v in prof.items()}
     dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 1))
     dom_launches = max(1, dom[1][1])                    # one launch per pipeline slab
     dom_ms = dom[1][0] / dom_launches                   # average launch duration of the dominant kernel
@@ -269,7 +273,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom[0].replace("zb::", ""))
+            traffic = {kname(k): v for k, v in json.load(open(tpath)).items()}.get(dom[0])
         except Exception:   # noqa: BLE001
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": round(achieved, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
