@@ -440,16 +440,28 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     // ---- each warp moves its 32 regions, coalesced, and tallies ----
     uint32_t* out = tok + (size_t)b * kBlockBytes;
     const uint32_t* tmp_blk = tok_tmp + (size_t)b * kTmpPerBlock;
-    for (int r = 0; r < 32; r++) {
-        const int t = warp * 32 + r;
-        const uint32_t dsc = s_cnt[t], src0 = s_first[t];
-        const uint32_t cnt = dsc >> 16, off = dsc & 0xffffu;
-        for (uint32_t k = lane; k < cnt; k += 32) {
-            const uint32_t v = tmp_blk[src0 + k];
-            out[off + k] = v;
-            const bool is_match = (v >> 16) != 0;
-            atomicAdd(&s_hist[is_match ? 257 + len_code(v & 0xffffu) : v], 1u);
-            if (is_match) atomicAdd(&s_hist[288 + dist_code((v >> 16) - 1)], 1u);
+    auto tally = [&](uint32_t v) {
+        const bool is_match = (v >> 16) != 0;
+        atomicAdd(&s_hist[is_match ? 257 + len_code(v & 0xffffu) : v], 1u);
+        if (is_match) atomicAdd(&s_hist[288 + dist_code((v >> 16) - 1)], 1u);
+    };
+    for (int r0 = 0; r0 < 32; r0 += 4) {                         // four regions at a time: their loads are in flight together
+        uint32_t cnt[4], off[4], src0[4], v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int t = warp * 32 + r0 + j;
+            const uint32_t dsc = s_cnt[t];
+            cnt[j] = dsc >> 16; off[j] = dsc & 0xffffu; src0[j] = s_first[t];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (uint32_t)lane < cnt[j] ? tmp_blk[src0[j] + lane] : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if ((uint32_t)lane < cnt[j]) { out[off[j] + lane] = v[j]; tally(v[j]); }
+            for (uint32_t k = lane + 32; k < cnt[j]; k += 32) {  // a region holds at most 66 tokens
+                const uint32_t w = tmp_blk[src0[j] + k];
+                out[off[j] + k] = w; tally(w);
+            }
         }
     }
     __syncthreads();
