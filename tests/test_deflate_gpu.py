@@ -197,6 +197,34 @@ def test_deflate_batch_independent_streams(gpu_lib, oracle):
     assert zlib.decompress(outs[8]) == bufs[8]
 
 
+def test_deflate_batch_many_slabs_and_big_jobs(gpu_lib, oracle):
+    """Job mode of zb200_deflate_batch: more jobs than one slab holds (tiny files, empty ones in between), a job above the
+    big-job threshold in the middle (single-stream pipeline), stored / greedy / lazy levels.  History never leaks from
+    one job into the next: every stream decodes on its own."""
+    rng = random.Random(77)
+    base = zhelpers.corpus(1, 1 << 20, 5)
+    bufs = []
+    for i in range(2100):                                      # > 2 slabs by job count
+        n = 0 if i % 97 == 0 else rng.randint(1, 3000)
+        o = rng.randrange(len(base) - n)
+        bufs.append(base[o:o + n])
+    big = gpu_lib.synth((33 << 20) + 12345, kind=1, seed=9).tobytes()
+    bufs.insert(1000, big)
+    bufs.insert(1500, gpu_lib.synth((5 << 20) + 1, kind=0, seed=10).tobytes())
+    for level, wrap, wbits in ((1, zb.WRAP_ZLIB, 15), (6, zb.WRAP_RAW, -15), (0, zb.WRAP_GZIP, 31), (9, zb.WRAP_ZLIB, 15)):
+        sub = bufs if level in (1, 6) else bufs[900:1100]
+        outs, st, crcs, adls = gpu_lib.deflate_batch(sub, level, wrap)
+        assert st == [0] * len(sub)
+        for d, z, c in zip(sub, outs, crcs):
+            assert zlib.decompress(z, wbits) == d
+            assert c == zlib.crc32(d)
+        k = sub.index(big)
+        if wrap == zb.WRAP_ZLIB:
+            rc, out, used = oracle.inflate(outs[k], len(big))
+            assert rc == 0 and out == big and used == len(outs[k])
+            assert adls[k] == oracle.adler32(big)
+
+
 def test_concurrent_host_threads(gpu_lib, oracle):
     """The library is re-entrant like the reference (qcsrc/readme.txt:3-4): different streams from different threads at
     once.  Contexts (stream + scratch) come from a pool, one per call in flight."""

@@ -103,7 +103,7 @@ __device__ __noinline__ uint2 ring_turn(uint32_t a0, uint32_t a1, uint32_t a2, u
 
 template <bool kExact>
 __global__ void __launch_bounds__(kLinkWarps * 32)
-k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict__ dist16)
+k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict__ dist16, const ChunkDesc* __restrict__ cd)
 {
     extern __shared__ uint16_t s_head[];                       // 2^15 entries: low 16 bits of the last position
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -111,9 +111,18 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
     for (int i = threadIdx.x; i < (1 << kHashBits) / 2; i += kLinkWarps * 32) reinterpret_cast<uint32_t*>(s_head)[i] = 0;
     __syncthreads();
 
-    const uint64_t seg_beg = (uint64_t)blockIdx.x * kChunk;
-    const uint64_t seg_end = min(total, seg_beg + kChunk);
-    const uint64_t prime_beg = seg_beg > kWindow ? seg_beg - kWindow : 0;
+    // the segment, the first position whose hash is entered (priming), the end of hashable data, position zero of the stream
+    uint64_t seg_beg, seg_end, prime_beg, lim, origin;
+    if (cd) {                                                   // job mode: the segment is a chunk of some job
+        const ChunkDesc d = cd[blockIdx.x];
+        seg_beg = d.beg; seg_end = (uint64_t)d.beg + d.len; origin = d.job_beg; lim = d.job_end;
+        prime_beg = seg_beg - origin > kWindow ? seg_beg - kWindow : origin;
+    } else {
+        seg_beg = (uint64_t)blockIdx.x * kChunk;
+        seg_end = min(total, seg_beg + kChunk);
+        prime_beg = seg_beg > kWindow ? seg_beg - kWindow : 0;
+        origin = 0; lim = total;
+    }
     const uint32_t mis = (uint32_t)((uintptr_t)buf & 3);
     // q = p + mis indexes bytes from the 4-byte aligned base; a tile is 128 consecutive q.  Everything below is
     // relative to the first tile of this segment, so it fits 32 bits (a segment spans <= 160 KiB + 128).
@@ -123,9 +132,9 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
     const uint32_t nwords = (uint32_t)min((uint64_t)0x7fffffffu, ((mis + total + 3) >> 2) - tile_beg * 32);
     uint16_t* dout = dist16 + q0 - mis;                         // dout[q - q0] = link of position q - mis (never dereferenced below q_seg)
     const int q_lo = (int)(prime_beg + mis - q0);               // first position to insert
-    const int q_hi = (int)(min(seg_end, total >= 2 ? total - 2 : 0) + mis - q0);   // one past the last hashable position
+    const int q_hi = (int)(min(seg_end, lim >= origin + 2 ? lim - 2 : origin) + mis) - (int)q0;   // one past the last hashable position
     const int q_seg = (int)(seg_beg + mis - q0), q_end = (int)(seg_end + mis - q0);   // positions whose link is stored
-    const int p_cap = (int)min((uint64_t)0x40000000u, q0 - mis + 128) - 128;   // global position of q0, saturated (only "dd > p" uses it)
+    const int p_cap = (int)min((uint64_t)0x40000000u, q0 - mis + 128 - origin) - 128;   // stream position of q0, saturated (only "dd > p" uses it)
     const uint32_t ntiles = (uint32_t)(tile_end - tile_beg);
     const uint32_t iters = (ntiles + kLinkWarps - 1) / kLinkWarps;
     const uint32_t head_base = (uint32_t)__cvta_generic_to_shared(s_head);
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(kT, kSmemLinks ? 1 : 3)
 k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
           uint32_t* __restrict__ tok_tmp, uint32_t* __restrict__ tok, uint32_t* __restrict__ blk_ntok,
           uint32_t* __restrict__ blk_hist, int kind, int max_chain, uint32_t nice, uint32_t max_lazy, uint32_t good,
-          int strategy)
+          int strategy, const ChunkDesc* __restrict__ cd)
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
     __shared__ uint32_t s_hist[kHistSize];
@@ -305,9 +314,19 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     __shared__ uint32_t s_wsum[kT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t b = blockIdx.x;
-    const uint32_t blk_beg = dict + b * kBlockBytes;            // absolute positions in buf
-    const uint32_t blk_end = min(total, blk_beg + kBlockBytes);
-    const uint32_t win_beg = blk_beg > kWindow ? blk_beg - kWindow : 0u;
+    uint32_t blk_beg, blk_end, win_beg;                         // absolute positions in buf
+    if (cd) {                                                   // job mode: block b is the (b % 4)-th block of a chunk of some job
+        const ChunkDesc d = cd[b / kBlocksPerChunk];
+        const uint32_t rel = (b % kBlocksPerChunk) * kBlockBytes;
+        if (rel >= d.len) return;                               // short chunk: this block slot is unused (nobody reads it)
+        blk_beg = d.beg + rel;
+        blk_end = d.beg + min(d.len, rel + kBlockBytes);
+        win_beg = blk_beg - d.job_beg > kWindow ? blk_beg - kWindow : d.job_beg;
+    } else {
+        blk_beg = dict + b * kBlockBytes;
+        blk_end = min(total, blk_beg + kBlockBytes);
+        win_beg = blk_beg > kWindow ? blk_beg - kWindow : 0u;
+    }
     const uint32_t stage_end = min(total, blk_end + kWalkPad);
     // ---- stage [win_beg, stage_end) ----
     const uintptr_t g_lo = (uintptr_t)(buf + win_beg) & ~(uintptr_t)15;
@@ -662,16 +681,24 @@ __device__ __forceinline__ uint32_t fixed_lit_code(uint32_t s)
 
 __global__ void __launch_bounds__(kCodeWarps * 32)
 k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict__ blk_hist,
-             uint32_t* __restrict__ blk_codes, uint32_t* __restrict__ blk_hdr, int force_fixed)
+             uint32_t* __restrict__ blk_codes, uint32_t* __restrict__ blk_hdr, int force_fixed,
+             const ChunkDesc* __restrict__ cd, uint64_t nslots)
 {
     __shared__ TreeScratch s_t[kCodeWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t nblocks = (n + kBlockBytes - 1) / kBlockBytes;
+    const uint64_t nblocks = cd ? nslots : (n + kBlockBytes - 1) / kBlockBytes;
     const uint64_t b = (uint64_t)blockIdx.x * kCodeWarps + warp;
     if (b >= nblocks) return;
     TreeScratch* t = &s_t[warp];
     uint32_t* codes = blk_codes + b * kHistSize;
-    const uint32_t in_len = (uint32_t)min((uint64_t)kBlockBytes, n - b * kBlockBytes);
+    uint32_t in_len;
+    if (cd) {                                                   // job mode: four block slots per chunk, short chunks leave some unused
+        const uint32_t clen = cd[b / kBlocksPerChunk].len, rel = (uint32_t)(b % kBlocksPerChunk) * kBlockBytes;
+        if (rel >= clen) return;
+        in_len = min(kBlockBytes, clen - rel);
+    } else {
+        in_len = (uint32_t)min((uint64_t)kBlockBytes, n - b * kBlockBytes);
+    }
 
     // ---- block histogram (+ the end-of-block symbol) ----
     for (int i = lane; i < (int)kHistSize; i += 32) t->hsum[i] = blk_hist[b * kHistSize + i] + (i == 256 ? 1u : 0u);
@@ -757,16 +784,16 @@ k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict
 __device__ __forceinline__ uint64_t stored_chunk_bytes(uint32_t len) { return (uint64_t)len + 5ull * ((len + 65534u) / 65535u); }
 
 __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chunks, const BlockMeta* __restrict__ blk,
-                       int last_is_final, int force_stored, int force_mark)
+                       int last_is_final, int force_stored, int force_mark, const ChunkDesc* __restrict__ cd)
 {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     ChunkMeta cm;
-    const uint32_t clen = (uint32_t)min((uint64_t)kChunk, n - c * kChunk);
+    const uint32_t clen = cd ? cd[c].len : (uint32_t)min((uint64_t)kChunk, n - c * kChunk);
     cm.nblocks = (clen + kBlockBytes - 1) / kBlockBytes;
     cm.offset = 0;
-    const bool final_chunk = last_is_final && c == nchunks - 1;
-    const bool mark = force_mark && !last_is_final && c == nchunks - 1;   // Z_SYNC_FLUSH marker wanted regardless
+    const bool final_chunk = cd ? cd[c].last != 0 : (last_is_final && c == nchunks - 1);
+    const bool mark = !cd && force_mark && !last_is_final && c == nchunks - 1;   // Z_SYNC_FLUSH marker wanted regardless
     uint64_t bytes;
     if (force_stored) {
         cm.stored = 1; bytes = stored_chunk_bytes(clen) + (mark ? 5 : 0);
@@ -825,6 +852,96 @@ __global__ void __launch_bounds__(1024) k_scan(uint64_t nchunks, ChunkMeta* __re
         __syncthreads();
     }
     if (threadIdx.x == 0) end[0] = s_carry;
+}
+
+// Job mode: the chunks of a slab belong to many independent streams, each with its own output slot.  Single CTA:
+// (1) exclusive prefix sum of the chunk sizes over the slab, (2) per job: payload size = span of its chunks, total =
+// header + payload + trailer, (3) chunk offset = slot + header + (prefix - prefix of the job's first chunk).
+__global__ void __launch_bounds__(1024) k_scan_jobs(uint32_t nchunks, ChunkMeta* __restrict__ chunks,
+                                                    const ChunkDesc* __restrict__ cd, const JobDesc* __restrict__ jobs,
+                                                    uint32_t njobs, uint32_t hdr_len, uint32_t trailer_len,
+                                                    JobResult* __restrict__ jres)
+{
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_carry;
+    __shared__ uint64_t s_base[kSlabChunks];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < nchunks; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint64_t v = i < nchunks ? chunks[i].bytes : 0;
+        uint64_t x = v;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) { const uint64_t y = __shfl_up_sync(kFullMask, x, k); if (lane >= k) x += y; }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = s_w[lane];
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) { const uint64_t y = __shfl_up_sync(kFullMask, w, k); if (lane >= k) w += y; }
+            s_w[lane] = w;
+        }
+        __syncthreads();
+        const uint64_t carry = s_carry;
+        const uint64_t incl = x + (warp ? s_w[warp - 1] : 0);
+        if (i < nchunks) chunks[i].offset = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + incl;
+        __syncthreads();
+    }
+    for (uint32_t j = threadIdx.x; j < njobs; j += 1024) {
+        const JobDesc jd = jobs[j];
+        uint64_t base = 0, payload = 2;                         // empty input: 03 00 (k_frame_jobs writes it)
+        if (jd.nchunks) {
+            const ChunkMeta last = chunks[jd.first_chunk + jd.nchunks - 1];
+            base = chunks[jd.first_chunk].offset;
+            payload = last.offset + last.bytes - base;
+        }
+        s_base[j] = base;
+        jres[j].total = hdr_len + payload + trailer_len;
+        jres[j].err = 0;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nchunks; i += 1024) {
+        const uint32_t j = cd[i].job;
+        chunks[i].offset = jobs[j].dst_off + hdr_len + (chunks[i].offset - s_base[j]);
+    }
+}
+
+// Job mode: header and trailer of every stream of the slab (deflate.c:577-650, 832-850), one thread per job.
+__global__ void k_frame_jobs(uint8_t* __restrict__ out, const JobDesc* __restrict__ jobs, uint32_t njobs,
+                             const uint32_t* __restrict__ crc, const uint32_t* __restrict__ adler, int level, int wrap,
+                             int strat, JobResult* __restrict__ jres)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    const JobDesc jd = jobs[j];
+    const uint32_t cr = crc[j], ad = adler[j];
+    jres[j].crc = cr; jres[j].adler = ad;
+    const uint64_t total = jres[j].total;
+    if (total > jd.dst_cap) return;
+    uint8_t* o = out + jd.dst_off;
+    uint32_t hl = 0;
+    if (wrap == ZB200_WRAP_ZLIB) {
+        const uint32_t fl = (level < 2 || strat >= 2) ? 0 : level < 6 ? 1 : level == 6 ? 2 : 3;   // deflate.c:628-636
+        uint32_t h = (0x78u << 8) | (fl << 6);
+        h += 31 - h % 31;
+        o[0] = h >> 8; o[1] = h; hl = 2;
+    } else if (wrap == ZB200_WRAP_GZIP) {
+        const uint8_t g[10] = {31, 139, 8, 0, 0, 0, 0, 0, (uint8_t)(level == 9 ? 2 : (level < 2 || strat >= 2) ? 4 : 0), 3};   // deflate.c:590-593
+        for (int i = 0; i < 10; i++) o[i] = g[i];
+        hl = 10;
+    }
+    if (jd.nchunks == 0) { o[hl] = 3; o[hl + 1] = 0; }
+    if (wrap == ZB200_WRAP_ZLIB) {
+        uint8_t* t = o + total - 4;
+        t[0] = ad >> 24; t[1] = ad >> 16; t[2] = ad >> 8; t[3] = ad;
+    } else if (wrap == ZB200_WRAP_GZIP) {
+        uint8_t* t = o + total - 8;
+        for (int i = 0; i < 4; i++) t[i] = cr >> (8 * i);
+        for (int i = 0; i < 4; i++) t[4 + i] = (uint8_t)(jd.src_len >> (8 * i));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -889,7 +1006,8 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
             const uint32_t* __restrict__ blk_ntok, const BlockMeta* __restrict__ blk,
             const uint32_t* __restrict__ blk_codes, const uint32_t* __restrict__ blk_hdr,
             const ChunkMeta* __restrict__ chunks, uint8_t* __restrict__ out, uint64_t cap, int last_is_final,
-            int force_mark, uint32_t* __restrict__ err)
+            int force_mark, uint32_t* __restrict__ err, const ChunkDesc* __restrict__ cd, const JobDesc* __restrict__ jobs,
+            JobResult* __restrict__ jres)
 {
     __shared__ uint32_t s_stage[2][kStageWords];
     __shared__ uint32_t s_sums[kPackThreads / 32];
@@ -897,11 +1015,19 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
     const uint64_t c = blockIdx.x;
     const uint64_t nchunks = gridDim.x;
     const ChunkMeta cm = chunks[c];
-    if (cm.offset + cm.bytes > cap) return;                     // caller reports Z_BUF_ERROR from the total
-    const uint64_t cbeg = c * kChunk;
-    const uint32_t clen = (uint32_t)min((uint64_t)kChunk, n - cbeg);
-    const bool final_chunk = last_is_final && c == nchunks - 1;
-    const bool mark = force_mark && !last_is_final && c == nchunks - 1;
+    uint64_t cbeg; uint32_t clen; bool final_chunk, mark;
+    if (cd) {                                                   // job mode: the chunk's place and role come from the table
+        const ChunkDesc d = cd[c];
+        if (jres[d.job].total > jobs[d.job].dst_cap) return;    // the job does not fit its slot: Z_BUF_ERROR from the total
+        cbeg = d.beg; clen = d.len; final_chunk = d.last != 0; mark = false;
+        err = &jres[d.job].err;
+    } else {
+        if (cm.offset + cm.bytes > cap) return;                 // caller reports Z_BUF_ERROR from the total
+        cbeg = c * kChunk;
+        clen = (uint32_t)min((uint64_t)kChunk, n - cbeg);
+        final_chunk = last_is_final && c == nchunks - 1;
+        mark = force_mark && !last_is_final && c == nchunks - 1;
+    }
     uint8_t* dst = out + cm.offset;
     const uint8_t* in = src + cbeg;
 
@@ -1102,28 +1228,85 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
         const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
         if (cfg.chain != 0 && P.strategy != 3) {                // Z_RLE needs no chains
             // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
-            if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
-            else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist);
+            if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
+            else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
         }
         if (cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3)
             ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), (unsigned)nblocks, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_buf, (uint32_t)total,
                       (uint32_t)dict, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy);
+                      (uint32_t)cfg.good, P.strategy, (const ChunkDesc*)nullptr);
         else
             ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), (unsigned)nblocks, kWalkThreadsFast, kWalkSmem, s, d_buf, (uint32_t)total,
                       (uint32_t)dict, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy);
+                      (uint32_t)cfg.good, P.strategy, (const ChunkDesc*)nullptr);
         ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, n, d_blk, d_hist,
-                  d_codes, d_hdr, P.strategy == 4 ? 1 : 0);
+                  d_codes, d_hdr, P.strategy == 4 ? 1 : 0, (const ChunkDesc*)nullptr, (uint64_t)0);
     }
-    ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0, force_mark);
+    ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0, force_mark, (const ChunkDesc*)nullptr);
     // Slabs alternate between two streams; only the running output offset links them: this slab's offsets need the
     // end of the previous slab, everything before this point (link, walk, codes, plan) does not.
     if (prev_scanned) ZB_CUDA(cudaStreamWaitEvent(s, prev_scanned, 0));
     ZB_LAUNCH(k_scan, 1, 1024, 0, s, nchunks, d_chunks, d_start, start_add, d_end);
     if (scanned) ZB_CUDA(cudaEventRecord(scanned, s));
     ZB_LAUNCH(k_huff_pack, (unsigned)nchunks, kPackThreads, 0, s, d_src, n, d_tok, d_ntok, d_blk, d_codes, d_hdr, d_chunks, d_out, cap,
-              last_is_final, force_mark, d_err);
+              last_is_final, force_mark, d_err, (const ChunkDesc*)nullptr, (const JobDesc*)nullptr, (JobResult*)nullptr);
+    ZB_CHECK_LAUNCH();
+    return 0;
+}
+
+// One slab in job mode: d_base[0, span) holds whole jobs back to back; chunk and job tables are on the device.  Every
+// stream lands in its own slot of d_out, complete with header and trailer; d_jres[j] = {length, checksums, error count}.
+static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uint32_t nchunks, uint32_t njobs,
+                               const ChunkDesc* d_cd, const JobDesc* d_jobs, const uint64_t* d_src_off, uint8_t* d_out,
+                               const DeflateParams& P, uint32_t* d_crc, uint32_t* d_adler, JobResult* d_jres, cudaStream_t s)
+{
+    const LevelCfg& cfg = P.cfg;
+    const uint64_t nblocks = (uint64_t)nchunks * kBlocksPerChunk;
+    const uint32_t hdr_len = P.wrap == ZB200_WRAP_ZLIB ? 2 : P.wrap == ZB200_WRAP_GZIP ? 10 : 0;
+    const uint32_t trailer_len = P.wrap == ZB200_WRAP_ZLIB ? 4 : P.wrap == ZB200_WRAP_GZIP ? 8 : 0;
+    int rc;
+    if ((rc = c->ws[2].ensure((uint64_t)(nchunks + 1) * sizeof(ChunkMeta))) != 0) return rc;
+    ChunkMeta* d_chunks = c->ws[2].as<ChunkMeta>();
+    BlockMeta* d_blk = nullptr;
+    uint32_t *d_hist = nullptr, *d_codes = nullptr, *d_hdr = nullptr, *d_tok = nullptr, *d_ntok = nullptr;
+    if (nchunks && cfg.kind != 0) {
+        if ((rc = c->ws[3].ensure(span * 2 + 64)) != 0) return rc;
+        if ((rc = c->ws[4].ensure(nblocks * kTmpPerBlock * 4 + 64)) != 0) return rc;
+        if ((rc = c->ws[5].ensure(nblocks * kBlockBytes * 4 + 64)) != 0) return rc;
+        if ((rc = c->ws[6].ensure(nblocks * sizeof(BlockMeta))) != 0) return rc;
+        if ((rc = c->ws[7].ensure(nblocks * kHistSize * 4)) != 0) return rc;
+        if ((rc = c->ws[8].ensure(nblocks * kHistSize * 4)) != 0) return rc;
+        if ((rc = c->ws[9].ensure(nblocks * kHdrWords * 4)) != 0) return rc;
+        if ((rc = c->ws[10].ensure(nblocks * 4)) != 0) return rc;
+        uint16_t* d_dist = c->ws[3].as<uint16_t>();
+        uint32_t* d_tmp = c->ws[4].as<uint32_t>();
+        d_tok = c->ws[5].as<uint32_t>();
+        d_blk = c->ws[6].as<BlockMeta>();
+        d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
+        d_ntok = c->ws[10].as<uint32_t>();
+        if (cfg.chain != 0 && P.strategy != 3) {
+            if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
+            else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
+        }
+        if (cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3)
+            ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), (unsigned)nblocks, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_base, (uint32_t)span,
+                      0u, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
+                      (uint32_t)cfg.good, P.strategy, d_cd);
+        else
+            ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), (unsigned)nblocks, kWalkThreadsFast, kWalkSmem, s, d_base, (uint32_t)span,
+                      0u, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
+                      (uint32_t)cfg.good, P.strategy, d_cd);
+        ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, span, d_blk, d_hist,
+                  d_codes, d_hdr, P.strategy == 4 ? 1 : 0, d_cd, nblocks);
+    }
+    if (nchunks)
+        ZB_LAUNCH(k_plan, (nchunks + 255) / 256, 256, 0, s, (uint64_t)nchunks, span, d_chunks, d_blk, 1, cfg.kind == 0 ? 1 : 0, 0, d_cd);
+    ZB_LAUNCH(k_scan_jobs, 1, 1024, 0, s, nchunks, d_chunks, d_cd, d_jobs, njobs, hdr_len, trailer_len, d_jres);
+    if (nchunks)
+        ZB_LAUNCH(k_huff_pack, nchunks, kPackThreads, 0, s, d_base, span, d_tok, d_ntok, d_blk, d_codes, d_hdr, d_chunks, d_out, (uint64_t)0,
+                  1, 0, (uint32_t*)nullptr, d_cd, d_jobs, d_jres);
+    if ((rc = checksum_batch_launch(d_base, d_src_off, nullptr, njobs, d_crc, d_adler, nullptr, nullptr, s)) != 0) return rc;
+    ZB_LAUNCH(k_frame_jobs, (njobs + 127) / 128, 128, 0, s, d_out, d_jobs, njobs, d_crc, d_adler, P.level, P.wrap, P.strategy, d_jres);
     ZB_CHECK_LAUNCH();
     return 0;
 }
@@ -1369,8 +1552,17 @@ ZB_API int zb200_deflate(const void* src, size_t src_len, void* dst, size_t* dst
     return zb200_deflate_shard(src, src_len, nullptr, 0, dst, dst_len, level, wrap, 0, nullptr, nullptr, stream);
 }
 
-// n independent inputs -> n independent streams.  Jobs are enqueued round robin on a few contexts (each with its own
-// stream and scratch), so small files overlap on the GPU; there is one synchronisation, at the end.
+// n independent inputs -> n independent streams (the per-member compressor a ZIP writer needs, zip.c:1034-1128).
+// Consecutive jobs are packed into slabs of up to kSlabChunks chunks / jobs that go through the kernels together in job
+// mode (chunks never cross a job boundary; each stream lands in its own slot with header and trailer), so ten thousand
+// small files cost a few dozen launches instead of ten per file.  Jobs above kBatchBigJob take the single-stream
+// pipeline.  Slabs alternate over a few contexts (stream + scratch each); with host arenas the H2D copy of the next
+// slab and the D2H copies of finished slabs overlap the kernels.  The host waits once per slab, for its result words.
+constexpr uint64_t kBatchBigJob = 32ull << 20;
+constexpr uint64_t kBatchGapCopy = 64ull << 10;                 // D2H ranges of neighbouring slots merge across gaps up to this
+
+struct BatchSlab { size_t j0, j1; bool big; uint32_t nchunks; size_t cd_at, job_at, off_at; };
+
 ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t n, void* dst, const uint64_t* dst_off,
                                uint64_t* dst_len, uint32_t* crc, uint32_t* adler, int32_t* status, int level, int wrap,
                                void* stream)
@@ -1386,60 +1578,155 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
         if (src_off[i + 1] < src_off[i] || dst_off[i + 1] < dst_off[i]) { set_error("zb200_deflate_batch: offsets must not decrease"); return ZB_STREAM_ERROR; }
     DeflateParams P;
     if ((rc = deflate_params(P, level, wrap, 0)) != 0) return rc;
-    constexpr int kLanes = 4;
+
+    // ---- slabs and their tables ----
+    std::vector<BatchSlab> slabs;
+    std::vector<ChunkDesc> h_cd;
+    std::vector<JobDesc> h_jobs;
+    std::vector<uint64_t> h_off;
+    {
+        BatchSlab cur{0, 0, false, 0, 0, 0, 0};
+        auto flush = [&](size_t upto) {
+            if (upto > cur.j0) { cur.j1 = upto; slabs.push_back(cur); }
+            cur = BatchSlab{upto, upto, false, 0, h_cd.size(), h_jobs.size(), h_off.size()};
+        };
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t len = src_off[i + 1] - src_off[i];
+            if (len > kBatchBigJob) {
+                flush(i);
+                cur.big = true; cur.j0 = i;
+                flush(i + 1);
+                continue;
+            }
+            const uint32_t nc = (uint32_t)((len + kChunk - 1) / kChunk);
+            if (cur.nchunks + nc > kSlabChunks || i - cur.j0 >= kSlabChunks) flush(i);
+            const uint64_t base = src_off[cur.j0];
+            const uint32_t jb = (uint32_t)(src_off[i] - base), je = (uint32_t)(src_off[i + 1] - base);
+            const uint32_t job = (uint32_t)(i - cur.j0), first = cur.nchunks;
+            h_jobs.push_back(JobDesc{dst_off[i], dst_off[i + 1] - dst_off[i], first, nc, jb, (uint32_t)len});
+            if (h_off.size() == cur.off_at) h_off.push_back(jb);
+            h_off.push_back(je);
+            for (uint32_t k = 0; k < nc; k++) {
+                const uint32_t cb = jb + k * kChunk;
+                h_cd.push_back(ChunkDesc{cb, std::min<uint32_t>(kChunk, je - cb), jb, je, job, first, k + 1 == nc ? 1u : 0u, 0u});
+            }
+            cur.nchunks += nc;
+        }
+        flush(n);
+    }
+    const size_t nslabs = slabs.size();
+
+    constexpr int kLanes = 3;
     cudaStream_t s0 = (cudaStream_t)stream;
     Ctx* c0 = ctx_acquire(s0);
     if (!c0) return ZB_MEM_ERROR;
-    Ctx* lane[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+    Ctx* lane[kLanes] = {nullptr, nullptr, nullptr};
     int nl = 0;
     do {
-        if ((rc = c0->ensure_aux(kLanes + 2)) != 0) break;
-        const size_t nlanes = n < (size_t)kLanes ? n : (size_t)kLanes;
+        if ((rc = c0->ensure_aux((int)(2 * nslabs + kLanes + 4))) != 0) break;
+        cudaStream_t s_in = c0->aux[0], s_out = c0->aux[1];
+        cudaEvent_t* ev_in = c0->evs;
+        cudaEvent_t* ev_done = c0->evs + nslabs;
+        cudaEvent_t* ev_misc = c0->evs + 2 * nslabs;            // [0] setup, [1..kLanes] lane joins
+        const size_t nlanes = nslabs < (size_t)kLanes ? nslabs : (size_t)kLanes;
         for (; nl < (int)nlanes; nl++) {
             lane[nl] = ctx_acquire_own();
             if (!lane[nl]) { rc = ZB_MEM_ERROR; break; }
         }
         if (rc) break;
-        const uint64_t src_total = src_off[n], dst_total = dst_off[n];
-        const uint8_t* d_src = to_device(c0, src, src_total, s0, &rc);
-        if (rc) break;
+        const uint64_t src_total = src_off[n] - src_off[0], dst_total = dst_off[n];
+        const bool src_on_host = src_total != 0 && classify(src) != kDevice;
         const bool dst_on_host = classify(dst) != kDevice;
+        const uint8_t* d_src = (const uint8_t*)src;             // indexed by absolute src_off
+        if (src_on_host || src_total == 0) {
+            if ((rc = c0->in.ensure(src_total + 64)) != 0) break;
+            d_src = c0->in.as<uint8_t>() - src_off[0];
+            cudaStreamWaitEvent(s_in, c0->idle, 0);             // the staging buffer may still be read by the previous borrower
+        }
         uint8_t* d_dst = (uint8_t*)dst;
         if (dst_on_host) {
             if ((rc = c0->out.ensure(dst_total + 16)) != 0) break;
             d_dst = c0->out.as<uint8_t>();
         }
-        if ((rc = c0->ws[11].ensure(n * 32)) != 0) break;
-        if ((rc = c0->ensure_pinned(n * 32)) != 0) break;
-        uint32_t* d_res = c0->ws[11].as<uint32_t>();
-        cudaError_t e = cudaEventRecord(c0->evs[0], s0);         // the input is on the device (and the caller's stream has reached us)
-        for (int k = 0; k < nl && e == cudaSuccess; k++) e = cudaStreamWaitEvent(lane[k]->own_stream, c0->evs[0], 0);
+        // device tables: results, checksums, chunk / job / offset tables of every job-mode slab
+        const size_t at_res = 0, at_crc = at_res + n * sizeof(JobResult), at_adl = at_crc + n * 4;
+        const size_t at_cd = (at_adl + n * 4 + 15) & ~(size_t)15, at_job = at_cd + h_cd.size() * sizeof(ChunkDesc);
+        const size_t at_off = at_job + h_jobs.size() * sizeof(JobDesc), tab_bytes = at_off + h_off.size() * 8 + 16;
+        if ((rc = c0->ws[11].ensure(tab_bytes)) != 0) break;
+        if ((rc = c0->ensure_pinned(n * sizeof(JobResult))) != 0) break;
+        uint8_t* d_tab = c0->ws[11].as<uint8_t>();
+        JobResult* d_jres = reinterpret_cast<JobResult*>(d_tab + at_res);
+        uint32_t* d_crc = reinterpret_cast<uint32_t*>(d_tab + at_crc);
+        uint32_t* d_adl = reinterpret_cast<uint32_t*>(d_tab + at_adl);
+        const ChunkDesc* d_cd = reinterpret_cast<const ChunkDesc*>(d_tab + at_cd);
+        const JobDesc* d_jobs = reinterpret_cast<const JobDesc*>(d_tab + at_job);
+        const uint64_t* d_off = reinterpret_cast<const uint64_t*>(d_tab + at_off);
+        cudaError_t e = cudaSuccess;
+        if (!h_cd.empty()) e = cudaMemcpyAsync(d_tab + at_cd, h_cd.data(), h_cd.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, s0);
+        if (e == cudaSuccess && !h_jobs.empty()) e = cudaMemcpyAsync(d_tab + at_job, h_jobs.data(), h_jobs.size() * sizeof(JobDesc), cudaMemcpyHostToDevice, s0);
+        if (e == cudaSuccess && !h_off.empty()) e = cudaMemcpyAsync(d_tab + at_off, h_off.data(), h_off.size() * 8, cudaMemcpyHostToDevice, s0);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_misc[0], s0);   // tables are up (and the caller's stream has reached us)
+        for (int k = 0; k < nl && e == cudaSuccess; k++) e = cudaStreamWaitEvent(lane[k]->own_stream, ev_misc[0], 0);
+        if (e == cudaSuccess && !src_on_host) e = cudaStreamWaitEvent(s_in, ev_misc[0], 0);
         if (e != cudaSuccess) { set_error("batch setup failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
-        for (size_t i = 0; i < n; i++) {
-            Ctx* ck = lane[i % nl];
-            if ((rc = deflate_enqueue_dev(ck, ck->own_stream, d_src + src_off[i], 0, src_off[i + 1] - src_off[i], d_dst + dst_off[i],
-                                          dst_off[i + 1] - dst_off[i], P, d_res + 8 * i)) != 0) break;
+
+        // ---- enqueue: copy in (s_in) -> kernels (lane) -> result words to the host ----
+        JobResult* h_res = (JobResult*)c0->pinned;
+        size_t enq = 0;
+        for (; enq < nslabs; enq++) {
+            const BatchSlab& sl = slabs[enq];
+            Ctx* ck = lane[enq % nl];
+            cudaStream_t sk = ck->own_stream;
+            const uint64_t a = src_off[sl.j0], span = src_off[sl.j1] - a;
+            if (src_on_host && span) {
+                e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + (a - src_off[0]), span, cudaMemcpyHostToDevice, s_in);
+                if (e == cudaSuccess) e = cudaEventRecord(ev_in[enq], s_in);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, ev_in[enq], 0);
+                if (e != cudaSuccess) { set_error("input staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+            }
+            if (sl.big)
+                rc = deflate_enqueue_dev(ck, sk, d_src + a, 0, span, d_dst + dst_off[sl.j0], dst_off[sl.j0 + 1] - dst_off[sl.j0], P,
+                                         reinterpret_cast<uint32_t*>(d_jres + sl.j0));
+            else
+                rc = deflate_jobs_launch(ck, d_src + a, span, sl.nchunks, (uint32_t)(sl.j1 - sl.j0), d_cd + sl.cd_at, d_jobs + sl.job_at,
+                                         d_off + sl.off_at, d_dst, P, d_crc + sl.j0, d_adl + sl.j0, d_jres + sl.j0, sk);
+            if (rc) break;
+            e = cudaMemcpyAsync(h_res + sl.j0, d_jres + sl.j0, (sl.j1 - sl.j0) * sizeof(JobResult), cudaMemcpyDeviceToHost, sk);
+            if (e == cudaSuccess) e = cudaEventRecord(ev_done[enq], sk);
+            if (e != cudaSuccess) { set_error("batch bookkeeping failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         }
         for (int k = 0; k < nl; k++) {                           // join the lanes (also after a failed enqueue)
-            cudaEventRecord(c0->evs[1 + k], lane[k]->own_stream);
-            cudaStreamWaitEvent(s0, c0->evs[1 + k], 0);
+            cudaEventRecord(ev_misc[1 + k], lane[k]->own_stream);
+            cudaStreamWaitEvent(s0, ev_misc[1 + k], 0);
         }
-        if (rc) { cudaStreamSynchronize(s0); break; }
-        e = cudaMemcpyAsync(c0->pinned, d_res, n * 32, cudaMemcpyDeviceToHost, s0);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
-        if (e != cudaSuccess) { set_error("deflate batch failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
-        const uint32_t* r = (const uint32_t*)c0->pinned;
-        for (size_t i = 0; i < n; i++) {
-            const uint64_t total = *(const uint64_t*)(r + 8 * i), cap = dst_off[i + 1] - dst_off[i];
-            dst_len[i] = total;
-            if (crc) crc[i] = r[8 * i + 2];
-            if (adler) adler[i] = r[8 * i + 3];
-            const int32_t st = r[8 * i + 4] ? ZB_STREAM_ERROR : total > cap ? ZB_BUF_ERROR : ZB_OK;
-            if (status) status[i] = st;
-            if (dst_on_host && st == ZB_OK && total)
-                if (cudaMemcpyAsync((uint8_t*)dst + dst_off[i], d_dst + dst_off[i], total, cudaMemcpyDeviceToHost, s0) != cudaSuccess) rc = ZB_STREAM_ERROR;
+        if (rc) { cudaStreamSynchronize(s0); cudaStreamSynchronize(s_in); break; }
+
+        // ---- collect: per slab, results -> caller's arrays; finished streams -> host arena while later slabs run ----
+        // A copy covers neighbouring slots and the short gaps between them (bytes past a stream's length in its own slot).
+        uint64_t ra = 0, rb = 0;
+        auto flush_copy = [&]() {
+            if (rb > ra && cudaMemcpyAsync((uint8_t*)dst + ra, d_dst + ra, rb - ra, cudaMemcpyDeviceToHost, s_out) != cudaSuccess) rc = ZB_STREAM_ERROR;
+            ra = rb = 0;
+        };
+        for (size_t k = 0; k < nslabs && !rc; k++) {
+            if ((e = cudaEventSynchronize(ev_done[k])) != cudaSuccess) { set_error("deflate batch failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+            for (size_t i = slabs[k].j0; i < slabs[k].j1; i++) {
+                const JobResult& r = h_res[i];
+                const uint64_t cap = dst_off[i + 1] - dst_off[i];
+                dst_len[i] = r.total;
+                if (crc) crc[i] = r.crc;
+                if (adler) adler[i] = r.adler;
+                const int32_t st = r.err ? ZB_STREAM_ERROR : r.total > cap ? ZB_BUF_ERROR : ZB_OK;
+                if (status) status[i] = st;
+                if (!dst_on_host || st != ZB_OK || r.total == 0) continue;
+                const uint64_t o = dst_off[i];
+                if (rb > ra && o >= rb && o - rb <= kBatchGapCopy) rb = o + r.total;
+                else { flush_copy(); ra = o; rb = o + r.total; }
+            }
         }
-        if (dst_on_host && cudaStreamSynchronize(s0) != cudaSuccess) rc = ZB_STREAM_ERROR;
+        flush_copy();
+        if (cudaStreamSynchronize(s0) != cudaSuccess) rc = ZB_STREAM_ERROR;
+        if (dst_on_host && cudaStreamSynchronize(s_out) != cudaSuccess) rc = ZB_STREAM_ERROR;
         if (rc) set_error("deflate batch readback failed: %s", cudaGetErrorString(cudaGetLastError()));
     } while (0);
     for (int k = 0; k < nl; k++) if (lane[k]) ctx_release(lane[k], lane[k]->own_stream);

@@ -32,6 +32,26 @@ struct ChunkMeta {
     uint64_t offset;                             // byte offset in the output stream
 };
 
+// Job mode (zb200_deflate_batch): many independent inputs share one slab.  Chunks never cross a job boundary and the
+// kernels take a chunk's position, its job's span (history and hashing stay inside it) and its role from this table
+// instead of computing them from the chunk index.  Positions are relative to the slab buffer.
+struct ChunkDesc {
+    uint32_t beg, len;                           // first byte and length (1..kChunk) of the chunk
+    uint32_t job_beg, job_end;                   // span of the job the chunk belongs to
+    uint32_t job, first;                         // job index within the slab; index of the job's first chunk
+    uint32_t last, pad;                          // 1 = last chunk of its job
+};
+struct JobDesc {
+    uint64_t dst_off, dst_cap;                   // the job's output slot in the destination arena
+    uint32_t first_chunk, nchunks;               // its chunks within the slab (nchunks == 0: empty input)
+    uint32_t src_beg, src_len;
+};
+struct JobResult {                               // 32 bytes per job, copied to the host as they are
+    uint64_t total;                              // length of the finished stream (header + blocks + trailer)
+    uint32_t crc, adler;                         // checksums of the job's input
+    uint32_t err, pad[3];                        // chunks packed to a size other than planned (must stay 0)
+};
+
 // Token: literal = byte value; match = (distance << 16) | (length - 3).
 __device__ __forceinline__ uint32_t len_code(uint32_t l)       // l = length - 3; trees.c _length_code
 {
