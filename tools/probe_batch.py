@@ -28,3 +28,28 @@ for i in rng.sample(range(nfiles), 20):
     z = bytes(dst[int(doff[i]):int(doff[i]) + int(dlen[i])])
     assert zlib.decompress(z, -15) == src[a:b].tobytes() and zlib.crc32(src[a:b].tobytes()) == crc[i]
 print("spot check ok")
+import torch
+# pinned arenas, then device arenas
+for kind in ("pinned", "device"):
+    if kind == "pinned":
+        tsrc = torch.from_numpy(src).pin_memory(); tdst = torch.empty(len(dst), dtype=torch.uint8).pin_memory()
+    else:
+        tsrc = torch.from_numpy(src).cuda(); tdst = torch.empty(len(dst), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for rep in range(3):
+        t0 = time.perf_counter()
+        rc = L.dll.zb200_deflate_batch(tsrc.data_ptr(), off.ctypes.data, nfiles, tdst.data_ptr(), doff.ctypes.data, dlen.ctypes.data,
+                                       crc.ctypes.data, None, st.ctypes.data, 1, zb.WRAP_RAW, None)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert rc == 0 and not st.any()
+        print(f"deflate_batch ({kind} arenas): {dt * 1e3:.1f} ms = {total / dt / 1e9:.2f} GB/s", flush=True)
+    out = tdst.cpu().numpy()
+    for i in rng.sample(range(nfiles), 10):
+        a, b = int(off[i]), int(off[i + 1])
+        assert zlib.decompress(bytes(out[int(doff[i]):int(doff[i]) + int(dlen[i])]), -15) == src[a:b].tobytes()
+L.dll.zb200_profile(1)
+rc = L.dll.zb200_deflate_batch(tsrc.data_ptr(), off.ctypes.data, nfiles, tdst.data_ptr(), doff.ctypes.data, dlen.ctypes.data,
+                               crc.ctypes.data, None, st.ctypes.data, 1, zb.WRAP_RAW, None)
+torch.cuda.synchronize()
+print(L.profile_report() if hasattr(L, "profile_report") else "")

@@ -27,7 +27,7 @@
 // closed form (the deferred-modulo idea of adler32.c:97-106, with the bound set by u32).
 //
 // Roofline: HBM.  Algorithmic bytes = len (read once), 8 bytes written.
-#include "zb_common.cuh"
+#include "zb_deflate.cuh"
 
 namespace zb {
 
@@ -275,7 +275,7 @@ k_checksum_final(const Partial* __restrict__ parts, uint32_t n_parts, const uint
 __global__ void __launch_bounds__(kStripeThreads)
 k_checksum_batch(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const uint64_t* __restrict__ lens,
                  uint32_t* __restrict__ crc_out, uint32_t* __restrict__ adler_out, const uint32_t* __restrict__ expect,
-                 int32_t* __restrict__ ok)
+                 int32_t* __restrict__ ok, const ChunkDesc* __restrict__ cd)
 {
     __shared__ uint32_t s_tab[256];
     __shared__ uint32_t s_reg[kStripeThreads / 32], s_a[kStripeThreads / 32], s_b[kStripeThreads / 32];
@@ -283,8 +283,8 @@ k_checksum_batch(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
     __syncthreads();
     const uint64_t i = blockIdx.x;
     if (expect && (ok[i] != 0 || expect[3 * i + 2] == 0)) return;   // failed already, or not a gzip member
-    const uint8_t* buf = base + off[i];
-    const uint64_t len = lens ? lens[i] : off[i + 1] - off[i];
+    const uint8_t* buf = base + (cd ? (uint64_t)cd[i].beg : off[i]);
+    const uint64_t len = cd ? (uint64_t)cd[i].len : lens ? lens[i] : off[i + 1] - off[i];
     const uint64_t stripe = (len + kStripeThreads - 1) / kStripeThreads;
     const uint64_t beg = min(len, (uint64_t)threadIdx.x * stripe), end = min(len, beg + stripe);
     uint32_t c = 0, a = 0, b = 0;                             // raw register, byte sum, sum of prefix sums (both mod 65521)
@@ -334,7 +334,45 @@ int checksum_batch_launch(const uint8_t* d_base, const uint64_t* d_off, const ui
                           uint32_t* d_adler, const uint32_t* d_expect, int32_t* d_ok, cudaStream_t s)
 {
     if (n == 0) return 0;
-    ZB_LAUNCH(k_checksum_batch, (unsigned)n, kStripeThreads, 0, s, d_base, d_off, d_lens, d_crc, d_adler, d_expect, d_ok);
+    ZB_LAUNCH(k_checksum_batch, (unsigned)n, kStripeThreads, 0, s, d_base, d_off, d_lens, d_crc, d_adler, d_expect, d_ok,
+              (const ChunkDesc*)nullptr);
+    ZB_CHECK_LAUNCH();
+    return 0;
+}
+
+// Job mode of the deflate batch: checksums per chunk (one CTA each, so a 16 MiB member is 128 CTAs, not one), then one
+// thread per job folds its chunks in order with crc32_combine / adler32_combine (crc32.c:370-423, adler32.c:128-149).
+__global__ void k_checksum_join_jobs(const uint32_t* __restrict__ ccrc, const uint32_t* __restrict__ cadl,
+                                     const ChunkDesc* __restrict__ cd, const JobDesc* __restrict__ jobs, uint32_t njobs,
+                                     uint32_t* __restrict__ crc_out, uint32_t* __restrict__ adler_out)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    const JobDesc jd = jobs[j];
+    uint32_t crc = 0, s1 = 1, s2 = 0;
+    const uint32_t xfull = pow8(ZB200_CHUNK);
+    for (uint32_t k = 0; k < jd.nchunks; k++) {
+        const uint32_t c = jd.first_chunk + k, len = cd[c].len;
+        crc = gf2_mul(crc, len == ZB200_CHUNK ? xfull : pow8(len)) ^ ccrc[c];
+        const uint32_t a2 = cadl[c], rem = len % kAdlerBase;
+        s2 = (s2 + (uint32_t)((uint64_t)rem * s1 % kAdlerBase) + (a2 >> 16) + kAdlerBase - rem) % kAdlerBase;
+        s1 = (s1 + (a2 & 0xffffu) + kAdlerBase - 1) % kAdlerBase;
+    }
+    crc_out[j] = crc;
+    adler_out[j] = (s2 << 16) | s1;
+}
+
+int checksum_jobs_launch(Ctx* c, const uint8_t* d_base, const ChunkDesc* d_cd, uint32_t nchunks, const JobDesc* d_jobs,
+                         uint32_t njobs, uint32_t* d_crc, uint32_t* d_adler, cudaStream_t s)
+{
+    int rc = c->ws[0].ensure((size_t)(nchunks + 1) * 8);
+    if (rc) return rc;
+    uint32_t* d_ccrc = c->ws[0].as<uint32_t>();
+    uint32_t* d_cadl = d_ccrc + nchunks;
+    if (nchunks)
+        ZB_LAUNCH(k_checksum_batch, nchunks, kStripeThreads, 0, s, d_base, (const uint64_t*)nullptr, (const uint64_t*)nullptr, d_ccrc,
+                  d_cadl, (const uint32_t*)nullptr, (int32_t*)nullptr, d_cd);
+    ZB_LAUNCH(k_checksum_join_jobs, (njobs + 127) / 128, 128, 0, s, d_ccrc, d_cadl, d_cd, d_jobs, njobs, d_crc, d_adler);
     ZB_CHECK_LAUNCH();
     return 0;
 }

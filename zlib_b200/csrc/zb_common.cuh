@@ -102,6 +102,10 @@ int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, 
 // Either writes crc/adler per buffer, or (d_expect != nullptr) checks {crc32, length} pairs and flags d_ok[i].
 int checksum_batch_launch(const uint8_t* d_base, const uint64_t* d_off, const uint64_t* d_lens, size_t n, uint32_t* d_crc,
                           uint32_t* d_adler, const uint32_t* d_expect, int32_t* d_ok, cudaStream_t s);
+// job mode of the deflate batch: per-chunk checksums joined per job (tables of zb_deflate.cuh)
+struct ChunkDesc; struct JobDesc;
+int checksum_jobs_launch(Ctx* c, const uint8_t* d_base, const ChunkDesc* d_cd, uint32_t nchunks, const JobDesc* d_jobs,
+                         uint32_t njobs, uint32_t* d_crc, uint32_t* d_adler, cudaStream_t s);
 const unsigned long* host_crc_table();
 
 }  // namespace zb

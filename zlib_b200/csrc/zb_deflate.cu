@@ -1257,7 +1257,7 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
 // One slab in job mode: d_base[0, span) holds whole jobs back to back; chunk and job tables are on the device.  Every
 // stream lands in its own slot of d_out, complete with header and trailer; d_jres[j] = {length, checksums, error count}.
 static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uint32_t nchunks, uint32_t njobs,
-                               const ChunkDesc* d_cd, const JobDesc* d_jobs, const uint64_t* d_src_off, uint8_t* d_out,
+                               const ChunkDesc* d_cd, const JobDesc* d_jobs, uint8_t* d_out,
                                const DeflateParams& P, uint32_t* d_crc, uint32_t* d_adler, JobResult* d_jres, cudaStream_t s)
 {
     const LevelCfg& cfg = P.cfg;
@@ -1305,7 +1305,7 @@ static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uin
     if (nchunks)
         ZB_LAUNCH(k_huff_pack, nchunks, kPackThreads, 0, s, d_base, span, d_tok, d_ntok, d_blk, d_codes, d_hdr, d_chunks, d_out, (uint64_t)0,
                   1, 0, (uint32_t*)nullptr, d_cd, d_jobs, d_jres);
-    if ((rc = checksum_batch_launch(d_base, d_src_off, nullptr, njobs, d_crc, d_adler, nullptr, nullptr, s)) != 0) return rc;
+    if ((rc = checksum_jobs_launch(c, d_base, d_cd, nchunks, d_jobs, njobs, d_crc, d_adler, s)) != 0) return rc;
     ZB_LAUNCH(k_frame_jobs, (njobs + 127) / 128, 128, 0, s, d_out, d_jobs, njobs, d_crc, d_adler, P.level, P.wrap, P.strategy, d_jres);
     ZB_CHECK_LAUNCH();
     return 0;
@@ -1561,7 +1561,7 @@ ZB_API int zb200_deflate(const void* src, size_t src_len, void* dst, size_t* dst
 constexpr uint64_t kBatchBigJob = 32ull << 20;
 constexpr uint64_t kBatchGapCopy = 64ull << 10;                 // D2H ranges of neighbouring slots merge across gaps up to this
 
-struct BatchSlab { size_t j0, j1; bool big; uint32_t nchunks; size_t cd_at, job_at, off_at; };
+struct BatchSlab { size_t j0, j1; bool big; uint32_t nchunks; size_t cd_at, job_at; };
 
 ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t n, void* dst, const uint64_t* dst_off,
                                uint64_t* dst_len, uint32_t* crc, uint32_t* adler, int32_t* status, int level, int wrap,
@@ -1583,12 +1583,11 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
     std::vector<BatchSlab> slabs;
     std::vector<ChunkDesc> h_cd;
     std::vector<JobDesc> h_jobs;
-    std::vector<uint64_t> h_off;
     {
-        BatchSlab cur{0, 0, false, 0, 0, 0, 0};
+        BatchSlab cur{0, 0, false, 0, 0, 0};
         auto flush = [&](size_t upto) {
             if (upto > cur.j0) { cur.j1 = upto; slabs.push_back(cur); }
-            cur = BatchSlab{upto, upto, false, 0, h_cd.size(), h_jobs.size(), h_off.size()};
+            cur = BatchSlab{upto, upto, false, 0, h_cd.size(), h_jobs.size()};
         };
         for (size_t i = 0; i < n; i++) {
             const uint64_t len = src_off[i + 1] - src_off[i];
@@ -1604,8 +1603,6 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
             const uint32_t jb = (uint32_t)(src_off[i] - base), je = (uint32_t)(src_off[i + 1] - base);
             const uint32_t job = (uint32_t)(i - cur.j0), first = cur.nchunks;
             h_jobs.push_back(JobDesc{dst_off[i], dst_off[i + 1] - dst_off[i], first, nc, jb, (uint32_t)len});
-            if (h_off.size() == cur.off_at) h_off.push_back(jb);
-            h_off.push_back(je);
             for (uint32_t k = 0; k < nc; k++) {
                 const uint32_t cb = jb + k * kChunk;
                 h_cd.push_back(ChunkDesc{cb, std::min<uint32_t>(kChunk, je - cb), jb, je, job, first, k + 1 == nc ? 1u : 0u, 0u});
@@ -1628,7 +1625,7 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
         cudaEvent_t* ev_in = c0->evs;
         cudaEvent_t* ev_done = c0->evs + nslabs;
         cudaEvent_t* ev_misc = c0->evs + 2 * nslabs;            // [0] setup, [1..kLanes] lane joins
-        const size_t nlanes = nslabs < (size_t)kLanes ? nslabs : (size_t)kLanes;
+        const size_t nlanes = g_profile ? 1 : nslabs < (size_t)kLanes ? nslabs : (size_t)kLanes;   // per-kernel timing wants the slabs serialized
         for (; nl < (int)nlanes; nl++) {
             lane[nl] = ctx_acquire_own();
             if (!lane[nl]) { rc = ZB_MEM_ERROR; break; }
@@ -1651,7 +1648,7 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
         // device tables: results, checksums, chunk / job / offset tables of every job-mode slab
         const size_t at_res = 0, at_crc = at_res + n * sizeof(JobResult), at_adl = at_crc + n * 4;
         const size_t at_cd = (at_adl + n * 4 + 15) & ~(size_t)15, at_job = at_cd + h_cd.size() * sizeof(ChunkDesc);
-        const size_t at_off = at_job + h_jobs.size() * sizeof(JobDesc), tab_bytes = at_off + h_off.size() * 8 + 16;
+        const size_t tab_bytes = at_job + h_jobs.size() * sizeof(JobDesc) + 16;
         if ((rc = c0->ws[11].ensure(tab_bytes)) != 0) break;
         if ((rc = c0->ensure_pinned(n * sizeof(JobResult))) != 0) break;
         uint8_t* d_tab = c0->ws[11].as<uint8_t>();
@@ -1660,11 +1657,9 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
         uint32_t* d_adl = reinterpret_cast<uint32_t*>(d_tab + at_adl);
         const ChunkDesc* d_cd = reinterpret_cast<const ChunkDesc*>(d_tab + at_cd);
         const JobDesc* d_jobs = reinterpret_cast<const JobDesc*>(d_tab + at_job);
-        const uint64_t* d_off = reinterpret_cast<const uint64_t*>(d_tab + at_off);
         cudaError_t e = cudaSuccess;
         if (!h_cd.empty()) e = cudaMemcpyAsync(d_tab + at_cd, h_cd.data(), h_cd.size() * sizeof(ChunkDesc), cudaMemcpyHostToDevice, s0);
         if (e == cudaSuccess && !h_jobs.empty()) e = cudaMemcpyAsync(d_tab + at_job, h_jobs.data(), h_jobs.size() * sizeof(JobDesc), cudaMemcpyHostToDevice, s0);
-        if (e == cudaSuccess && !h_off.empty()) e = cudaMemcpyAsync(d_tab + at_off, h_off.data(), h_off.size() * 8, cudaMemcpyHostToDevice, s0);
         if (e == cudaSuccess) e = cudaEventRecord(ev_misc[0], s0);   // tables are up (and the caller's stream has reached us)
         for (int k = 0; k < nl && e == cudaSuccess; k++) e = cudaStreamWaitEvent(lane[k]->own_stream, ev_misc[0], 0);
         if (e == cudaSuccess && !src_on_host) e = cudaStreamWaitEvent(s_in, ev_misc[0], 0);
@@ -1689,7 +1684,7 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
                                          reinterpret_cast<uint32_t*>(d_jres + sl.j0));
             else
                 rc = deflate_jobs_launch(ck, d_src + a, span, sl.nchunks, (uint32_t)(sl.j1 - sl.j0), d_cd + sl.cd_at, d_jobs + sl.job_at,
-                                         d_off + sl.off_at, d_dst, P, d_crc + sl.j0, d_adl + sl.j0, d_jres + sl.j0, sk);
+                                         d_dst, P, d_crc + sl.j0, d_adl + sl.j0, d_jres + sl.j0, sk);
             if (rc) break;
             e = cudaMemcpyAsync(h_res + sl.j0, d_jres + sl.j0, (sl.j1 - sl.j0) * sizeof(JobResult), cudaMemcpyDeviceToHost, sk);
             if (e == cudaSuccess) e = cudaEventRecord(ev_done[enq], sk);
