@@ -35,7 +35,6 @@ constexpr int kStride = 512;               // bytes a warp consumes per iteratio
 constexpr int kMainThreads = 1024;
 constexpr int kMainWarps = kMainThreads / 32;
 constexpr uint32_t kMaxIters = 1024;       // keeps the u32 Adler accumulators exact (see below)
-constexpr size_t kMainSmem = 4 * 256 * 32 * sizeof(uint32_t);   // 128 KiB of replicated tables
 constexpr size_t kMainThreshold = 1u << 20;                      // below this the stripe kernel runs alone
 constexpr int kStripeThreads = 256;
 constexpr uint32_t kMaxStripe = 4096;      // u32 bound for the serial s2 accumulation
@@ -113,12 +112,25 @@ int checksum_setup()
 }
 
 // ---- main kernel: aligned bulk, one segment of `iters_per_warp` x 512 B per warp ----
-__device__ __forceinline__ uint32_t stride_step(const uint32_t* __restrict__ lane_tab, uint32_t c)
+// Table image in shared memory: entry v of table t for lane l is the word at byte offset
+//     (t >> 1) * 65536 + v * 256 + (t & 1) * 128 + l * 4
+// from a 64 KiB-aligned shared address, so bank = l (a warp's 32 lookups never conflict) and the address of a lookup
+// is ONE byte permute: byte 1 of the address is the index byte of the register, bytes 0, 2, 3 come from a per-lane
+// constant (PRMT), instead of extract + scale + add.  The kernel is instruction bound, so this is what moves it.
+constexpr uint32_t kTabImage = 2 * 65536;                       // bytes of the table image
+constexpr size_t kMainSmem = kTabImage + 65536;                 // + slack to align the image to 64 KiB
+
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
-    // lane_tab points at word `lane` of the replicated tables; entry v of table t sits at
-    // lane_tab[(t*256 + v)*32].
-    return lane_tab[((c & 0xffu)) * 32] ^ lane_tab[(256 + ((c >> 8) & 0xffu)) * 32] ^
-           lane_tab[(512 + ((c >> 16) & 0xffu)) * 32] ^ lane_tab[(768 + (c >> 24)) * 32];
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t stride_step(uint32_t c, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3)
+{
+    return lds32(__byte_perm(c, k0, 0x7604)) ^ lds32(__byte_perm(c, k1, 0x7614)) ^
+           lds32(__byte_perm(c, k2, 0x7624)) ^ lds32(__byte_perm(c, k3, 0x7634));
 }
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p)
@@ -133,63 +145,91 @@ __global__ void __launch_bounds__(kMainThreads, 1)
 k_checksum_main(const uint8_t* __restrict__ base, uint64_t n_units, uint32_t iters_per_warp,
                 uint64_t base_off, Partial* __restrict__ parts)
 {
-    extern __shared__ __align__(16) uint32_t s_tab[];
-    for (int i = threadIdx.x; i < 4 * 256 * 32; i += kMainThreads) s_tab[i] = (&g_tab_stride[0][0])[i >> 5];
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ Partial s_part[kMainWarps];
+    const uint32_t img = ((uint32_t)__cvta_generic_to_shared(s_raw) + 65535u) & ~65535u;   // shared address of the image
+    for (uint32_t i = threadIdx.x; i < kTabImage / 4; i += kMainThreads) {
+        const uint32_t t = ((i >> 14) << 1) | ((i >> 5) & 1u), v = (i >> 6) & 255u;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(img + i * 4), "r"(g_tab_stride[t][v]) : "memory");
+    }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp = (uint64_t)blockIdx.x * kMainWarps + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t warp = (uint64_t)blockIdx.x * kMainWarps + wid;
     const uint64_t u0 = warp * iters_per_warp;
-    if (u0 >= n_units) {
-        if (lane == 0) parts[warp] = Partial{0, 0, 0, 0, 0};
-        return;
-    }
-    const uint32_t iters = (uint32_t)min((uint64_t)iters_per_warp, n_units - u0);
-    const uint4* p = reinterpret_cast<const uint4*>(base + u0 * kStride) + lane;
-    const uint32_t* lane_tab = s_tab + lane;
+    Partial mine{0, 0, 0, 0, 0};
+    if (u0 < n_units) {
+        const uint32_t iters = (uint32_t)min((uint64_t)iters_per_warp, n_units - u0);
+        const uint4* p = reinterpret_cast<const uint4*>(base + u0 * kStride) + lane;
+        const uint32_t k0 = img + lane * 4, k1 = k0 + 128, k2 = k0 + 65536, k3 = k2 + 128;
 
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    uint32_t s_a = 0, s_j = 0, s_b = 0;    // sum, iteration-weighted sum, in-piece weighted sum
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        uint32_t s_a = 0, s_j = 0, s_b = 0;    // sum, iteration-weighted sum, in-piece weighted sum
 
-    uint32_t j = 0;
-    // two loads in flight per lane
-    for (; j + 2 <= iters; j += 2) {
-        uint4 w0 = ld_stream(p + (size_t)j * 32);
-        uint4 w1 = ld_stream(p + (size_t)(j + 1) * 32);
-        c0 = stride_step(lane_tab, c0) ^ w0.x; c1 = stride_step(lane_tab, c1) ^ w0.y;
-        c2 = stride_step(lane_tab, c2) ^ w0.z; c3 = stride_step(lane_tab, c3) ^ w0.w;
-        uint32_t sum0 = __dp4a(w0.x, 0x01010101u, __dp4a(w0.y, 0x01010101u, __dp4a(w0.z, 0x01010101u, __dp4a(w0.w, 0x01010101u, 0u))));
-        s_b = __dp4a(w0.x, 0x0d0e0f10u, __dp4a(w0.y, 0x090a0b0cu, __dp4a(w0.z, 0x05060708u, __dp4a(w0.w, 0x01020304u, s_b))));
-        s_a += sum0; s_j += j * sum0;
-        c0 = stride_step(lane_tab, c0) ^ w1.x; c1 = stride_step(lane_tab, c1) ^ w1.y;
-        c2 = stride_step(lane_tab, c2) ^ w1.z; c3 = stride_step(lane_tab, c3) ^ w1.w;
-        uint32_t sum1 = __dp4a(w1.x, 0x01010101u, __dp4a(w1.y, 0x01010101u, __dp4a(w1.z, 0x01010101u, __dp4a(w1.w, 0x01010101u, 0u))));
-        s_b = __dp4a(w1.x, 0x0d0e0f10u, __dp4a(w1.y, 0x090a0b0cu, __dp4a(w1.z, 0x05060708u, __dp4a(w1.w, 0x01020304u, s_b))));
-        s_a += sum1; s_j += (j + 1) * sum1;
-    }
-    for (; j < iters; ++j) {
-        uint4 w0 = ld_stream(p + (size_t)j * 32);
-        c0 = stride_step(lane_tab, c0) ^ w0.x; c1 = stride_step(lane_tab, c1) ^ w0.y;
-        c2 = stride_step(lane_tab, c2) ^ w0.z; c3 = stride_step(lane_tab, c3) ^ w0.w;
-        uint32_t sum0 = __dp4a(w0.x, 0x01010101u, __dp4a(w0.y, 0x01010101u, __dp4a(w0.z, 0x01010101u, __dp4a(w0.w, 0x01010101u, 0u))));
-        s_b = __dp4a(w0.x, 0x0d0e0f10u, __dp4a(w0.y, 0x090a0b0cu, __dp4a(w0.z, 0x05060708u, __dp4a(w0.w, 0x01020304u, s_b))));
-        s_a += sum0; s_j += j * sum0;
-    }
+        uint32_t j = 0;
+        // two loads in flight per lane
+        for (; j + 2 <= iters; j += 2) {
+            uint4 w0 = ld_stream(p + (size_t)j * 32);
+            uint4 w1 = ld_stream(p + (size_t)(j + 1) * 32);
+            c0 = stride_step(c0, k0, k1, k2, k3) ^ w0.x; c1 = stride_step(c1, k0, k1, k2, k3) ^ w0.y;
+            c2 = stride_step(c2, k0, k1, k2, k3) ^ w0.z; c3 = stride_step(c3, k0, k1, k2, k3) ^ w0.w;
+            uint32_t sum0 = __dp4a(w0.x, 0x01010101u, __dp4a(w0.y, 0x01010101u, __dp4a(w0.z, 0x01010101u, __dp4a(w0.w, 0x01010101u, 0u))));
+            s_b = __dp4a(w0.x, 0x0d0e0f10u, __dp4a(w0.y, 0x090a0b0cu, __dp4a(w0.z, 0x05060708u, __dp4a(w0.w, 0x01020304u, s_b))));
+            s_a += sum0; s_j += j * sum0;
+            c0 = stride_step(c0, k0, k1, k2, k3) ^ w1.x; c1 = stride_step(c1, k0, k1, k2, k3) ^ w1.y;
+            c2 = stride_step(c2, k0, k1, k2, k3) ^ w1.z; c3 = stride_step(c3, k0, k1, k2, k3) ^ w1.w;
+            uint32_t sum1 = __dp4a(w1.x, 0x01010101u, __dp4a(w1.y, 0x01010101u, __dp4a(w1.z, 0x01010101u, __dp4a(w1.w, 0x01010101u, 0u))));
+            s_b = __dp4a(w1.x, 0x0d0e0f10u, __dp4a(w1.y, 0x090a0b0cu, __dp4a(w1.z, 0x05060708u, __dp4a(w1.w, 0x01020304u, s_b))));
+            s_a += sum1; s_j += (j + 1) * sum1;
+        }
+        for (; j < iters; ++j) {
+            uint4 w0 = ld_stream(p + (size_t)j * 32);
+            c0 = stride_step(c0, k0, k1, k2, k3) ^ w0.x; c1 = stride_step(c1, k0, k1, k2, k3) ^ w0.y;
+            c2 = stride_step(c2, k0, k1, k2, k3) ^ w0.z; c3 = stride_step(c3, k0, k1, k2, k3) ^ w0.w;
+            uint32_t sum0 = __dp4a(w0.x, 0x01010101u, __dp4a(w0.y, 0x01010101u, __dp4a(w0.z, 0x01010101u, __dp4a(w0.w, 0x01010101u, 0u))));
+            s_b = __dp4a(w0.x, 0x0d0e0f10u, __dp4a(w0.y, 0x090a0b0cu, __dp4a(w0.z, 0x05060708u, __dp4a(w0.w, 0x01020304u, s_b))));
+            s_a += sum0; s_j += j * sum0;
+        }
 
-    // Move the four lane registers to the end of the segment and reduce across the warp.
-    uint32_t reg = gf2_mul(c0, g_lane_mul[lane * 4 + 0]) ^ gf2_mul(c1, g_lane_mul[lane * 4 + 1]) ^
-                   gf2_mul(c2, g_lane_mul[lane * 4 + 2]) ^ gf2_mul(c3, g_lane_mul[lane * 4 + 3]);
-    // Adler: byte at segment offset o = 512 j + 16 lane + t weighs (L - o).
-    const uint64_t L = (uint64_t)iters * kStride;
-    uint64_t bw = (L - 16u * lane - 16u) * (uint64_t)s_a + (uint64_t)s_b - (uint64_t)kStride * s_j;
-    uint32_t a = s_a % kAdlerBase, b = (uint32_t)(bw % kAdlerBase);
+        // Move the four lane registers to the end of the segment and reduce across the warp.
+        uint32_t reg = gf2_mul(c0, g_lane_mul[lane * 4 + 0]) ^ gf2_mul(c1, g_lane_mul[lane * 4 + 1]) ^
+                       gf2_mul(c2, g_lane_mul[lane * 4 + 2]) ^ gf2_mul(c3, g_lane_mul[lane * 4 + 3]);
+        // Adler: byte at segment offset o = 512 j + 16 lane + t weighs (L - o).
+        const uint64_t L = (uint64_t)iters * kStride;
+        uint64_t bw = (L - 16u * lane - 16u) * (uint64_t)s_a + (uint64_t)s_b - (uint64_t)kStride * s_j;
+        uint32_t a = s_a % kAdlerBase, b = (uint32_t)(bw % kAdlerBase);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
+        for (int o = 16; o; o >>= 1) {
+            reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        mine = Partial{reg, a % kAdlerBase, b % kAdlerBase, 0, base_off + (u0 + iters) * kStride};
     }
-    if (lane == 0) parts[warp] = Partial{reg, a % kAdlerBase, b % kAdlerBase, 0, base_off + (u0 + iters) * kStride};
+    // The CTA's warps cover consecutive segments: fold their partials to the end of the last one here (one modular
+    // power per warp, all CTAs at once), so the final kernel sees one record per CTA instead of one per warp.
+    if (lane == 0) s_part[wid] = mine;
+    __syncthreads();
+    if (wid == 0) {
+        const Partial p = s_part[lane];
+        uint64_t cta_end = p.end;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { const uint64_t y = __shfl_xor_sync(0xffffffffu, cta_end, o); cta_end = y > cta_end ? y : cta_end; }
+        uint32_t reg = 0, a = 0, b = 0;
+        if (p.end) {
+            const uint64_t suffix = cta_end - p.end;
+            reg = suffix ? gf2_mul(p.reg, pow8(suffix)) : p.reg;
+            a = p.a;
+            b = (p.b + (uint32_t)((suffix % kAdlerBase) * p.a % kAdlerBase)) % kAdlerBase;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) parts[blockIdx.x] = Partial{reg, a % kAdlerBase, b % kAdlerBase, 0, cta_end};
+    }
 }
 
 // ---- stripe kernel: small or ragged ranges, one contiguous stripe per thread ----
@@ -412,7 +452,7 @@ int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, 
     if (iters < 8) iters = 8;
     uint64_t used_warps = (n_units + iters - 1) / iters;
     uint32_t blocks = (uint32_t)((used_warps + kMainWarps - 1) / kMainWarps);
-    uint64_t n_parts = (uint64_t)blocks * kMainWarps;
+    uint64_t n_parts = blocks;                                  // one record per CTA
     int rc = c->ws[0].ensure(n_parts * sizeof(Partial));
     if (rc) return rc;
     ZB_LAUNCH(k_checksum_main, blocks, kMainThreads, kMainSmem, s, d_buf + head, n_units, iters, head, c->ws[0].as<Partial>());
