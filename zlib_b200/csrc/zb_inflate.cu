@@ -40,13 +40,20 @@ constexpr uint32_t kWindow32 = 32768;
 
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// entry: bits 0-3 code length (0 = not in the primary table), 4-7 extra-bit count, 8-9 kind,
-// 16-31 literal value / symbol, or base of a length or distance
+// entry: bits 0-4 code length (0 = not in the primary table), 5-9 code length + extra-bit count (what the symbol
+// consumes), 10-11 kind, 15 set for a length / distance base that is in the table, 16-30 literal value / symbol, or
+// base of a length or distance, 31 set for a literal that is in the table.  Bits 15 and 31 are what the lean loop
+// tests: one sign test for "literal", one bit test for "base", anything else goes to the careful decoder.
 enum { kLit = 0, kBase = 1, kEob = 2, kBad = 3 };
 __device__ __forceinline__ uint32_t mk_entry(uint32_t len, uint32_t extra, uint32_t kind, uint32_t val)
 {
-    return len | (extra << 4) | (kind << 8) | (val << 16);
+    const uint32_t flags = len == 0 ? 0u : kind == kBase ? 0x8000u : kind == kLit ? 0x80000000u : 0u;
+    return len | ((len + extra) << 5) | (kind << 10) | (val << 16) | flags;
 }
+__device__ __forceinline__ uint32_t ent_len(uint32_t e) { return e & 31u; }
+__device__ __forceinline__ uint32_t ent_extra(uint32_t e) { return ((e >> 5) & 31u) - (e & 31u); }
+__device__ __forceinline__ uint32_t ent_kind(uint32_t e) { return (e >> 10) & 3u; }
+__device__ __forceinline__ uint32_t ent_val(uint32_t e) { return (e >> 16) & 0x7fffu; }
 __device__ __forceinline__ uint32_t litlen_entry(uint32_t s, uint32_t len)
 {
     if (s < 256) return mk_entry(len, 0, kLit, s);
@@ -225,7 +232,7 @@ __device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st,
         const uint64_t mark = b.used;
         refill(b);
         uint32_t e = t->lit[peek(b, kLitBits)];
-        const uint32_t len = e & 15u;
+        const uint32_t len = ent_len(e);
         if (len != 0) {
             if (!have(b, (int)len)) { b.used = mark; return kShortIn; }
             drop(b, (int)len);
@@ -235,23 +242,23 @@ __device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st,
             if (s == -2) { st->msg = kMsgBadLit; return kError; }
             e = litlen_entry((uint32_t)s, 1);
         }
-        const uint32_t kind = (e >> 8) & 3u;
+        const uint32_t kind = ent_kind(e);
         if (kind == kLit) {
             if (o.pos >= o.cap) { if (streaming) b.used = mark; return kShortOut; }
-            if (lane == 0) o.p[o.pos] = (uint8_t)(e >> 16);
+            if (lane == 0) o.p[o.pos] = (uint8_t)ent_val(e);
             o.pos++;
             if (one) return kRunning;
             continue;
         }
         if (kind == kEob) return kDone;
         if (kind == kBad) { st->msg = kMsgBadLit; return kError; }
-        const int xl = (int)((e >> 4) & 15u);
+        const int xl = (int)ent_extra(e);
         if (!have(b, xl)) { b.used = mark; return kShortIn; }
-        const uint32_t mlen = (e >> 16) + peek(b, xl);
+        const uint32_t mlen = ent_val(e) + peek(b, xl);
         drop(b, xl);
         refill(b);
         uint32_t de = t->dist[peek(b, kDistBits)];
-        const uint32_t dl = de & 15u;
+        const uint32_t dl = ent_len(de);
         if (dl != 0) {
             if (!have(b, (int)dl)) { b.used = mark; return kShortIn; }
             drop(b, (int)dl);
@@ -261,11 +268,11 @@ __device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st,
             if (s == -2) { st->msg = kMsgBadDist; return kError; }
             de = dist_entry((uint32_t)s, 1);
         }
-        if (((de >> 8) & 3u) == kBad) { st->msg = kMsgBadDist; return kError; }
-        const int xd = (int)((de >> 4) & 15u);
+        if (ent_kind(de) == kBad) { st->msg = kMsgBadDist; return kError; }
+        const int xd = (int)ent_extra(de);
         refill(b);
         if (!have(b, xd)) { b.used = mark; return kShortIn; }
-        const uint32_t dist = (de >> 16) + peek(b, xd);
+        const uint32_t dist = ent_val(de) + peek(b, xd);
         drop(b, xd);
         if ((uint64_t)dist > o.pos + o.hist) { st->msg = kMsgFar; return kError; }
         const uint32_t done = copy_match(o, mlen, dist);
@@ -277,90 +284,92 @@ __device__ Stop decode_block(Bits& b, Out& o, const WarpTables* t, InfState* st,
     }
 }
 
-// The same decode without the bookkeeping, for the stretch of a block where neither buffer can run out: at
-// least 72 valid input bits beyond the bit buffer (a symbol takes at most 48) and 258 bytes of room (the
-// reference's inflate_fast makes the same deal, inffast.c:24-30,67-70).  Bit accounting is one 32-bit counter,
-// there are no per-field input checks and no state for resuming.  Anything unusual -- a code longer than the
-// primary table, an invalid symbol, a distance beyond the history -- rewinds to the start of that symbol and
-// returns kRunning, and the careful decoder above deals with it (and produces the error, if it is one).
-// Returns kDone at end-of-block, kRunning otherwise.
+// The same decode without the bookkeeping, for the stretch of a block where neither buffer can run out: a symbol
+// starts only while five whole input words lie ahead (it takes at most 48 bits) and 260 bytes of room are left (the
+// reference's inflate_fast makes the same deal, inffast.c:24-30,67-70).  Every lane executes this loop, so its cost is
+// its instruction count: the bit position is a word index plus an offset below 64 into a register pair (lo, hi) with
+// the following word already loaded (its latency hides behind the symbols in between), a code is looked up in the 32
+// bits at the offset (one funnel shift), a field is "bits below the total, shifted by the code length", and the only
+// tests on an entry are its sign (literal) and bit 15 (length / distance base).  Anything else -- a code longer than
+// the primary table, end of block, an invalid symbol, a distance beyond the history -- leaves the loop at the start
+// of that symbol and the careful decoder above deals with it (and produces the error, if it is one).
+// Returns kDone after an end-of-block code, kRunning otherwise.
 __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t* in)
 {
     const int lane = threadIdx.x & 31;
-    uint64_t buf = b.buf;
-    int cnt = b.cnt;
-    uint32_t nextw = b.nextw;
     const uint32_t nwords = b.nwords;
     const uint32_t* words = b.words;
-    uint8_t* p = o.p + o.pos;
     const uint64_t room64 = o.cap - o.pos, back64 = o.pos + o.hist;
     const uint32_t room = room64 > 0x7fffffffu ? 0x7fffffffu : (uint32_t)room64;
     const uint32_t back = back64 > 0x7fffffffu ? 0x7fffffffu : (uint32_t)back64;   // bytes behind p at entry
-    if (room < 260 || nwords < 3) return kRunning;
-    // a symbol may start while nextw <= w_lim (>= 72 valid bits ahead) and produced <= p_lim (>= 260 bytes of room);
-    // the bit position is nextw * 32 - cnt, kept in 32 bits: the loop returns before 2^28 bits go by
-    const uint32_t w_lim = min(nwords - 3, nextw + (1u << 23));
-    const uint32_t p_lim = room - 260;
-    const uint32_t entry32 = nextw * 32u - (uint32_t)cnt;
-    uint32_t produced = 0, mark32 = entry32;
-    bool rewind = false;
+    if (room < 260 || nwords < 6) return kRunning;
+    const uint32_t w_lim = nwords - 5, p_lim = room - 260;
+    const uint64_t pos0 = (uint64_t)b.nextw * 32u - (uint64_t)b.cnt;              // bit position from the word base
+    const uint32_t wi0 = (uint32_t)(pos0 >> 5), off0 = (uint32_t)pos0 & 31u;
+    if (wi0 > w_lim) return kRunning;
+    uint32_t wi = wi0, off = off0;
+    uint32_t lo = __ldg(words + wi), hi = __ldg(words + wi + 1), nxt = __ldg(words + wi + 2);
+    uint8_t* p = o.p + o.pos;
+    asm volatile("" : "+l"(p));                                 // one register pair; not re-derived from its parts at every use
+    __builtin_assume(__isGlobal(p));
+    const uint32_t* const lit = t->lit;
+    const uint32_t* const dtab = t->dist;
+    uint32_t produced = 0;
+    uint32_t end_wi, end_off;                                   // where the careful decoder takes over
     Stop result = kRunning;
     for (;;) {
-        if (nextw > w_lim || produced > p_lim) break;
-        mark32 = nextw * 32u - (uint32_t)cnt;
-        if (__builtin_expect(cnt <= 32, 0)) { buf |= (uint64_t)__ldg(words + nextw) << cnt; nextw++; cnt += 32; }
-        const uint32_t e = t->lit[(uint32_t)buf & (kLitSize - 1)];
-        const uint32_t len = e & 15u;
-        if (len == 0) { rewind = true; break; }
-        buf >>= len; cnt -= (int)len;
-        const uint32_t kind = (e >> 8) & 3u;
-        if (kind == kLit) {
-            // literals come in runs: try the next symbol too -- at least 18 bits are left, enough for any code
-            const uint32_t e2 = t->lit[(uint32_t)buf & (kLitSize - 1)];
-            const uint32_t len2 = e2 & 15u;
-            const bool lit2 = len2 != 0 && ((e2 >> 8) & 3u) == kLit;
-            if (lane == 0) {
-                p[produced] = (uint8_t)(e >> 16);
-                if (lit2) p[produced + 1] = (uint8_t)(e2 >> 16);
-            }
-            produced++;
-            if (lit2) { buf >>= len2; cnt -= (int)len2; produced++; }
+        if (off >= 32) {
+            off -= 32; lo = hi; hi = nxt; wi++;
+            nxt = __ldg(words + wi + 2);
+        }
+        end_wi = wi; end_off = off;
+        if (wi > w_lim || produced > p_lim) break;
+        const uint32_t win = __funnelshift_r(lo, hi, off);
+        const uint32_t e = lit[win & (kLitSize - 1)];
+        if ((int32_t)e < 0) {
+            // literals come in runs: try the next symbol too -- at least 17 bits of the window are left, enough for any
+            // code.  Every lane stores the (same) byte: cheaper than electing one.
+            const uint32_t e2 = lit[__funnelshift_r(win, 0u, e) & (kLitSize - 1)];
+            uint8_t* q = p + produced;
+            q[0] = (uint8_t)(e >> 16);
+            off += e & 31u; produced++;
+            if ((int32_t)e2 < 0) { q[1] = (uint8_t)(e2 >> 16); off += e2 & 31u; produced++; }
             continue;
         }
-        if (kind != kBase) {
-            if (kind == kEob) { result = kDone; break; }
-            rewind = true; break;
+        if (!(e & 0x8000u)) {
+            if (ent_kind(e) == kEob && ent_len(e) != 0) { end_off = off + ent_len(e); result = kDone; }
+            break;
         }
-        const uint32_t xl = (e >> 4) & 15u;
-        const uint32_t mlen = (e >> 16) + ((uint32_t)buf & ((1u << xl) - 1u));
-        buf >>= xl; cnt -= (int)xl;
-        if (cnt <= 32) { buf |= (uint64_t)__ldg(words + nextw) << cnt; nextw++; cnt += 32; }
-        const uint32_t de = t->dist[(uint32_t)buf & (kDistSize - 1)];
-        const uint32_t dl = de & 15u;
-        if (dl == 0 || ((de >> 8) & 3u) != kBase) { rewind = true; break; }
-        buf >>= dl; cnt -= (int)dl;
-        const uint32_t xd = (de >> 4) & 15u;
-        const uint32_t dist = (de >> 16) + ((uint32_t)buf & ((1u << xd) - 1u));
-        buf >>= xd; cnt -= (int)xd;
-        if (dist > back + produced) { rewind = true; break; }
-        uint8_t* d = p + produced;
+        const uint32_t tot = (e >> 5) & 31u;
+        const uint32_t mlen = (e >> 16) + __funnelshift_r(win & ((1u << tot) - 1u), 0u, e);   // bit 31 is clear: not a literal
+        off += tot;
+        if (off >= 32) { off -= 32; lo = hi; hi = nxt; wi++; nxt = __ldg(words + wi + 2); }
+        const uint32_t dwin = __funnelshift_r(lo, hi, off);
+        const uint32_t de = dtab[dwin & (kDistSize - 1)];
+        const uint32_t dtot = (de >> 5) & 31u;
+        const uint32_t dist = (de >> 16) + __funnelshift_r(dwin & ((1u << dtot) - 1u), 0u, de);
+        if (!(de & 0x8000u) || dist > back + produced) break;
+        off += dtot;
+        uint8_t* d = p + produced + lane;
         const uint8_t* s = d - dist;
+        produced += mlen;
         __syncwarp();
-        if (dist >= mlen) {
-            for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i];
+        if (dist >= 32u || dist >= mlen) {
+            // a pass of 32 bytes never reads what the same pass writes; later passes may read earlier ones
+            if ((uint32_t)lane < mlen) *d = *s;
+            if (mlen > 32) {
+#pragma unroll 1
+                for (uint32_t i0 = 32; i0 < mlen; i0 += 32) { __syncwarp(); if (i0 + lane < mlen) d[i0] = s[i0]; }
+            }
         } else {
-            for (uint32_t i = lane; i < mlen; i += 32) d[i] = s[i % dist];
+            const uint8_t* s0 = s - lane;
+#pragma unroll 1
+            for (uint32_t i = lane; i < mlen; i += 32) d[i - lane] = s0[i % dist];
         }
         __syncwarp();
-        produced += mlen;
     }
     o.pos += produced;
-    if (rewind) {
-        seek_bits(b, in, b.used + (uint32_t)(mark32 - entry32));
-    } else {
-        b.used += (uint32_t)(nextw * 32u - (uint32_t)cnt - entry32);
-        b.buf = buf; b.cnt = cnt; b.nextw = nextw;
-    }
+    seek_bits(b, in, b.used + ((uint64_t)(end_wi - wi0) * 32u + end_off - off0));
     return result;
 }
 
@@ -544,9 +553,9 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
                         drop(b, 1); sym = 0;
                     } else {
                         const uint32_t e = t->dist[peek(b, kClBits)];
-                        const int l = (int)(e & 15u);
+                        const int l = (int)ent_len(e);
                         if (!have(b, l)) { shortin = true; break; }
-                        drop(b, l); sym = e >> 16;
+                        drop(b, l); sym = ent_val(e);
                     }
                     if (sym < 16) {
                         if (lane == 0) t->lens[idx] = (uint8_t)sym;
