@@ -302,8 +302,10 @@ __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t*
     const uint64_t room64 = o.cap - o.pos, back64 = o.pos + o.hist;
     const uint32_t room = room64 > 0x7fffffffu ? 0x7fffffffu : (uint32_t)room64;
     const uint32_t back = back64 > 0x7fffffffu ? 0x7fffffffu : (uint32_t)back64;   // bytes behind p at entry
-    if (room < 260 || nwords < 6) return kRunning;
-    const uint32_t w_lim = nwords - 5, p_lim = room - 260;
+    if (room < 324 || nwords < 6) return kRunning;
+    // Limits are tested where the word index moves and after a match (not per literal): between two tests at most 32
+    // bits go by, i.e. at most 64 bytes of literals -- the 64 on top of the 260 bytes a symbol may need.
+    const uint32_t w_lim = nwords - 5, p_lim = room - 324;
     const uint64_t pos0 = (uint64_t)b.nextw * 32u - (uint64_t)b.cnt;              // bit position from the word base
     const uint32_t wi0 = (uint32_t)(pos0 >> 5), off0 = (uint32_t)pos0 & 31u;
     if (wi0 > w_lim) return kRunning;
@@ -316,14 +318,17 @@ __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t*
     const uint32_t* const dtab = t->dist;
     uint32_t produced = 0;
     uint32_t end_wi, end_off;                                   // where the careful decoder takes over
+    bool pend = false;                                          // this lane holds a byte of the last copy that is still to be stored
+    uint32_t pend_v = 0;
+    uint8_t* pend_d = p;
     Stop result = kRunning;
     for (;;) {
         if (off >= 32) {
             off -= 32; lo = hi; hi = nxt; wi++;
             nxt = __ldg(words + wi + 2);
+            asm volatile("");                                   // keep this a branch: it runs once per 32 bits, not per symbol
+            if (wi > w_lim || produced > p_lim) { end_wi = wi; end_off = off; break; }
         }
-        end_wi = wi; end_off = off;
-        if (wi > w_lim || produced > p_lim) break;
         const uint32_t win = __funnelshift_r(lo, hi, off);
         const uint32_t e = lit[win & (kLitSize - 1)];
         if ((int32_t)e < 0) {
@@ -336,6 +341,7 @@ __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t*
             if ((int32_t)e2 < 0) { q[1] = (uint8_t)(e2 >> 16); off += e2 & 31u; produced++; }
             continue;
         }
+        end_wi = wi; end_off = off;                             // start of this symbol
         if (!(e & 0x8000u)) {
             if (ent_kind(e) == kEob && ent_len(e) != 0) { end_off = off + ent_len(e); result = kDone; }
             break;
@@ -353,21 +359,32 @@ __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t*
         uint8_t* d = p + produced + lane;
         const uint8_t* s = d - dist;
         produced += mlen;
+        // The bytes of a short copy are loaded now and stored when the next match arrives (or the loop ends): the trip
+        // to L2 -- the output was written moments ago and is not in L1 -- overlaps the decoding of the symbols in between
+        // instead of stalling the warp at the store.  Literal stores in between go to other addresses.
+        if (pend) *pend_d = (uint8_t)pend_v;
         __syncwarp();
-        if (dist >= 32u || dist >= mlen) {
-            // a pass of 32 bytes never reads what the same pass writes; later passes may read earlier ones
-            if ((uint32_t)lane < mlen) *d = *s;
-            if (mlen > 32) {
-#pragma unroll 1
-                for (uint32_t i0 = 32; i0 < mlen; i0 += 32) { __syncwarp(); if (i0 + lane < mlen) d[i0] = s[i0]; }
-            }
+        if (mlen <= 32u && dist >= mlen) {
+            pend = (uint32_t)lane < mlen;
+            if (pend) pend_v = *s;
+            pend_d = d;
         } else {
-            const uint8_t* s0 = s - lane;
+            pend = false;
+            if (dist >= 32u || dist >= mlen) {
+                // a pass of 32 bytes never reads what the same pass writes; later passes may read earlier ones
 #pragma unroll 1
-            for (uint32_t i = lane; i < mlen; i += 32) d[i - lane] = s0[i % dist];
+                for (uint32_t i0 = 0; i0 < mlen; i0 += 32) { if (i0 + lane < mlen) d[i0] = s[i0]; __syncwarp(); }
+            } else {
+                const uint8_t* s0 = s - lane;
+#pragma unroll 1
+                for (uint32_t i = lane; i < mlen; i += 32) d[i - lane] = s0[i % dist];
+                __syncwarp();
+            }
         }
-        __syncwarp();
+        if (produced > p_lim) { end_wi = wi; end_off = off; break; }
     }
+    if (pend) *pend_d = (uint8_t)pend_v;
+    __syncwarp();
     o.pos += produced;
     seek_bits(b, in, b.used + ((uint64_t)(end_wi - wi0) * 32u + end_off - off0));
     return result;
