@@ -93,13 +93,29 @@ int zb200_deflate_batch(const void *src, const uint64_t *src_off, size_t n,
                         int level, int wrap, void *stream);
 
 /* ---- ZIP32 archive of n files compressed in one batch (qcsrc/zip.c:902-1128 member by member) ----
- * names[i] is the member name, file i is src[src_off[i] .. src_off[i+1]) (host memory).  The archive is written
- * to dst (host memory); *dst_len: in = capacity, out = archive size (the size needed when Z_BUF_ERROR is
+ * names[i] is the member name, file i is src[src_off[i] .. src_off[i+1]) (host or device memory).  The archive is
+ * written to dst (host memory); *dst_len: in = capacity, out = archive size (the size needed when Z_BUF_ERROR is
  * returned).  dos_datetime = MS-DOS time in the low and date in the high 16 bits, as in zip.c's dosDate.
  * Z_STREAM_ERROR beyond ZIP32 (65535 members, sizes and offsets below 4 GiB). */
 size_t zb200_zip_bound(const char *const *names, const uint64_t *src_off, size_t n);
 int zb200_zip_build(const char *const *names, const void *src, const uint64_t *src_off, size_t n,
                     int level, uint32_t dos_datetime, void *dst, size_t *dst_len);
+
+/* The two halves of zb200_zip_build, for archives whose members are compressed on several GPUs (BASELINE
+ * config 5): a *segment* is the run of [local header | name | raw deflate data] records of some members, laid out
+ * on the device and delivered to dst (host or device memory) in one piece; segments concatenate.  members[i]
+ * receives what the central directory needs; local_off is relative to the segment -- add the segment's position in
+ * the archive before calling zb200_zip_directory, which writes the central directory and the end record for ALL
+ * members of the archive at dst (host memory; the directory starts at byte cd_offset of the archive). */
+typedef struct zb200_zip_member {
+    uint64_t local_off;              /* position of the member's local header */
+    uint64_t comp_len, raw_len;
+    uint32_t crc32, reserved;
+} zb200_zip_member;
+int zb200_zip_segment(const char *const *names, const void *src, const uint64_t *src_off, size_t n,
+                      int level, uint32_t dos_datetime, void *dst, size_t *dst_len, zb200_zip_member *members);
+int zb200_zip_directory(const char *const *names, const zb200_zip_member *members, size_t n,
+                        uint32_t dos_datetime, uint64_t cd_offset, void *dst, size_t *dst_len);
 
 /* ---- inflate: n independent streams (qcsrc/uncompr.c:26 uncompress, batched) ----
  * Stream i occupies src[src_off[i] .. src_off[i+1]) and is decoded into

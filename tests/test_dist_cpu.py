@@ -148,3 +148,77 @@ def test_sharded_checksum_and_inflate(world):
     for p in ps:
         p.join(60)
     assert all(m == "ok" for _, m in res), res
+
+
+def _standin_segment(names, datas):
+    """Test-only stand-in for zb200_zip_segment: system zlib for the members, the local headers of zip.c:969-1032."""
+    import struct
+    from zlib_b200.binding import DOS_DATETIME
+    seg, metas = bytearray(), []
+    for nm, d in zip(names, datas):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        z = co.compress(d) + co.flush()
+        metas.append((len(seg), len(z), len(d), zlib.crc32(d)))
+        seg += struct.pack("<IHHHIIIIHH", 0x04034b50, 20, 0, 8, DOS_DATETIME, zlib.crc32(d), len(z), len(d), len(nm.encode()), 0)
+        seg += nm.encode() + z
+    return bytes(seg), metas
+
+
+def _worker_c5(rank, world, port, q, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import io
+        import random
+        import zipfile
+        import zhelpers
+        from zlib_b200 import dist as zd, load
+        lib = load()
+        rng = random.Random(11)
+        sizes = [0, 1, 4096, 70000, 300000] + [int(4096 * 2 ** rng.uniform(0, 7)) for _ in range(40)]
+        names = [f"d{i % 3}/f{i:05d}.bin" for i in range(len(sizes))]
+        datas = [zhelpers.corpus(i % 5, n, 40 + i) for i, n in enumerate(sizes)]
+        shares = zd.assign_files(sizes, world)
+        assert sorted(i for sh in shares for i in sh) == list(range(len(sizes)))
+        loads = [sum(sizes[i] for i in sh) for sh in shares]
+        assert max(loads) - min(loads) <= max(sizes)                # LPT bound
+        arc = zd.zip_sharded(lib, names, datas, 6, segment_fn=_standin_segment)   # the directory is the library's own (host C)
+        if rank == 0:
+            zf = zipfile.ZipFile(io.BytesIO(arc))
+            assert zf.testzip() is None and sorted(zf.namelist()) == sorted(names)
+            for nm, d in zip(names, datas):
+                assert zf.read(nm) == d
+            with open(os.path.join(outdir, "sharded.zip"), "wb") as f:
+                f.write(arc)
+        else:
+            assert arc is None
+        q.put((rank, "ok"))
+    except Exception:          # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_zip_archive(world, tmp_path):
+    """BASELINE config 5 host logic: files dealt to the ranks, segments gathered, central directory by the library;
+    the archive is read back by Python's zipfile and, when built, by the reference's miniunz."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_c5, args=(r, world, port, q, str(tmp_path))) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert all(m == "ok" for _, m in res), res
+    miniunz = os.path.join(ROOT, "oracle", "_ref", "miniunz")
+    if os.path.exists(miniunz):
+        import subprocess
+        out = tmp_path / "x"
+        out.mkdir()
+        r = subprocess.run([miniunz, "-o", str(tmp_path / "sharded.zip")], cwd=out, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert sum(len(fs) for _, _, fs in os.walk(out)) == 45

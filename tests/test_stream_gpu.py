@@ -183,6 +183,34 @@ def test_zip_archive_from_one_gpu_batch(gpu_lib, tmp_path):
         assert (out / name).read_bytes() == data, name
 
 
+def test_zip_segments_concatenate(gpu_lib, tmp_path):
+    """The multi-GPU form of config 5 on one GPU: two segments (zb200_zip_segment, laid out on the device) concatenated
+    and closed by zb200_zip_directory are one archive that the reference's miniunz extracts bit-exact; members of
+    several MiB exercise the piecewise copy kernel at every relative misalignment."""
+    import zipfile
+    rng = random.Random(32)
+    names = [f"s/{'x' * (i % 7)}f{i:04d}.dat" for i in range(60)]
+    datas = [zhelpers.corpus(rng.choice([0, 1, 3, 4]), int(1000 * 2 ** rng.uniform(0, 11)) + i % 5, 700 + i) for i in range(60)]
+    datas[7] = b""
+    datas[8] = gpu_lib.synth((3 << 20) + 3, kind=1, seed=4).tobytes()
+    datas[40] = gpu_lib.synth((2 << 20) + 1, kind=2, seed=5).tobytes()     # noise: stored blocks
+    seg_a, meta_a = gpu_lib.zip_segment(names[:25], datas[:25], level=1)
+    seg_b, meta_b = gpu_lib.zip_segment(names[25:], datas[25:], level=6)
+    metas = meta_a + [(m[0] + len(seg_a), m[1], m[2], m[3]) for m in meta_b]
+    assert [m[3] for m in metas] == [zlib.crc32(d) for d in datas]
+    arc = seg_a + seg_b + gpu_lib.zip_directory(names, metas, len(seg_a) + len(seg_b))
+    path = tmp_path / "two_segments.zip"
+    path.write_bytes(arc)
+    zf = zipfile.ZipFile(path)
+    assert zf.testzip() is None and zf.namelist() == names
+    out = tmp_path / "x"
+    out.mkdir()
+    p = subprocess.run([_need(os.path.join(REFDIR, "miniunz")), "-o", str(path)], cwd=out, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    for name, data in zip(names, datas):
+        assert (out / name).read_bytes() == data, name
+
+
 def test_strategies(gpu_lib, oracle):
     """deflateInit2 strategies (deflate.c:1485-1494, 1594-1612, trees.c:986): every one decodes; Z_RLE only emits
     distance-1 matches, Z_HUFFMAN_ONLY none, Z_FIXED only fixed blocks; sizes order like the reference's."""

@@ -32,6 +32,21 @@ zs = [zlib.compress(data[i * sz:(i + 1) * sz].tobytes(), 6) for i in range(512)]
 idx, outs, st, lens = zd.inflate_sharded(L, zs, [sz] * len(zs))
 assert st == [0] * len(zs) and lens == [sz] * len(zs)
 assert all(outs[k] == data[i * sz:(i + 1) * sz].tobytes() for k, i in enumerate(idx))
+# config 5: files dealt to the ranks, one archive on the root
+import io, random, zipfile
+rng = random.Random(5)
+fsz = [int(4096 * 2 ** rng.uniform(0, 10)) for _ in range(300)]
+foff = [0]
+for z in fsz:
+    foff.append(foff[-1] + z)
+blob = L.synth(foff[-1], kind=1, seed=78)
+names = [f"f{i:05d}.bin" for i in range(len(fsz))]
+datas = [blob[foff[i]:foff[i + 1]].tobytes() for i in range(len(fsz))]
+arc = zd.zip_sharded(L, names, datas, 1)
+if rank == 0:
+    zf = zipfile.ZipFile(io.BytesIO(arc))
+    assert zf.testzip() is None and sorted(zf.namelist()) == names
+    assert all(zf.read(nm) == d for nm, d in zip(names, datas))
 dist.barrier()
 if rank == 0:
     print(f"dist_check ok on {world} GPUs: crc {crc:08x}, stream {plan.total} bytes, {len(zs)} streams inflated")

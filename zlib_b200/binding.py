@@ -18,6 +18,7 @@ Z_ERRNO, Z_STREAM_ERROR, Z_DATA_ERROR, Z_MEM_ERROR, Z_BUF_ERROR, Z_VERSION_ERROR
 Z_NO_FLUSH, Z_PARTIAL_FLUSH, Z_SYNC_FLUSH, Z_FULL_FLUSH, Z_FINISH, Z_BLOCK = 0, 1, 2, 3, 4, 5
 Z_DEFLATED = 8
 WRAP_RAW, WRAP_ZLIB, WRAP_GZIP = 0, 1, 2
+DOS_DATETIME = 46 << 25 | 10 << 21 | 18 << 16            # 2026-10-18 00:00:00 in zip.c's dosDate layout
 ZB200_DEFLATE_NOT_LAST, ZB200_DEFLATE_NO_HEADER, ZB200_DEFLATE_NO_TRAILER = 1, 2, 4
 ZLIB_VERSION = b"1.2.3"
 
@@ -114,6 +115,8 @@ class Lib:
             "zb200_deflate_batch": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
             "zb200_zip_bound": (sz, [vp, vp, sz]),
             "zb200_zip_build": (C.c_int, [vp, vp, vp, sz, C.c_int, C.c_uint32, vp, C.POINTER(sz)]),
+            "zb200_zip_segment": (C.c_int, [vp, vp, vp, sz, C.c_int, C.c_uint32, vp, C.POINTER(sz), vp]),
+            "zb200_zip_directory": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint64, vp, C.POINTER(sz)]),
             "zb200_inflate_batch": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
             "zb200_inflate_batch_dev": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
             "zb200_kernel_launches": (C.c_uint64, []),
@@ -241,7 +244,7 @@ class Lib:
         outs = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + int(dst_len[i])]) if status[i] == 0 else b"" for i in range(n)]
         return outs, [int(x) for x in status[:n]], [int(x) for x in crc[:n]], [int(x) for x in adl[:n]]
 
-    def zip_build(self, files, level: int = 6, dos_datetime: int = (46 << 25 | 10 << 21 | 18 << 16)):
+    def zip_build(self, files, level: int = 6, dos_datetime: int = DOS_DATETIME):
         """zb200_zip_build over {name: bytes} -> archive bytes."""
         import numpy as np
         names = list(files)
@@ -255,6 +258,38 @@ class Lib:
         ol = C.c_size_t(cap)
         self._check(self.dll.zb200_zip_build(arr, src.ctypes.data, off.ctypes.data, n, level, dos_datetime, out, C.byref(ol)),
                     "zb200_zip_build")
+        return out.raw[:ol.value]
+
+    def zip_segment(self, names, datas, level: int = 6, dos_datetime: int = DOS_DATETIME):
+        """zb200_zip_segment over parallel lists of names and bytes -> (segment bytes, [(local_off, comp_len, raw_len, crc32)])."""
+        import numpy as np
+        n = len(names)
+        arr = (C.c_char_p * max(n, 1))(*[nm.encode() for nm in names])
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(d) for d in datas], dtype=np.uint64)
+        src = np.frombuffer(b"".join(datas) + b"\0" * 8, dtype=np.uint8)
+        cap = self.dll.zb200_zip_bound(arr, off.ctypes.data, n)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        members = np.zeros((max(n, 1), 4), dtype=np.uint64)     # zb200_zip_member: 3 x u64, then {u32 crc32, u32 reserved}
+        ol = C.c_size_t(cap)
+        self._check(self.dll.zb200_zip_segment(arr, src.ctypes.data, off.ctypes.data, n, level, dos_datetime, out.ctypes.data,
+                                               C.byref(ol), members.ctypes.data), "zb200_zip_segment")
+        metas = [(int(m[0]), int(m[1]), int(m[2]), int(m[3]) & 0xFFFFFFFF) for m in members[:n]]
+        return out[:ol.value].tobytes(), metas
+
+    def zip_directory(self, names, metas, cd_offset: int, dos_datetime: int = DOS_DATETIME):
+        """zb200_zip_directory: central directory + end record for members given as (local_off, comp_len, raw_len, crc32)."""
+        import numpy as np
+        n = len(names)
+        arr = (C.c_char_p * max(n, 1))(*[nm.encode() for nm in names])
+        members = np.zeros((max(n, 1), 4), dtype=np.uint64)
+        for i, m in enumerate(metas):
+            members[i] = (m[0], m[1], m[2], m[3])
+        cap = 22 + sum(46 + len(nm.encode()) for nm in names)
+        out = C.create_string_buffer(cap)
+        ol = C.c_size_t(cap)
+        self._check(self.dll.zb200_zip_directory(arr, members.ctypes.data, n, dos_datetime, cd_offset, out, C.byref(ol)),
+                    "zb200_zip_directory")
         return out.raw[:ol.value]
 
     def inflate_batch(self, streams, caps, wrap: int = WRAP_ZLIB, stream=None):

@@ -216,3 +216,71 @@ def inflate_sharded(lib, streams: Sequence[bytes], caps: Sequence[int], wrap: in
     dist.all_reduce(local, op=dist.ReduceOp.MAX, group=group)     # every stream has exactly one owner; the rest hold -100
     res = local.cpu().tolist()
     return mine, outs, [int(r[0]) for r in res], [int(r[1]) for r in res]
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 5: one ZIP archive whose members are compressed on all ranks
+# ---------------------------------------------------------------------------------------------
+def assign_files(sizes: Sequence[int], world: int) -> List[List[int]]:
+    """Longest-processing-time-first: files by decreasing size, each to the rank with the least bytes so far
+    (ties to the lowest rank).  Every rank's list is returned in increasing index order."""
+    load = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in sorted(range(len(sizes)), key=lambda k: (-sizes[k], k)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        out[r].append(i)
+        load[r] += sizes[i]
+    return [sorted(x) for x in out]
+
+
+def zip_sharded(lib, names: Sequence[str], datas: Sequence[bytes], level: int = 6, group=None, root: int = 0,
+                segment_fn: Optional[Callable] = None, directory_fn: Optional[Callable] = None):
+    """One ZIP32 archive from files compressed on every rank.
+
+    The unit is the file (independent raw-deflate streams): files are dealt to the ranks by size, every rank turns
+    its share into a *segment* -- [local header | name | data] records laid out on its GPU by zb200_zip_segment --
+    and the archive is the segments in rank order followed by the central directory.  Exchange: one all-gather of
+    the per-member records {file index, local offset, compressed size, raw size, crc32} (padded to the largest share)
+    and the variable-length gather of the segments to the root, which appends the directory (zb200_zip_directory).
+    Returns the archive (bytes) on the root, None elsewhere.
+    """
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    shares = assign_files([len(d) for d in datas], world)
+    mine = shares[rank]
+    seg_fn = segment_fn or (lambda nm, ds: lib.zip_segment(nm, ds, level))
+    dir_fn = directory_fn or (lambda nm, metas, cd_off: lib.zip_directory(nm, metas, cd_off))
+    seg, metas = seg_fn([names[i] for i in mine], [datas[i] for i in mine]) if mine else (b"", [])
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    width = max(len(x) for x in shares)
+    rec = torch.full((width + 1, 5), -1, dtype=torch.int64)
+    rec[0, 0] = len(seg)
+    for k, (i, m) in enumerate(zip(mine, metas)):
+        rec[k + 1] = torch.tensor([i, m[0], m[1], m[2], m[3]], dtype=torch.int64)
+    rec = rec.to(dev).view(-1)
+    allrec = torch.empty(world * (width + 1) * 5, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allrec, rec, group=group)
+    allrec = allrec.view(world, width + 1, 5).cpu()
+    seg_len = [int(allrec[r, 0, 0]) for r in range(world)]
+    seg_t = torch.frombuffer(bytearray(seg), dtype=torch.uint8).to(dev) if seg else torch.empty(0, dtype=torch.uint8, device=dev)
+    if rank != root:
+        if len(seg):
+            dist.send(seg_t, dst=root, group=group)
+        return None
+    parts, base, order, glob = [], 0, [], []
+    for r in range(world):
+        if r == root:
+            parts.append(seg)
+        elif seg_len[r]:
+            buf = torch.empty(seg_len[r], dtype=torch.uint8, device=dev)
+            dist.recv(buf, src=r, group=group)
+            parts.append(bytes(buf.cpu().numpy()))
+        else:
+            parts.append(b"")
+        for k in range(len(shares[r])):
+            i, lo, cl, rl, crc = (int(v) for v in allrec[r, k + 1])
+            order.append(names[i])
+            glob.append((base + lo, cl, rl, crc))
+        base += seg_len[r]
+    return b"".join(parts) + dir_fn(order, glob, base)
