@@ -332,6 +332,25 @@ k_checksum_batch(const uint8_t* __restrict__ base, const uint64_t* __restrict__ 
         const uint64_t stop = min(end, p + 4096);             // u32 bound for the deferred modulo
         uint32_t aa = 0, bb = 0;
         const uint32_t n = (uint32_t)(stop - p);
+        // bytes up to a 16-byte boundary, then 16 bytes per load (a thread's stripe is contiguous, so byte loads would
+        // cost a cache wavefront per byte and lane), then the ragged end
+        for (; p < stop && ((uintptr_t)(buf + p) & 15u); ++p) {
+            const uint32_t v = buf[p];
+            c = s_tab[(c ^ v) & 0xffu] ^ (c >> 8);
+            aa += v; bb += aa;
+        }
+        for (; p + 16 <= stop; p += 16) {
+            const uint4 q = *reinterpret_cast<const uint4*>(buf + p);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                c ^= w[k];
+#pragma unroll
+                for (int j = 0; j < 4; j++) c = s_tab[c & 0xffu] ^ (c >> 8);
+                bb += 4u * aa + __dp4a(w[k], 0x01020304u, 0u);  // byte 0 of the word comes first: weight 4
+                aa += __dp4a(w[k], 0x01010101u, 0u);
+            }
+        }
         for (; p < stop; ++p) {
             const uint32_t v = buf[p];
             c = s_tab[(c ^ v) & 0xffu] ^ (c >> 8);
