@@ -117,6 +117,7 @@ int checksum_setup()
 // from a 64 KiB-aligned shared address, so bank = l (a warp's 32 lookups never conflict) and the address of a lookup
 // is ONE byte permute: byte 1 of the address is the index byte of the register, bytes 0, 2, 3 come from a per-lane
 // constant (PRMT), instead of extract + scale + add.  The kernel is instruction bound, so this is what moves it.
+constexpr uint32_t kPrefetchAhead = 16;                          // iterations (512 B each) between an L2 prefetch and its use
 constexpr uint32_t kTabImage = 2 * 65536;                       // bytes of the table image
 constexpr size_t kMainSmem = kTabImage + 65536;                 // + slack to align the image to 64 KiB
 
@@ -169,6 +170,9 @@ k_checksum_main(const uint8_t* __restrict__ base, uint64_t n_units, uint32_t ite
         uint32_t j = 0;
         // two loads in flight per lane
         for (; j + 2 <= iters; j += 2) {
+            // two iterations use 1 KiB per warp; ask L2 for the 1 KiB that is kPrefetchAhead iterations away (registers cap
+            // the loads in flight at two per lane, which alone does not cover the HBM latency-bandwidth product)
+            if (lane < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p - lane) + (size_t)min(j + kPrefetchAhead, iters - 2) * kStride + (lane * 128) % 1024));
             uint4 w0 = ld_stream(p + (size_t)j * 32);
             uint4 w1 = ld_stream(p + (size_t)(j + 1) * 32);
             c0 = stride_step(c0, k0, k1, k2, k3) ^ w0.x; c1 = stride_step(c1, k0, k1, k2, k3) ^ w0.y;
