@@ -1,2 +1,2 @@
-python -m pytest tests/test_checksum_gpu.py -m gpu -x -q 2>&1 | tail -2
-python tools/probe_checksum.py 2>&1 | tail -5
+python -m pytest tests/test_inflate_gpu.py tests/test_stream_gpu.py -m gpu -x -q 2>&1 | tail -2
+python tools/probe_codec.py 1024 2>&1 | tail -1
