@@ -375,6 +375,31 @@ def main():
         ok = int(d_st.abs().sum()) == 0 and bool((d_len == sz).all())
         extra["inflate_batch"] = {"GBps": round(ns * sz / msi / 1e6, 3), "streams": ns, "stream_bytes": sz, "ms": round(msi, 2),
                                   "source": src_kind, "all_ok": ok, "compressed_fraction": round(int(src_off[-1]) / (ns * sz), 4)}
+        # the full shape of BASELINE config 3: 100 000 streams of 64 KiB (the 2048 distinct ones repeated), 6.1 GiB out
+        ns3 = 100000
+        zs3 = (zs[:distinct] * ((ns3 + distinct - 1) // distinct))[:ns3]
+        so3 = np.zeros(ns3 + 1, dtype=np.int64)
+        so3[1:] = np.cumsum([len(z) for z in zs3])
+        d_z3 = torch.from_numpy(np.frombuffer(b"".join(zs3) + b"\0" * 8, dtype=np.uint8).copy()).to(dev)
+        d_so3 = torch.from_numpy(so3).to(dev)
+        d_do3 = torch.arange(ns3 + 1, dtype=torch.int64, device=dev) * sz
+        d_out3 = torch.empty(ns3 * sz, dtype=torch.uint8, device=dev)
+        d_len3 = torch.zeros(ns3, dtype=torch.int64, device=dev)
+        d_st3 = torch.zeros(ns3, dtype=torch.int32, device=dev)
+        msi3, _ = timed(lambda: lib.inflate_batch_dev(d_z3.data_ptr(), d_so3.data_ptr(), ns3, d_out3.data_ptr(), d_do3.data_ptr(),
+                                                      d_len3.data_ptr(), d_st3.data_ptr(), zb.WRAP_ZLIB, s), 3, 2)
+        ok3 = int(d_st3.abs().sum()) == 0 and bool((d_len3 == sz).all()) and bool(torch.equal(d_out3[:distinct * sz], d_src[:distinct * sz]))
+        extra["inflate_batch_config3"] = {"GBps": round(ns3 * sz / msi3 / 1e6, 3), "streams": ns3, "stream_bytes": sz, "ms": round(msi3, 2),
+                                          "all_ok": ok3}
+        del d_z3, d_out3
+        # checksum at the per-GPU size of BASELINE config 4 scaled to one call's uInt limit: 4 GiB - 64 KiB
+        n4 = (4 << 30) - 65536
+        d_big = torch.empty(n4, dtype=torch.uint8, device=dev)
+        d_big.view(torch.int64).random_()
+        msc4, _ = timed(lambda: lib.checksum_dev(d_big.data_ptr(), n4, out2.data_ptr(), s), 5, 2)
+        extra["crc32_adler32_fused_4GiB"] = {"GBps": round(n4 / msc4 / 1e6, 1), "ms": round(msc4, 4),
+                                             "frac_of_hbm_peak": round(n4 / msc4 / 1e6 / peaks["hbm_gbs"], 4)}
+        del d_big
         # ZIP archive (config 5 shape): files of log-uniform size 4 KiB .. 16 MiB cut from the same corpus, one
         # zb200_zip_build call on pinned host buffers (H2D + batch deflate + device-side assembly + one D2H)
         import random as _r

@@ -1,2 +1,1 @@
-python -m pytest tests/test_inflate_gpu.py tests/test_stream_gpu.py -m gpu -x -q 2>&1 | tail -2
-python tools/probe_codec.py 1024 2>&1 | tail -1
+python bench.py > gpurun_out/bench11.json 2> gpurun_out/bench11.log; tail -3 gpurun_out/bench11.log | cut -c1-1500
