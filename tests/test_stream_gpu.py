@@ -157,6 +157,64 @@ def test_gzip_stream_decoding(gpu_lib):
     assert rc == zb.Z_STREAM_END and out == data
 
 
+def test_inflate_get_header(gpu_lib):
+    """inflateGetHeader (inflate.c:1211-1227, header walk :634-759): the gzip header fields reach the caller's gz_header
+    while the stream is fed three bytes at a time; buffers clip; a zlib stream under windowBits + 32 reports done = -1."""
+    import ctypes as C
+    import struct
+    data = zhelpers.corpus(1, 50000, 77)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = co.compress(data) + co.flush()
+    extra, name, comment = b"EX\x04\x00abcd", b"file name.txt", b"a comment that is longer than the buffer"
+    hdr = bytes([31, 139, 8, 1 | 2 | 4 | 8 | 16]) + struct.pack("<IBB", 1234567890, 2, 3)
+    hdr += struct.pack("<H", len(extra)) + extra + name + b"\0" + comment + b"\0"
+    hdr += struct.pack("<H", zlib.crc32(hdr) & 0xffff)
+    member = hdr + body + struct.pack("<II", zlib.crc32(data), len(data))
+    assert zlib.decompress(member, 31) == data
+    for wbits in (31, 47):
+        strm = zb.z_stream()
+        assert gpu_lib.dll.inflateInit2_(C.byref(strm), wbits, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+        ebuf, nbuf, cbuf = C.create_string_buffer(64), C.create_string_buffer(64), C.create_string_buffer(10)
+        head = zb.gz_header()
+        head.extra, head.extra_max = C.addressof(ebuf), 64
+        head.name, head.name_max = C.addressof(nbuf), 64
+        head.comment, head.comm_max = C.addressof(cbuf), 10
+        assert gpu_lib.dll.inflateGetHeader(C.byref(strm), C.byref(head)) == zb.Z_OK and head.done == 0
+        src = C.create_string_buffer(member, len(member))
+        out = C.create_string_buffer(len(data) + 16)
+        strm.next_out, strm.avail_out = C.addressof(out), len(data) + 16
+        pos, rc, done_at = 0, zb.Z_OK, None
+        while rc in (zb.Z_OK, zb.Z_BUF_ERROR) and pos < len(member):
+            n = 3 if pos < len(hdr) + 6 else len(member) - pos
+            strm.next_in, strm.avail_in = C.addressof(src) + pos, n
+            rc = gpu_lib.dll.inflate(C.byref(strm), zb.Z_NO_FLUSH)
+            pos += n - strm.avail_in
+            if head.done == 1 and done_at is None:
+                done_at = pos
+        assert rc == zb.Z_STREAM_END and out.raw[:len(data)] == data
+        assert done_at is not None and len(hdr) <= done_at <= len(hdr) + 3
+        assert (head.text, head.time, head.xflags, head.os, head.hcrc, head.done) == (1, 1234567890, 2, 3, 1, 1)
+        assert head.extra_len == len(extra) and ebuf.raw[:len(extra)] == extra
+        assert nbuf.raw[:len(name) + 1] == name + b"\0"
+        assert cbuf.raw == comment[:10]                           # clipped to comm_max, no terminator
+        gpu_lib.dll.inflateEnd(C.byref(strm))
+    # a zlib stream where gzip was allowed: done = -1; plain zlib decoding refuses the call
+    strm = zb.z_stream()
+    assert gpu_lib.dll.inflateInit2_(C.byref(strm), 47, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+    head = zb.gz_header()
+    assert gpu_lib.dll.inflateGetHeader(C.byref(strm), C.byref(head)) == zb.Z_OK
+    z = zlib.compress(data)
+    src = C.create_string_buffer(z, len(z))
+    out = C.create_string_buffer(len(data))
+    strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(z), C.addressof(out), len(data)
+    assert gpu_lib.dll.inflate(C.byref(strm), zb.Z_FINISH) == zb.Z_STREAM_END and head.done == -1
+    gpu_lib.dll.inflateEnd(C.byref(strm))
+    strm = zb.z_stream()
+    assert gpu_lib.dll.inflateInit2_(C.byref(strm), 15, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+    assert gpu_lib.dll.inflateGetHeader(C.byref(strm), C.byref(head)) == zb.Z_STREAM_ERROR
+    gpu_lib.dll.inflateEnd(C.byref(strm))
+
+
 def test_zip_archive_from_one_gpu_batch(gpu_lib, tmp_path):
     """BASELINE config 5 in small: many files compressed by ONE zb200_deflate_batch call and laid out as a ZIP32
     archive by zb200_zip_build; the reference's miniunz extracts every member bit-exact, Python's zipfile agrees."""

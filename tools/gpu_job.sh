@@ -1,1 +1,1 @@
-python bench.py > gpurun_out/bench11.json 2> gpurun_out/bench11.log; tail -3 gpurun_out/bench11.log | cut -c1-1500
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4

@@ -64,6 +64,14 @@ def _stream(stream) -> C.c_void_p:
     return C.c_void_p(stream.cuda_stream)                         # torch.cuda.Stream
 
 
+class gz_header(C.Structure):
+    """h/zlib.h:105-121."""
+    _fields_ = [("text", C.c_int), ("time", C.c_ulong), ("xflags", C.c_int), ("os", C.c_int),
+                ("extra", C.c_void_p), ("extra_len", C.c_uint), ("extra_max", C.c_uint),
+                ("name", C.c_void_p), ("name_max", C.c_uint), ("comment", C.c_void_p), ("comm_max", C.c_uint),
+                ("hcrc", C.c_int), ("done", C.c_int)]
+
+
 class Lib:
     """One loaded copy of libzb200.so."""
 

@@ -26,6 +26,7 @@
 
 enum { KIND_DEFLATE = 0x5a44, KIND_INFLATE = 0x5a49 };
 enum { ST_INIT = 1, ST_BUSY = 2, ST_FINISH = 3 };
+enum { GZ_FIXED = 0, GZ_XLEN, GZ_EXTRA, GZ_NAME, GZ_COMMENT, GZ_HCRC, GZ_DONE };   /* gzip header capture, see gz_capture */
 
 struct internal_state {
     int kind;
@@ -43,6 +44,10 @@ struct internal_state {
     zb200i_inflater *inf;
     int inf_wrap, inf_done, inf_bad;
     uLong inf_dict_id;
+    /* gzip header capture for inflateGetHeader (inflate.c:634-759): a host-side shadow of the bytes the device skips */
+    gz_headerp gz_head;
+    int gz_st; unsigned gz_have, gz_flags, gz_xlen;
+    unsigned char gz_fix[10];
 };
 typedef struct internal_state zs;
 
@@ -460,6 +465,7 @@ ZAPI int inflateReset(z_streamp strm)                           /* inflate.c:103
     strm->msg = Z_NULL;
     strm->adler = 1;
     s->inf_done = s->inf_bad = 0;
+    s->gz_head = Z_NULL; s->gz_st = GZ_FIXED; s->gz_have = 0;
     return zb200i_inflate_reset(s->inf, s->inf_wrap) == 0 ? Z_OK : Z_STREAM_ERROR;
 }
 
@@ -471,6 +477,76 @@ ZAPI int inflateEnd(z_streamp strm)                             /* inflate.c:115
     strm->zfree(strm->opaque, strm->state);
     strm->state = Z_NULL;
     return Z_OK;
+}
+
+/* Walks the gzip header as its bytes are consumed and fills the caller's gz_header the way inflate.c:634-759 does:
+ * fixed fields, then FEXTRA / FNAME / FCOMMENT clipped to the caller's buffers, then FHCRC; done = 1 at the end of the
+ * header, -1 if the stream turns out not to be gzip (windowBits + 32).  The device decoder validates the same bytes. */
+static void gz_capture(zs *s, const unsigned char *p, size_t n)
+{
+    gz_headerp h = s->gz_head;
+    while (n && s->gz_st != GZ_DONE) {
+        const unsigned c = *p++;
+        n--;
+        switch (s->gz_st) {
+        case GZ_FIXED:
+            s->gz_fix[s->gz_have++] = (unsigned char)c;
+            if (s->gz_have == 2 && (s->gz_fix[0] != 0x1f || s->gz_fix[1] != 0x8b)) {      /* a zlib stream */
+                if (h != Z_NULL) h->done = -1;
+                s->gz_st = GZ_DONE;
+                break;
+            }
+            if (s->gz_have < 10) break;
+            s->gz_flags = s->gz_fix[3];
+            if (h != Z_NULL) {
+                h->text = (int)(s->gz_flags & 1);
+                h->time = (uLong)s->gz_fix[4] | ((uLong)s->gz_fix[5] << 8) | ((uLong)s->gz_fix[6] << 16) | ((uLong)s->gz_fix[7] << 24);
+                h->xflags = s->gz_fix[8]; h->os = s->gz_fix[9];
+                if (!(s->gz_flags & 4)) h->extra = Z_NULL;
+                if (!(s->gz_flags & 8)) h->name = Z_NULL;
+                if (!(s->gz_flags & 16)) h->comment = Z_NULL;
+            }
+            s->gz_have = 0;
+            s->gz_st = (s->gz_flags & 4) ? GZ_XLEN : (s->gz_flags & 8) ? GZ_NAME : (s->gz_flags & 16) ? GZ_COMMENT : (s->gz_flags & 2) ? GZ_HCRC : GZ_DONE;
+            break;
+        case GZ_XLEN:
+            s->gz_xlen = s->gz_have ? (s->gz_xlen | (c << 8)) : c;
+            if (++s->gz_have < 2) break;
+            if (h != Z_NULL) h->extra_len = s->gz_xlen;
+            s->gz_have = 0;
+            s->gz_st = s->gz_xlen ? GZ_EXTRA : (s->gz_flags & 8) ? GZ_NAME : (s->gz_flags & 16) ? GZ_COMMENT : (s->gz_flags & 2) ? GZ_HCRC : GZ_DONE;
+            break;
+        case GZ_EXTRA:
+            if (h != Z_NULL && h->extra != Z_NULL && s->gz_have < h->extra_max) h->extra[s->gz_have] = (Bytef)c;
+            if (++s->gz_have < s->gz_xlen) break;
+            s->gz_have = 0;
+            s->gz_st = (s->gz_flags & 8) ? GZ_NAME : (s->gz_flags & 16) ? GZ_COMMENT : (s->gz_flags & 2) ? GZ_HCRC : GZ_DONE;
+            break;
+        case GZ_NAME:
+            if (h != Z_NULL && h->name != Z_NULL && s->gz_have < h->name_max) h->name[s->gz_have] = (Bytef)c;
+            s->gz_have++;
+            if (c != 0) break;
+            s->gz_have = 0;
+            s->gz_st = (s->gz_flags & 16) ? GZ_COMMENT : (s->gz_flags & 2) ? GZ_HCRC : GZ_DONE;
+            break;
+        case GZ_COMMENT:
+            if (h != Z_NULL && h->comment != Z_NULL && s->gz_have < h->comm_max) h->comment[s->gz_have] = (Bytef)c;
+            s->gz_have++;
+            if (c != 0) break;
+            s->gz_have = 0;
+            s->gz_st = (s->gz_flags & 2) ? GZ_HCRC : GZ_DONE;
+            break;
+        case GZ_HCRC:
+            if (++s->gz_have == 2) s->gz_st = GZ_DONE;
+            break;
+        default:
+            break;
+        }
+        if (s->gz_st == GZ_DONE && h != Z_NULL && h->done == 0) {
+            h->hcrc = (int)((s->gz_flags >> 1) & 1);
+            h->done = 1;
+        }
+    }
 }
 
 ZAPI int inflate(z_streamp strm, int flush)                     /* inflate.c:554-1153 */
@@ -492,6 +568,7 @@ ZAPI int inflate(z_streamp strm, int flush)                     /* inflate.c:554
 
     rc = zb200i_inflate_run(s->inf, strm->next_in, in0, strm->next_out, out0, &in_used, &out_len, &status, &msg, &check);
     if (rc != Z_OK) { strm->msg = ERR_MSG(rc == Z_MEM_ERROR ? Z_MEM_ERROR : Z_STREAM_ERROR); return rc == Z_MEM_ERROR ? Z_MEM_ERROR : Z_STREAM_ERROR; }
+    if (s->inf_wrap >= 2 && s->gz_st != GZ_DONE) gz_capture(s, strm->next_in, in_used);
     strm->next_in += in_used; strm->avail_in -= (uInt)in_used; strm->total_in += in_used;
     strm->next_out += out_len; strm->avail_out -= (uInt)out_len; strm->total_out += out_len;
     if (s->inf_wrap) strm->adler = check;
@@ -585,9 +662,13 @@ ZAPI int inflatePrime(z_streamp strm, int bits, int value)
     return Z_STREAM_ERROR;            /* sub-byte priming is not offered by the device decoder */
 }
 
-ZAPI int inflateGetHeader(z_streamp strm, gz_headerp head)
+ZAPI int inflateGetHeader(z_streamp strm, gz_headerp head)      /* inflate.c:1211-1227 */
 {
-    (void)head;
-    if (strm == Z_NULL || strm->state == Z_NULL) return Z_STREAM_ERROR;
-    return Z_STREAM_ERROR;            /* only meaningful for gzip decoding (inflate.c:1211-1227), see inflateInit2_ */
+    zs *s;
+    if (strm == Z_NULL || strm->state == Z_NULL || strm->state->kind != KIND_INFLATE) return Z_STREAM_ERROR;
+    s = strm->state;
+    if ((s->inf_wrap & 2) == 0) return Z_STREAM_ERROR;          /* only for gzip decoding (windowBits + 16 or + 32) */
+    s->gz_head = head;
+    head->done = 0;
+    return Z_OK;
 }
