@@ -3,6 +3,7 @@ import ctypes as C
 import json
 import os
 import random
+import zlib
 
 import numpy as np
 import pytest
@@ -108,3 +109,30 @@ def test_checksum_batch(gpu_lib, oracle):
     bufs = [bytes([255]) * 70000, bytes(70000)]                # extreme sums
     crcs, adls = gpu_lib.checksum_batch(bufs)
     assert crcs == [oracle.crc32(b) for b in bufs] and adls == [oracle.adler32(b) for b in bufs]
+
+
+def test_ten_thousand_unaligned_slices(gpu_lib, oracle):
+    """SURVEY.md 8(d) gate (c): bit-equal crc32 / adler32 on >= 10^4 (offset, length) pairs, unaligned starts and ends --
+    consecutive random-length slices of one buffer through zb200_checksum_batch (every start alignment mod 16 occurs),
+    then the whole buffer rebuilt from the slices with the library's crc32_combine and the exact Adler join (the
+    reference's adler32_combine keeps a non-canonical 65521 now and then, adler32.c:142-147, so it is not chained here)."""
+    from zlib_b200.dist import adler_join
+    import random
+    rng = random.Random(2026)
+    sizes = [rng.choice([0, 1, 2, 3, 5, 15, 16, 17, 31, 33, rng.randint(0, 300), rng.randint(0, 9000)]) for _ in range(10000)]
+    sizes[1234] = 300001
+    blob = zhelpers.corpus(0, sum(sizes), 3)
+    bufs, pos = [], 0
+    for n in sizes:
+        bufs.append(blob[pos:pos + n])
+        pos += n
+    crcs, adls = gpu_lib.checksum_batch(bufs)
+    crc_all, adl_all = 0, 1
+    for b, c, a in zip(bufs, crcs, adls):
+        assert c == zlib.crc32(b) and a == zlib.adler32(b), len(b)
+        crc_all = gpu_lib.crc32_combine(crc_all, c, len(b))
+        adl_all = adler_join(adl_all, a, len(b))
+    for i in rng.sample(range(len(bufs)), 300):                    # the CPU oracle on a sample (system zlib checked all)
+        assert crcs[i] == oracle.crc32(bufs[i]) and adls[i] == oracle.adler32(bufs[i])
+    assert crc_all == oracle.crc32(blob) and adl_all == oracle.adler32(blob)
+    assert gpu_lib.checksum(blob) == (crc_all, adl_all)

@@ -1,1 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python -m pytest tests/test_checksum_gpu.py -m gpu -x -q 2>&1 | tail -3
+bench() { python bench.py --steps 2 --warmup 1 --no-extra --no-verify; }
+bench > gpurun_out/plain.json 2> gpurun_out/plain.log && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches_d.csv python bench.py --steps 2 --warmup 1 --no-extra --no-verify > gpurun_out/ncu_l2.log 2>&1
+wc -l gpurun_out/r1_launches_d.csv
