@@ -139,6 +139,58 @@ def reference_compress_throughput(level, sample_bytes, kind=1, seed=1):
     return per * cores / dt / 1e9, cores, dt, per * cores / max(1, sum(outs)), per * cores
 
 
+def reference_side_paths(sample_per_thread=16 << 20, kind=1, seed=1):
+    """The other paths of the reference on all host cores, bounded samples (reported beside the GPU extras):
+    compress2 level 6, uncompress of those streams, crc32 and adler32 -- every thread on its own slice."""
+    import zhelpers
+    from zlib_b200 import load
+    if not os.path.exists(zhelpers.REF_PATH):
+        return None
+    ref = zhelpers.Ref()
+    lib = load()
+    cores = os.cpu_count() or 1
+    per = sample_per_thread
+    data = lib.synth(per * cores, kind=kind, seed=seed)
+    cap = ref.dll.compressBound(per)
+    zbufs = [C.create_string_buffer(cap) for _ in range(cores)]
+    obufs = [C.create_string_buffer(per) for _ in range(cores)]
+    zlen = [0] * cores
+    sink = [0] * cores
+
+    def run(fn):
+        ths = [threading.Thread(target=fn, args=(i,)) for i in range(cores)]
+        t0 = time.perf_counter()
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        return time.perf_counter() - t0
+
+    def f_comp(i):
+        ol = C.c_ulong(cap)
+        assert ref.dll.compress2(zbufs[i], C.byref(ol), C.c_void_p(data.ctypes.data + i * per), per, 6) == 0
+        zlen[i] = ol.value
+
+    def f_unc(i):
+        ol = C.c_ulong(per)
+        assert ref.dll.uncompress(obufs[i], C.byref(ol), zbufs[i], zlen[i]) == 0 and ol.value == per
+
+    def f_crc(i):
+        for _ in range(8):
+            sink[i] = ref.dll.crc32(0, C.c_void_p(data.ctypes.data + i * per), per)
+
+    def f_adl(i):
+        for _ in range(8):
+            sink[i] = ref.dll.adler32(1, C.c_void_p(data.ctypes.data + i * per), per)
+
+    tot = per * cores
+    out = {"cores": cores, "sample": f"{per >> 20} MiB of the mixed corpus per host thread"}
+    out["compress2_level6_GBps"] = round(tot / run(f_comp) / 1e9, 4)
+    out["level6_ratio"] = round(tot / max(1, sum(zlen)), 4)
+    out["uncompress_GBps"] = round(tot / run(f_unc) / 1e9, 4)
+    out["crc32_GBps"] = round(8 * tot / run(f_crc) / 1e9, 3)
+    out["adler32_GBps"] = round(8 * tot / run(f_adl) / 1e9, 3)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -433,6 +485,7 @@ def main():
         extra["zip_build_level1"] = {"GBps": round(n / min(zt) / 1e9, 3), "files": nf, "archive_bytes": int(ol.value),
                                      "ms": round(min(zt) * 1e3, 1), "host_buffers": "pinned", "members_read_back": zok}
         lib.dll.zb200_free_pinned(C.c_void_p(pin_zip))
+        extra["reference_cpu"] = reference_side_paths()        # the reference's other paths on this box's host cores
         log(f"[rank 0] extras: {json.dumps(extra)}")
 
     if rank == 0:
