@@ -215,6 +215,33 @@ def test_inflate_get_header(gpu_lib):
     gpu_lib.dll.inflateEnd(C.byref(strm))
 
 
+def test_inflate_prime(gpu_lib):
+    """inflatePrime (inflate.c:128-142): the first bits of a raw deflate stream handed over as primed bits, the rest as
+    bytes that start right after them, decode to the same output; priming is refused once input is pending."""
+    import ctypes as C
+    data = zhelpers.corpus(1, 30000, 78)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    z = co.compress(data) + co.flush()
+    val = int.from_bytes(z, "little")
+    for bits in (0, 1, 3, 8, 11, 16):
+        rest = (val >> bits).to_bytes(len(z), "little")
+        strm = zb.z_stream()
+        assert gpu_lib.dll.inflateInit2_(C.byref(strm), -15, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+        assert gpu_lib.dll.inflatePrime(C.byref(strm), bits, val & ((1 << bits) - 1)) == zb.Z_OK
+        src = C.create_string_buffer(rest, len(rest))
+        out = C.create_string_buffer(len(data) + 8)
+        strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(rest), C.addressof(out), len(data) + 8
+        assert gpu_lib.dll.inflate(C.byref(strm), zb.Z_FINISH) == zb.Z_STREAM_END
+        assert out.raw[:len(data)] == data and strm.total_out == len(data)
+        gpu_lib.dll.inflateEnd(C.byref(strm))
+    strm = zb.z_stream()
+    assert gpu_lib.dll.inflateInit2_(C.byref(strm), -15, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+    assert gpu_lib.dll.inflatePrime(C.byref(strm), 17, 0) == zb.Z_STREAM_ERROR
+    assert gpu_lib.dll.inflatePrime(C.byref(strm), 3, 5) == zb.Z_OK
+    assert gpu_lib.dll.inflatePrime(C.byref(strm), 3, 5) == zb.Z_STREAM_ERROR      # primed bits are pending input
+    gpu_lib.dll.inflateEnd(C.byref(strm))
+
+
 def test_zip_archive_from_one_gpu_batch(gpu_lib, tmp_path):
     """BASELINE config 5 in small: many files compressed by ONE zb200_deflate_batch call and laid out as a ZIP32
     archive by zb200_zip_build; the reference's miniunz extracts every member bit-exact, Python's zipfile agrees."""

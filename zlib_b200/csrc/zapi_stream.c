@@ -655,11 +655,11 @@ ZAPI int inflateCopy(z_streamp dest, z_streamp source)          /* inflate.c:132
     return Z_OK;
 }
 
-ZAPI int inflatePrime(z_streamp strm, int bits, int value)
+ZAPI int inflatePrime(z_streamp strm, int bits, int value)     /* inflate.c:128-142 */
 {
-    (void)bits; (void)value;
-    if (strm == Z_NULL || strm->state == Z_NULL) return Z_STREAM_ERROR;
-    return Z_STREAM_ERROR;            /* sub-byte priming is not offered by the device decoder */
+    if (strm == Z_NULL || strm->state == Z_NULL || strm->state->kind != KIND_INFLATE) return Z_STREAM_ERROR;
+    if (bits > 16 || bits < 0) return Z_STREAM_ERROR;
+    return zb200i_inflate_prime(strm->state->inf, bits, value) == 0 ? Z_OK : Z_STREAM_ERROR;
 }
 
 ZAPI int inflateGetHeader(z_streamp strm, gz_headerp head)      /* inflate.c:1211-1227 */

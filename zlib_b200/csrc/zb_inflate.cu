@@ -895,6 +895,24 @@ extern "C" int zb200i_inflate_resync(zb200i_inflater* h)
     return 0;
 }
 
+// inflatePrime (inflate.c:128-142): `bits` bits of `value` are to be decoded ahead of the next input byte.  The decoder
+// already knows how to start inside a byte (bit_off = bits of the first byte that are spent), so the primed bits become
+// one or two bytes at the front of the pending input with the unused low bits marked as spent.
+extern "C" int zb200i_inflate_prime(zb200i_inflater* h, int bits, int value)
+{
+    if (bits < 0 || bits > 16) return ZB_STREAM_ERROR;
+    if (bits == 0) return 0;
+    InfState st;
+    ZB_CUDA(cudaMemcpy(&st, h->d_state, sizeof(InfState) - sizeof(st.lens), cudaMemcpyDeviceToHost));
+    if (!h->carry.empty() || st.bit_off != 0) { set_error("inflatePrime: only on a byte boundary with no input pending"); return ZB_STREAM_ERROR; }
+    const int nbytes = (bits + 7) / 8, pad = nbytes * 8 - bits;
+    const uint32_t v = ((uint32_t)value & ((1u << bits) - 1u)) << pad;
+    for (int i = 0; i < nbytes; i++) h->carry.push_back((uint8_t)(v >> (8 * i)));
+    st.bit_off = (uint32_t)pad;
+    ZB_CUDA(cudaMemcpy(h->d_state, &st, sizeof(InfState) - sizeof(st.lens), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 extern "C" int zb200i_inflate_run(zb200i_inflater* h, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap,
                                   size_t* in_used, size_t* out_len, int* status, int* msg, uint32_t* check)
 {
