@@ -431,7 +431,9 @@ def main():
         zin = int(src_off[-1])
         pin_z = lib.dll.zb200_alloc_pinned(zin + 64)
         assert pin_z
-        C.memmove(C.c_void_p(pin_z), d_z.cpu().numpy().ctypes.data, zin)
+        z_host = d_z.cpu().numpy()                              # keep the array alive across the copy
+        C.memmove(C.c_void_p(pin_z), C.c_void_p(z_host.ctypes.data), zin)
+        del z_host
         h_so, h_do = src_off.astype(np.uint64), (np.arange(ns + 1, dtype=np.uint64) * sz)
         h_len, h_st = np.zeros(ns, dtype=np.uint64), np.zeros(ns, dtype=np.int32)
         th = []

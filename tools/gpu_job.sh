@@ -1,2 +1,1 @@
-python -m pytest tests/test_inflate_gpu.py tests/test_stream_gpu.py tests/test_abi.py -x -q 2>&1 | tail -2
-python tools/probe_inflate_host.py 32768 2>&1 | tail -4
+python bench.py > gpurun_out/bench12.json 2> gpurun_out/bench12.log; tail -1 gpurun_out/bench12.log | cut -c1-2500
