@@ -3,6 +3,7 @@ import base64
 import json
 import os
 import random
+import zlib
 
 import numpy as np
 import pytest
@@ -180,3 +181,87 @@ def test_gzip_members_batch(gpu_lib, oracle):
             want.append(-3)
     outs, st = gpu_lib.inflate_batch(bad, [len(datas[5])] * 6 + [len(datas[5])] * 2, wrap=zb.WRAP_GZIP)
     assert st == want == [-3] * len(bad), (st, want)
+
+
+def _used_parallel(lib, fn):
+    """Runs fn with per-kernel timing on and tells whether the segment-parallel decoder's kernels were launched."""
+    lib.profile(True)
+    try:
+        r = fn()
+        rep = lib.profile_report()
+    finally:
+        lib.profile(False)
+    return r, any("k_inflate_segments" in k for k in rep), any("k_inflate_batch" in k for k in rep)
+
+
+def test_long_single_stream_decodes_in_parallel(gpu_lib, oracle):
+    """uncompress() of ONE long stream: streams with byte-aligned block boundaries (this library's chunked output; any
+    stream with Z_SYNC_FLUSH / Z_FULL_FLUSH points) are cut at the 00 00 FF FF markers, the segments are validated by a
+    counting pass and decoded in parallel, and matches that reach back over a segment start are resolved afterwards.
+    Output is bit-exact; everything the scheme cannot take goes to the serial decoder with the same result as before."""
+    n = (24 << 20) + 12345
+    data = gpu_lib.synth(n, kind=1, seed=21).tobytes()
+    for level in (1, 6):
+        rc, z = gpu_lib.compress2(data, level)
+        assert rc == zb.Z_OK
+        (rc, out), par, ser = _used_parallel(gpu_lib, lambda: gpu_lib.uncompress(z, n))
+        assert rc == zb.Z_OK and out == data and par and not ser
+        assert zlib.decompress(z) == data
+    # exact capacity fits; one byte less is Z_BUF_ERROR (the serial decoder reports it the reference's way)
+    rc, out = gpu_lib.uncompress(z, n - 1)
+    assert rc == zb.Z_BUF_ERROR
+    # a foreign stream with flush points of both kinds, matches reaching back across them, and a stored stretch
+    rng = random.Random(8)
+    parts = [zhelpers.corpus(rng.choice([1, 1, 3, 4]), rng.randint(50000, 400000), 50 + i) for i in range(30)]
+    parts[11] = rng.randbytes(200000)                           # incompressible: stored blocks
+    co = zlib.compressobj(6)
+    zf = b""
+    for i, p in enumerate(parts):
+        zf += co.compress(p) + co.flush(zlib.Z_FULL_FLUSH if i % 5 == 4 else zlib.Z_SYNC_FLUSH)
+    zf += co.flush()
+    plain = b"".join(parts)
+    (rc, out), par, ser = _used_parallel(gpu_lib, lambda: gpu_lib.uncompress(zf, len(plain)))
+    assert rc == zb.Z_OK and out == plain and par and not ser
+    # raw deflate, same boundaries
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    zr = b"".join(co.compress(p) + co.flush(zlib.Z_SYNC_FLUSH) for p in parts) + co.flush()
+    outs, st = gpu_lib.inflate_batch([zr], [len(plain)], wrap=zb.WRAP_RAW)
+    assert st == [0] and outs[0] == plain
+
+
+def test_long_single_stream_fallbacks(gpu_lib, oracle):
+    """What the parallel scheme must leave to the serial decoder: no boundaries at all, the marker pattern occurring as
+    DATA (inside stored blocks), and damage -- results and return codes are those of the reference's uncompress()."""
+    data = zhelpers.corpus(1, 1500000, 9)
+    z = zlib.compress(data, 6)                                  # one block sequence, no flush points
+    (rc, out), par, ser = _used_parallel(gpu_lib, lambda: gpu_lib.uncompress(z, len(data)))
+    assert rc == zb.Z_OK and out == data and ser
+    # level 0: the stream shows its input, so 00 00 FF FF in the input is a false candidate every time
+    rng = random.Random(10)
+    raw = bytearray(rng.randbytes(900000))
+    for k in range(20000, len(raw) - 8, 40000):
+        raw[k:k + 4] = b"\x00\x00\xff\xff"
+    raw = bytes(raw)
+    z0 = zlib.compress(raw, 0)
+    assert z0.count(b"\x00\x00\xff\xff") >= 20
+    rc, out = gpu_lib.uncompress(z0, len(raw))
+    assert rc == zb.Z_OK and out == raw
+    # the same false candidates in front of real ones
+    co = zlib.compressobj(0)
+    zm = co.compress(raw) + co.flush(zlib.Z_SYNC_FLUSH)
+    co2 = zlib.compressobj(6, zlib.DEFLATED, -15)
+    # damage in the middle of a chunked stream: the reference's code and ours agree
+    n = 3 << 20
+    d2 = gpu_lib.synth(n, kind=1, seed=22).tobytes()
+    rc, z2 = gpu_lib.compress2(d2, 1)
+    bad = bytearray(z2)
+    bad[len(bad) // 2] ^= 0x55
+    rc, out = gpu_lib.uncompress(bytes(bad), n)
+    want, _, _ = oracle.inflate(bytes(bad), n)
+    assert rc == want and rc != zb.Z_OK
+    bad = bytearray(z2)
+    bad[-2] ^= 1                                                # Adler-32 trailer
+    rc, out = gpu_lib.uncompress(bytes(bad), n)
+    assert rc == zb.Z_DATA_ERROR
+    rc, out = gpu_lib.uncompress(z2[:len(z2) * 2 // 3], n)      # truncated
+    assert rc == zb.Z_DATA_ERROR

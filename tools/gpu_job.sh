@@ -1,1 +1,1 @@
-python bench.py > gpurun_out/bench12.json 2> gpurun_out/bench12.log; tail -1 gpurun_out/bench12.log | cut -c1-2500
+timeout 900 python -m pytest tests/test_inflate_gpu.py -m gpu -x -q 2>&1 | tail -12

@@ -27,6 +27,7 @@
 #include "zb_inflate.cuh"
 #include "zb200_internal.h"
 #include <vector>
+#include <algorithm>
 #include <string.h>
 #include <stdlib.h>
 
@@ -771,6 +772,337 @@ __global__ void __launch_bounds__(1024) k_slide_history(uint8_t* arena, uint64_t
     for (int i = 0; i < 32; i++) if (base + i < keep) dst[base + i] = r[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// One long stream, decoded in parallel wherever it offers a byte-aligned block boundary
+// ------------------------------------------------------------------------------------------
+// A single DEFLATE stream is serial, and one warp decodes it at some 15 MB/s.  But streams written by this library
+// end every 128 KiB chunk with an empty stored block (00 00 FF FF on a byte boundary), and so does any stream written
+// with Z_SYNC_FLUSH / Z_FULL_FLUSH points (deflate.c:808-825): after such a marker a new block starts on a byte
+// boundary.  Only the 32 KiB of history are missing there.  So (the scheme of two-stage parallel gzip decoders):
+//   find     every 00 00 FF FF in the compressed bytes is a candidate boundary;
+//   count    one warp per segment decodes from its candidate without producing output: the segment is valid if the
+//            decoder arrives EXACTLY at the next candidate at the end of a block (or at the final block, for the last
+//            one); this also yields every segment's output size, hence its place.  Any failure -- a pattern that was
+//            data, a damaged stream -- makes the whole call fall back to the serial decoder, which reports it;
+//   decode   the same decode again, now into 16-bit symbols: a byte, or 0x8000 | w for "byte w of the 32 KiB in front
+//            of this segment", which is what a match reaching back over the segment start becomes (later copies
+//            propagate such symbols unchanged);
+//   tails    one CTA walks the segments in order and resolves the last 32 KiB of each against the 32 KiB in front of it
+//            (already final by then): the only sequential part, ~64 KiB of traffic per segment;
+//   rest     every other symbol of every segment resolves in parallel against the final bytes in front of its segment.
+struct SegDesc { uint64_t start, stop, out_off, out_len; };     // byte range of the segment's blocks; its place in the output
+struct SegResult { uint64_t out_len, end_bit; int32_t status, final; };   // status 0 = arrived exactly, 1 = missed, 2 = invalid data
+constexpr uint32_t kSegMinBytes = 16384;                        // candidates closer than this to the previous boundary are skipped
+constexpr size_t kParMinInput = 256u << 10;                     // shorter streams are not worth the extra passes
+
+__global__ void k_find_markers(const uint8_t* __restrict__ in, uint64_t first, uint64_t len, uint32_t* __restrict__ count,
+                               uint64_t* __restrict__ pos, uint32_t cap)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p + 4 <= len; p += stride) {
+        if (in[p] == 0 && in[p + 1] == 0 && in[p + 2] == 0xff && in[p + 3] == 0xff) {
+            const uint32_t k = atomicAdd(count, 1u);
+            if (k < cap) pos[k] = p + 4;
+        }
+    }
+}
+
+// kEmit == false: count only.  kEmit == true: 16-bit symbols to sym[sd.out_off ...), exactly sd.out_len of them.
+template <bool kEmit>
+__device__ void seg_decode(const uint8_t* in, uint64_t in_len, const SegDesc sd, bool first_seg, bool last_seg,
+                           uint16_t* __restrict__ sym, WarpTables* t, SegResult* res)
+{
+    const int lane = threadIdx.x & 31;
+    Bits b;
+    b.words = reinterpret_cast<const uint32_t*>((uintptr_t)in & ~(uintptr_t)3);
+    b.nwords = (uint32_t)(((((uintptr_t)in + in_len + 3) & ~(uintptr_t)3) - (uintptr_t)b.words) >> 2);
+    b.total = in_len * 8;
+    seek_bits(b, in, sd.start * 8);
+    uint16_t* out = kEmit ? sym + sd.out_off : nullptr;
+    uint64_t produced = 0;
+    int status = 2, last = 0;
+    for (;;) {
+        // ---- at a block boundary ----
+        if (last) { status = last_seg ? 0 : 1; break; }
+        if (!last_seg) {
+            if (b.used == sd.stop * 8) { status = 0; break; }
+            if (b.used > sd.stop * 8) { status = 1; break; }
+        }
+        if (!have(b, 3)) break;
+        refill(b);
+        last = (int)peek(b, 1); drop(b, 1);
+        const uint32_t type = peek(b, 2); drop(b, 2);
+        if (type == 0) {                                        // stored, inflate.c:807-836
+            const int pad = (int)((8 - (b.used & 7)) & 7);
+            if (!have(b, pad + 32)) break;
+            drop(b, pad);
+            refill(b);
+            const uint32_t len = peek(b, 16); drop(b, 16);
+            refill(b);
+            const uint32_t nlen = peek(b, 16); drop(b, 16);
+            if (len != (nlen ^ 0xffffu)) break;
+            const uint64_t bytepos = b.used >> 3;
+            if (bytepos + len > in_len) break;
+            if (kEmit) {
+                if (produced + len > sd.out_len) break;
+                __syncwarp();
+                for (uint32_t i = lane; i < len; i += 32) out[produced + i] = in[bytepos + i];
+                __syncwarp();
+            }
+            produced += len;
+            seek_bits(b, in, (bytepos + len) * 8);
+            continue;
+        }
+        if (type == 3) break;
+        int nlen = 288, ndist = 32;
+        if (type == 1) {                                        // fixed code, inflate.c:205-246
+            store_lens(t, 0, 144, 8); store_lens(t, 144, 112, 9); store_lens(t, 256, 24, 7);
+            store_lens(t, 280, 8, 8); store_lens(t, 288, 32, 5);
+            __syncwarp();
+        } else {                                                // dynamic, inflate.c:837-949
+            if (!have(b, 14)) break;
+            refill(b);
+            nlen = (int)peek(b, 5) + 257; drop(b, 5);
+            ndist = (int)peek(b, 5) + 1; drop(b, 5);
+            const int ncode = (int)peek(b, 4) + 4; drop(b, 4);
+            if (nlen > 286 || ndist > 30) break;
+            if (lane < 20) t->cl_lens[lane] = 0;
+            __syncwarp();
+            if (!have(b, 3 * ncode)) break;
+            for (int i = 0; i < ncode; i++) {
+                refill(b);
+                const uint32_t v = peek(b, 3); drop(b, 3);
+                if (lane == 0) t->cl_lens[c_cl_order[i]] = (uint8_t)v;
+            }
+            __syncwarp();
+            if (build_table(t->cl_lens, 19, 0, t->dist, kClBits, nullptr, t->dist_count, t, &t->dist_max)) break;
+            __syncwarp();
+            const int cl_max = t->dist_max, total = nlen + ndist;
+            int idx = 0;
+            bool bad = false;
+            uint32_t prev = 0;
+            while (idx < total) {
+                refill(b);
+                uint32_t s;
+                if (cl_max == 0) { if (!have(b, 1)) { bad = true; break; } drop(b, 1); s = 0; }
+                else {
+                    const uint32_t e = t->dist[peek(b, kClBits)];
+                    const int l = (int)ent_len(e);
+                    if (l == 0 || !have(b, l)) { bad = true; break; }
+                    drop(b, l); s = ent_val(e);
+                }
+                if (s < 16) { if (lane == 0) t->lens[idx] = (uint8_t)s; prev = s; idx++; continue; }
+                uint32_t rep, val = 0;
+                if (s == 16) { if (!have(b, 2) || idx == 0) { bad = true; break; } val = prev; rep = 3 + peek(b, 2); drop(b, 2); }
+                else if (s == 17) { if (!have(b, 3)) { bad = true; break; } rep = 3 + peek(b, 3); drop(b, 3); }
+                else { if (!have(b, 7)) { bad = true; break; } rep = 11 + peek(b, 7); drop(b, 7); }
+                if (idx + (int)rep > total) { bad = true; break; }
+                store_lens(t, idx, (int)rep, (uint8_t)val);
+                idx += (int)rep; prev = val;
+            }
+            if (bad) break;
+            __syncwarp();
+        }
+        if (build_table(t->lens, nlen, 1, t->lit, kLitBits, t->lit_sorted, t->lit_count, t, &t->lit_max)) break;
+        if (build_table(t->lens + nlen, ndist, 2, t->dist, kDistBits, t->dist_sorted, t->dist_count, t, &t->dist_max)) break;
+        // ---- symbols of the block ----
+        bool bad = false;
+        for (;;) {
+            refill(b);
+            uint32_t e = t->lit[peek(b, kLitBits)];
+            const uint32_t len = ent_len(e);
+            if (len != 0) { if (!have(b, (int)len)) { bad = true; break; } drop(b, (int)len); }
+            else {
+                const int s = slow_symbol(b, t->lit_count, t->lit_sorted, t->lit_max);
+                if (s < 0) { bad = true; break; }
+                e = litlen_entry((uint32_t)s, 1);
+            }
+            const uint32_t kind = ent_kind(e);
+            if (kind == kLit) {
+                if (kEmit) {
+                    if (produced >= sd.out_len) { bad = true; break; }
+                    if (lane == 0) out[produced] = (uint16_t)ent_val(e);
+                }
+                produced++;
+                continue;
+            }
+            if (kind == kEob) break;
+            if (kind == kBad) { bad = true; break; }
+            const int xl = (int)ent_extra(e);
+            if (!have(b, xl)) { bad = true; break; }
+            const uint32_t mlen = ent_val(e) + peek(b, xl);
+            drop(b, xl);
+            refill(b);
+            uint32_t de = t->dist[peek(b, kDistBits)];
+            const uint32_t dl = ent_len(de);
+            if (dl != 0) { if (!have(b, (int)dl)) { bad = true; break; } drop(b, (int)dl); }
+            else {
+                const int s = slow_symbol(b, t->dist_count, t->dist_sorted, t->dist_max);
+                if (s < 0) { bad = true; break; }
+                de = dist_entry((uint32_t)s, 1);
+            }
+            if (ent_kind(de) == kBad) { bad = true; break; }
+            const int xd = (int)ent_extra(de);
+            refill(b);
+            if (!have(b, xd)) { bad = true; break; }
+            const uint32_t dist = ent_val(de) + peek(b, xd);
+            drop(b, xd);
+            if (dist > produced && (first_seg || dist - produced > kWindow32)) { bad = true; break; }   // beyond the history
+            if (kEmit) {
+                if (produced + mlen > sd.out_len) { bad = true; break; }
+                __syncwarp();
+                const int64_t src0 = (int64_t)produced - (int64_t)dist;    // may lie in front of the segment
+                for (uint32_t i = lane; i < mlen; i += 32) {
+                    const int64_t q = src0 + (int64_t)(dist < mlen ? i % dist : i);
+                    out[produced + i] = q >= 0 ? out[q] : (uint16_t)(0x8000u | (uint32_t)(q + (int64_t)kWindow32));
+                }
+                __syncwarp();
+            }
+            produced += mlen;
+        }
+        if (bad) break;
+    }
+    if (lane == 0) { res->out_len = produced; res->end_bit = b.used; res->status = status; res->final = last; }
+}
+
+template <bool kEmit>
+__global__ void __launch_bounds__(kInfWarps * 32)
+k_inflate_segments(const uint8_t* __restrict__ in, uint64_t in_len, const SegDesc* __restrict__ segs, uint32_t nseg,
+                   uint16_t* __restrict__ sym, SegResult* __restrict__ res)
+{
+    __shared__ WarpTables s_tab[kInfWarps];
+    const uint32_t j = blockIdx.x * kInfWarps + (threadIdx.x >> 5);
+    if (j >= nseg) return;
+    seg_decode<kEmit>(in, in_len, segs[j], j == 0, j == nseg - 1, sym, &s_tab[threadIdx.x >> 5], &res[j]);
+}
+
+// The sequential part: segment by segment, the last 32 KiB of symbols become bytes; a window symbol reads the 32 KiB in
+// front of the segment, which the earlier trips of this loop (same CTA) have made final.
+__global__ void __launch_bounds__(1024) k_resolve_tails(const uint16_t* __restrict__ sym, uint8_t* out,
+                                                        const SegDesc* __restrict__ segs, uint32_t nseg, uint32_t* __restrict__ err)
+{
+    for (uint32_t j = 0; j < nseg; j++) {
+        const SegDesc sd = segs[j];
+        const uint64_t t = min(sd.out_len, (uint64_t)kWindow32), base = sd.out_off + sd.out_len - t;
+        for (uint64_t i = threadIdx.x; i < t; i += 1024) {
+            const uint32_t v = sym[base + i];
+            uint32_t byte = v;
+            if (v & 0x8000u) {
+                const int64_t q = (int64_t)sd.out_off - (int64_t)kWindow32 + (int64_t)(v & 0x7fffu);
+                if (q < 0) { atomicAdd(err, 1u); byte = 0; }
+                else byte = __ldcg(out + q);
+            }
+            out[base + i] = (uint8_t)byte;
+        }
+        __syncthreads();
+    }
+}
+
+// Everything in front of the tails, all segments at once.
+__global__ void __launch_bounds__(256) k_resolve_rest(const uint16_t* __restrict__ sym, uint8_t* __restrict__ out,
+                                                      const SegDesc* __restrict__ segs, uint32_t* __restrict__ err)
+{
+    const SegDesc sd = segs[blockIdx.x];
+    const uint64_t t = min(sd.out_len, (uint64_t)kWindow32), n = sd.out_len - t;
+    for (uint64_t i = threadIdx.x; i < n; i += 256) {
+        const uint32_t v = sym[sd.out_off + i];
+        uint32_t byte = v;
+        if (v & 0x8000u) {
+            const int64_t q = (int64_t)sd.out_off - (int64_t)kWindow32 + (int64_t)(v & 0x7fffu);
+            if (q < 0) { atomicAdd(err, 1u); byte = 0; }
+            else byte = __ldcg(out + q);
+        }
+        out[sd.out_off + i] = (uint8_t)byte;
+    }
+}
+
+// Returns 0 when the stream was decoded here (*status, *out_len set), 1 when the caller should use the serial decoder
+// (no usable boundaries, a candidate that was not one, output that does not fit, damaged data), negative on CUDA errors.
+int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t* d_dst, uint64_t cap, int wrap,
+                            uint64_t* out_len, int32_t* status, cudaStream_t s)
+{
+    if (len < kParMinInput || (wrap != ZB200_WRAP_ZLIB && wrap != ZB200_WRAP_RAW)) return 1;
+    uint64_t hdr = 0;
+    uint8_t h2[2];
+    if (wrap == ZB200_WRAP_ZLIB) {                              // inflate.c:589-632; a preset dictionary goes the serial way
+        ZB_CUDA(cudaMemcpyAsync(h2, d_src, 2, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaStreamSynchronize(s));
+        if (((h2[0] << 8) + h2[1]) % 31 || (h2[0] & 15) != 8 || (h2[0] >> 4) + 8 > 15 || (h2[1] & 0x20)) return 1;
+        hdr = 2;
+    }
+    const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(len / 1024 + 16, 1u << 22);
+    int rc;
+    if ((rc = c->small.ensure(256)) != 0) return rc;
+    if ((rc = c->ws[1].ensure((size_t)cand_cap * 8 + 64)) != 0) return rc;
+    uint32_t* d_count = c->small.as<uint32_t>() + 16;
+    uint32_t* d_err = d_count + 1;
+    uint64_t* d_pos = c->ws[1].as<uint64_t>();
+    ZB_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+    ZB_LAUNCH(k_find_markers, kSMs * 8, 256, 0, s, d_src, hdr, len, d_count, d_pos, cand_cap);
+    uint32_t ncand = 0;
+    ZB_CUDA(cudaMemcpyAsync(&ncand, d_count, 4, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    if (ncand == 0 || ncand > cand_cap) return 1;
+    std::vector<uint64_t> pos(ncand);
+    ZB_CUDA(cudaMemcpyAsync(pos.data(), d_pos, (size_t)ncand * 8, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    std::sort(pos.begin(), pos.end());
+    std::vector<SegDesc> segs;
+    segs.push_back(SegDesc{hdr, len, 0, 0});
+    for (uint64_t p : pos)
+        if (p >= segs.back().start + kSegMinBytes && p + 8 <= len) { segs.back().stop = p; segs.push_back(SegDesc{p, len, 0, 0}); }
+    const uint32_t nseg = (uint32_t)segs.size();
+    if (nseg < 2) return 1;
+    if ((rc = c->ws[2].ensure((size_t)nseg * sizeof(SegDesc))) != 0) return rc;
+    if ((rc = c->ws[3].ensure((size_t)nseg * sizeof(SegResult))) != 0) return rc;
+    SegDesc* d_segs = c->ws[2].as<SegDesc>();
+    SegResult* d_res = c->ws[3].as<SegResult>();
+    const unsigned blocks = (nseg + kInfWarps - 1) / kInfWarps;
+    // ---- count ----
+    ZB_CUDA(cudaMemcpyAsync(d_segs, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
+    ZB_LAUNCH(k_inflate_segments<false>, blocks, kInfWarps * 32, 0, s, d_src, len, d_segs, nseg, (uint16_t*)nullptr, d_res);
+    std::vector<SegResult> res(nseg);
+    ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nseg * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    for (uint32_t j = 0; j < nseg; j++) {
+        if (res[j].status != 0 || (res[j].final != 0) != (j == nseg - 1)) return 1;
+        segs[j].out_off = total; segs[j].out_len = res[j].out_len;
+        total += res[j].out_len;
+    }
+    if (total > cap) return 1;                                  // the serial decoder reports Z_BUF_ERROR the reference's way
+    const uint64_t trailer_at = (res[nseg - 1].end_bit + 7) >> 3;
+    if (wrap == ZB200_WRAP_ZLIB && trailer_at + 4 > len) return 1;
+    // ---- decode, tails, rest ----
+    if ((rc = c->ws[4].ensure((size_t)total * 2 + 64)) != 0) return rc;
+    uint16_t* d_sym = c->ws[4].as<uint16_t>();
+    ZB_CUDA(cudaMemcpyAsync(d_segs, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
+    ZB_LAUNCH(k_inflate_segments<true>, blocks, kInfWarps * 32, 0, s, d_src, len, d_segs, nseg, d_sym, d_res);
+    ZB_LAUNCH(k_resolve_tails, 1, 1024, 0, s, d_sym, d_dst, d_segs, nseg, d_err);
+    ZB_LAUNCH(k_resolve_rest, nseg, 256, 0, s, d_sym, d_dst, d_segs, d_err);
+    ZB_CHECK_LAUNCH();
+    uint32_t sums[2] = {0, 1}, nerr = 0;
+    uint8_t tr[4] = {0, 0, 0, 0};
+    if (wrap == ZB200_WRAP_ZLIB) {
+        if ((rc = checksum_launch(c, d_dst, (size_t)total, c->small.as<uint32_t>(), s)) != 0) return rc;
+        ZB_CUDA(cudaMemcpyAsync(sums, c->small.p, 8, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaMemcpyAsync(tr, d_src + trailer_at, 4, cudaMemcpyDeviceToHost, s));
+    }
+    ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nseg * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaMemcpyAsync(&nerr, d_err, 4, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    if (nerr) return 1;
+    for (uint32_t j = 0; j < nseg; j++)
+        if (res[j].status != 0 || res[j].out_len != segs[j].out_len) return 1;
+    if (wrap == ZB200_WRAP_ZLIB) {                              // inflate.c:1077-1098
+        const uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
+        if (want != sums[1]) return 1;                          // let the serial decoder find and name the damage
+    }
+    *out_len = total;
+    *status = ZB_OK;
+    return 0;
+}
+
 }  // namespace zb
 
 using namespace zb;
@@ -1065,6 +1397,28 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             if ((rc = c->out.ensure(dst_total + 16)) != 0) break;
             d_dst = c->out.as<uint8_t>();
         }
+        cudaError_t e = cudaSuccess;
+        bool staged = false;
+        if (n == 1 && src_off[1] - src_off[0] >= kParMinInput) {
+            // one long stream (uncompress() of a big buffer): try the segment-parallel decoder; the serial one is the fallback
+            const uint64_t a = src_off[0], len = src_off[1] - a;
+            if (src_on_host) {
+                e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + a, len, cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess) { set_error("input staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+                staged = true;
+            }
+            uint64_t got = 0;
+            int32_t st = ZB_OK;
+            const int pr = inflate_single_parallel(c, d_src + a, len, d_dst + dst_off[0], dst_off[1] - dst_off[0], wrap, &got, &st, s);
+            if (pr < 0) { rc = pr; break; }
+            if (pr == 0) {
+                if (dst_on_host && got) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[0], d_dst + dst_off[0], got, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+                if (e != cudaSuccess) { set_error("inflate readback failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+                dst_len[0] = got; status[0] = st;
+                break;
+            }
+        }
         // descriptors: [src_off n+1][dst_off n+1][dst_len n][status n][gzip trailer values 3n]
         const size_t desc_bytes = (size_t)(3 * n + 2) * 8 + n * 4 + n * 12;
         if ((rc = c->ws[0].ensure(desc_bytes)) != 0) break;
@@ -1073,7 +1427,7 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
         uint64_t* d_len = d_dst_off + (n + 1);
         int32_t* d_status = (int32_t*)(d_len + n);
         uint32_t* d_expect = (uint32_t*)(d_status + n);
-        cudaError_t e = cudaMemcpyAsync(d_src_off, src_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
+        e = cudaMemcpyAsync(d_src_off, src_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst_off, dst_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess && c2) {                            // the second stream starts once the descriptors are up
             e = cudaEventRecord(c->evs[2 * ng], s);
@@ -1085,7 +1439,7 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             const size_t i0 = cut[k], i1 = cut[k + 1];
             const uint64_t a = src_off[i0], b = src_off[i1];
             cudaStream_t s = (c2 && (k & 1)) ? c2->own_stream : s_main;
-            if (src_on_host && b > a) {
+            if (src_on_host && b > a && !staged) {
                 e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + a, b - a, cudaMemcpyHostToDevice, s_in);
                 if (e == cudaSuccess) e = cudaEventRecord(ev_in[k], s_in);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev_in[k], 0);
