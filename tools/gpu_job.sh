@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_inflate_gpu.py -m gpu -x -q 2>&1 | tail -12
+timeout 900 python -m pytest tests/test_inflate_gpu.py -m gpu -x -q -k long 2>&1 | tail -3
+timeout 600 python tools/probe_single.py 1024 2>&1 | tail -8
