@@ -447,6 +447,24 @@ def main():
         extra["inflate_batch_host_e2e"] = {"GBps": round(ns * sz / min(th) / 1e9, 3), "ms": round(min(th) * 1e3, 2), "host_buffers": "pinned",
                                            "h2d_bytes": zin, "d2h_bytes": ns * sz, "output_matches": okh}
         lib.dll.zb200_free_pinned(C.c_void_p(pin_z))
+        # uncompress() of ONE long stream: the compress2 output of the e2e leg (1 GiB in one zlib stream, pinned host
+        # buffers); decoded in parallel at its chunk boundaries (BASELINE config 1's round trip, at config 2's size)
+        step_e2e()                                             # pin_dst holds the level-1 stream again
+        zlen1 = int(state["e2e_len"])
+        pin_rt = lib.dll.zb200_alloc_pinned(n)
+        assert pin_rt
+        tu = []
+        for _ in range(3):
+            ul = C.c_ulong(n)
+            t0 = time.perf_counter()
+            rc = lib.dll.uncompress(C.c_void_p(pin_rt), C.byref(ul), C.c_void_p(pin_dst), zlen1)
+            tu.append(time.perf_counter() - t0)
+            assert rc == 0 and ul.value == n, (rc, lib.last_error())
+        rt_ok = bool(np.array_equal(np.ctypeslib.as_array(C.cast(pin_rt, C.POINTER(C.c_uint8)), shape=(n,)), host))
+        assert rt_ok, "uncompress(compress2(x)) != x"
+        extra["uncompress_one_stream"] = {"GBps": round(n / min(tu) / 1e9, 3), "ms": round(min(tu) * 1e3, 1), "stream_bytes": zlen1,
+                                          "host_buffers": "pinned", "round_trip_exact": rt_ok}
+        lib.dll.zb200_free_pinned(C.c_void_p(pin_rt))
         # the full shape of BASELINE config 3: 100 000 streams of 64 KiB (the 2048 distinct ones repeated), 6.1 GiB out
         ns3 = 100000
         zs3 = (zs[:distinct] * ((ns3 + distinct - 1) // distinct))[:ns3]
