@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/bench13.json 2> gpurun_out/bench13.log; tail -1 gpurun_out/bench13.log | cut -c1-3000
+timeout 900 python -m pytest tests/test_inflate_gpu.py -m gpu -x -q 2>&1 | tail -3
+timeout 600 python tools/probe_single.py 1024 2>&1 | tail -8

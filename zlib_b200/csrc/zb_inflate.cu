@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(1024) k_slide_history(uint8_t* arena, uint64_t
 struct SegDesc { uint64_t start, stop, out_off, out_len; };     // byte range of the segment's blocks; its place in the output
 struct SegResult { uint64_t out_len, end_bit; int32_t status, final; };   // status 0 = arrived exactly, 1 = missed, 2 = invalid data
 constexpr uint32_t kSegMinBytes = 16384;                        // candidates closer than this to the previous boundary are skipped
-constexpr size_t kParMinInput = 256u << 10;                     // shorter streams are not worth the extra passes
+constexpr size_t kParMinInput = 64u << 10;                      // shorter streams are not worth the extra passes (one warp: ~15 MB/s)
 
 __global__ void k_find_markers(const uint8_t* __restrict__ in, uint64_t first, uint64_t len, uint32_t* __restrict__ count,
                                uint64_t* __restrict__ pos, uint32_t cap)
@@ -806,6 +806,92 @@ __global__ void k_find_markers(const uint8_t* __restrict__ in, uint64_t first, u
             if (k < cap) pos[k] = p + 4;
         }
     }
+}
+
+// The lean in-bounds loop of decode_fast for a segment: same bit handling, but the output is counted (kEmit == false)
+// or written as 16-bit symbols, where a source in front of the segment becomes a window symbol.  Returns true after an
+// end-of-block code; otherwise the careful loop of seg_decode continues at the symbol where this one stopped.
+template <bool kEmit>
+__device__ bool seg_fast(Bits& b, const WarpTables* t, const uint8_t* in, uint16_t* __restrict__ out, uint64_t& produced_io,
+                         uint64_t out_len, bool first_seg)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwords = b.nwords;
+    const uint32_t* words = b.words;
+    const uint64_t produced0 = produced_io;
+    uint32_t p_lim = 0x70000000u;
+    if (kEmit) {
+        const uint64_t room = out_len - produced0;
+        if (room < 324) return false;
+        p_lim = (uint32_t)min(room - 324, (uint64_t)0x70000000u);
+    }
+    if (nwords < 6) return false;
+    const uint32_t w_lim = nwords - 5;
+    const uint64_t pos0 = (uint64_t)b.nextw * 32u - (uint64_t)b.cnt;
+    const uint32_t wi0 = (uint32_t)(pos0 >> 5), off0 = (uint32_t)pos0 & 31u;
+    if (wi0 > w_lim) return false;
+    uint32_t wi = wi0, off = off0;
+    uint32_t lo = __ldg(words + wi), hi = __ldg(words + wi + 1), nxt = __ldg(words + wi + 2);
+    uint16_t* const o16 = kEmit ? out + produced0 : nullptr;
+    const uint32_t* const lit = t->lit;
+    const uint32_t* const dtab = t->dist;
+    const uint64_t back_known = first_seg ? produced0 : produced0 + kWindow32;   // how far a distance may reach at produced == 0
+    uint32_t produced = 0, end_wi, end_off;
+    bool eob = false;
+    for (;;) {
+        if (off >= 32) {
+            off -= 32; lo = hi; hi = nxt; wi++;
+            nxt = __ldg(words + wi + 2);
+            asm volatile("");
+            if (wi > w_lim || produced > p_lim) { end_wi = wi; end_off = off; break; }
+        }
+        const uint32_t win = __funnelshift_r(lo, hi, off);
+        const uint32_t e = lit[win & (kLitSize - 1)];
+        if ((int32_t)e < 0) {
+            const uint32_t e2 = lit[__funnelshift_r(win, 0u, e) & (kLitSize - 1)];
+            if (kEmit) o16[produced] = (uint16_t)((e >> 16) & 0xffu);
+            off += e & 31u; produced++;
+            if ((int32_t)e2 < 0) { if (kEmit) o16[produced] = (uint16_t)((e2 >> 16) & 0xffu); off += e2 & 31u; produced++; }
+            continue;
+        }
+        end_wi = wi; end_off = off;
+        if (!(e & 0x8000u)) {
+            if (ent_kind(e) == kEob && ent_len(e) != 0) { end_off = off + ent_len(e); eob = true; }
+            break;
+        }
+        const uint32_t tot = (e >> 5) & 31u;
+        const uint32_t mlen = (e >> 16) + __funnelshift_r(win & ((1u << tot) - 1u), 0u, e);
+        off += tot;
+        if (off >= 32) { off -= 32; lo = hi; hi = nxt; wi++; nxt = __ldg(words + wi + 2); }
+        const uint32_t dwin = __funnelshift_r(lo, hi, off);
+        const uint32_t de = dtab[dwin & (kDistSize - 1)];
+        const uint32_t dtot = (de >> 5) & 31u;
+        const uint32_t dist = (de >> 16) + __funnelshift_r(dwin & ((1u << dtot) - 1u), 0u, de);
+        if (!(de & 0x8000u) || (uint64_t)dist > back_known + produced) break;
+        off += dtot;
+        if (kEmit) {
+            __syncwarp();
+            const int64_t src0 = (int64_t)(produced0 + produced) - (int64_t)dist;      // relative to the segment start
+            uint16_t* d = o16 + produced;
+            if (dist >= mlen) {
+                for (uint32_t i = lane; i < mlen; i += 32) {
+                    const int64_t q = src0 + i;
+                    d[i] = q >= 0 ? out[q] : (uint16_t)(0x8000u | (uint32_t)(q + (int64_t)kWindow32));
+                }
+            } else {
+                for (uint32_t i = lane; i < mlen; i += 32) {
+                    const int64_t q = src0 + (i % dist);
+                    d[i] = q >= 0 ? out[q] : (uint16_t)(0x8000u | (uint32_t)(q + (int64_t)kWindow32));
+                }
+            }
+            __syncwarp();
+        }
+        produced += mlen;
+        if (produced > p_lim) { end_wi = wi; end_off = off; break; }
+    }
+    produced_io = produced0 + produced;
+    seek_bits(b, in, b.used + ((uint64_t)(end_wi - wi0) * 32u + end_off - off0));
+    return eob;
 }
 
 // kEmit == false: count only.  kEmit == true: 16-bit symbols to sym[sd.out_off ...), exactly sd.out_len of them.
@@ -906,9 +992,10 @@ __device__ void seg_decode(const uint8_t* in, uint64_t in_len, const SegDesc sd,
         }
         if (build_table(t->lens, nlen, 1, t->lit, kLitBits, t->lit_sorted, t->lit_count, t, &t->lit_max)) break;
         if (build_table(t->lens + nlen, ndist, 2, t->dist, kDistBits, t->dist_sorted, t->dist_count, t, &t->dist_max)) break;
-        // ---- symbols of the block ----
+        // ---- symbols of the block: the lean loop while both buffers have room, one careful symbol whenever it stops ----
         bool bad = false;
         for (;;) {
+            if (seg_fast<kEmit>(b, t, in, out, produced, sd.out_len, first_seg)) break;
             refill(b);
             uint32_t e = t->lit[peek(b, kLitBits)];
             const uint32_t len = ent_len(e);
