@@ -215,6 +215,35 @@ def test_inflate_get_header(gpu_lib):
     gpu_lib.dll.inflateEnd(C.byref(strm))
 
 
+def test_inflate_finish_whole_buffer_takes_parallel_decoder(gpu_lib):
+    """inflateInit + inflate(Z_FINISH) with the whole stream and the whole buffer -- uncompress() spelled out
+    (uncompr.c:26-61) -- decodes a chunked stream through the segment-parallel path: Z_STREAM_END, totals, adler and
+    avail_in as the reference leaves them (bytes after the trailer stay with the caller)."""
+    import ctypes as C
+    n = (6 << 20) + 77
+    data = gpu_lib.synth(n, kind=1, seed=31).tobytes()
+    rc, z = gpu_lib.compress2(data, 1)
+    assert rc == zb.Z_OK
+    for wbits, stream in ((15, z + b"trailing"), (-15, z[2:-4] + b"xy")):
+        strm = zb.z_stream()
+        assert gpu_lib.dll.inflateInit2_(C.byref(strm), wbits, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+        src = C.create_string_buffer(stream, len(stream))
+        out = C.create_string_buffer(n + 100)
+        strm.next_in, strm.avail_in, strm.next_out, strm.avail_out = C.addressof(src), len(stream), C.addressof(out), n + 100
+        gpu_lib.profile(True)
+        rc = gpu_lib.dll.inflate(C.byref(strm), zb.Z_FINISH)
+        rep = gpu_lib.profile_report()
+        gpu_lib.profile(False)
+        assert rc == zb.Z_STREAM_END and any("k_inflate_segments" in k for k in rep)
+        assert out.raw[:n] == data and strm.total_out == n and strm.avail_out == 100
+        extra = 8 if wbits > 0 else 2
+        assert strm.avail_in == extra and strm.total_in == len(stream) - extra
+        if wbits > 0:
+            assert strm.adler == zlib.adler32(data)
+        assert gpu_lib.dll.inflate(C.byref(strm), zb.Z_FINISH) == zb.Z_STREAM_END
+        gpu_lib.dll.inflateEnd(C.byref(strm))
+
+
 def test_inflate_prime(gpu_lib):
     """inflatePrime (inflate.c:128-142): the first bits of a raw deflate stream handed over as primed bits, the rest as
     bytes that start right after them, decode to the same output; priming is refused once input is pending."""

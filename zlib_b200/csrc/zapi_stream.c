@@ -42,7 +42,7 @@ struct internal_state {
     int trailer_done;
     /* ---- inflate ---- */
     zb200i_inflater *inf;
-    int inf_wrap, inf_done, inf_bad;
+    int inf_wrap, inf_done, inf_bad, inf_started;
     uLong inf_dict_id;
     /* gzip header capture for inflateGetHeader (inflate.c:634-759): a host-side shadow of the bytes the device skips */
     gz_headerp gz_head;
@@ -464,7 +464,7 @@ ZAPI int inflateReset(z_streamp strm)                           /* inflate.c:103
     strm->total_in = strm->total_out = 0;
     strm->msg = Z_NULL;
     strm->adler = 1;
-    s->inf_done = s->inf_bad = 0;
+    s->inf_done = s->inf_bad = s->inf_started = 0;
     s->gz_head = Z_NULL; s->gz_st = GZ_FIXED; s->gz_have = 0;
     return zb200i_inflate_reset(s->inf, s->inf_wrap) == 0 ? Z_OK : Z_STREAM_ERROR;
 }
@@ -565,6 +565,18 @@ ZAPI int inflate(z_streamp strm, int flush)                     /* inflate.c:554
     in0 = strm->avail_in; out0 = strm->avail_out;
     if (zb200i_inflate_mode(s->inf) == 8 /* awaiting dictionary */) { strm->adler = s->inf_dict_id; return Z_NEED_DICT; }
     if (out0 == 0 && in0 == 0) return Z_BUF_ERROR;
+    if (!s->inf_started && flush == Z_FINISH && s->inf_wrap <= 1 && in0 >= 65536u) {
+        /* uncompress() spelled out: the whole stream and the whole buffer in the first call */
+        if (zb200i_inflate_try_parallel(strm->next_in, in0, strm->next_out, out0, s->inf_wrap, &in_used, &out_len, &check) == 0) {
+            strm->next_in += in_used; strm->avail_in -= (uInt)in_used; strm->total_in += in_used;
+            strm->next_out += out_len; strm->avail_out -= (uInt)out_len; strm->total_out += out_len;
+            if (s->inf_wrap) strm->adler = check;
+            s->inf_started = s->inf_done = 1;
+            return Z_STREAM_END;
+        }
+        in_used = out_len = 0; check = 1;
+    }
+    s->inf_started = 1;
 
     rc = zb200i_inflate_run(s->inf, strm->next_in, in0, strm->next_out, out0, &in_used, &out_len, &status, &msg, &check);
     if (rc != Z_OK) { strm->msg = ERR_MSG(rc == Z_MEM_ERROR ? Z_MEM_ERROR : Z_STREAM_ERROR); return rc == Z_MEM_ERROR ? Z_MEM_ERROR : Z_STREAM_ERROR; }
@@ -592,6 +604,7 @@ ZAPI int inflateSetDictionary(z_streamp strm, const Bytef *dictionary, uInt dict
         uLong id = adler32(adler32(0L, Z_NULL, 0), dictionary, dictLength);
         if (id != s->inf_dict_id) return Z_DATA_ERROR;
     }
+    s->inf_started = 1;                                         /* so does the dictionary */
     return zb200i_inflate_set_dict(s->inf, dictionary, dictLength) == 0 ? Z_OK : Z_MEM_ERROR;
 }
 
@@ -659,6 +672,7 @@ ZAPI int inflatePrime(z_streamp strm, int bits, int value)     /* inflate.c:128-
 {
     if (strm == Z_NULL || strm->state == Z_NULL || strm->state->kind != KIND_INFLATE) return Z_STREAM_ERROR;
     if (bits > 16 || bits < 0) return Z_STREAM_ERROR;
+    strm->state->inf_started = 1;                               /* primed bits live in the streaming decoder */
     return zb200i_inflate_prime(strm->state->inf, bits, value) == 0 ? Z_OK : Z_STREAM_ERROR;
 }
 

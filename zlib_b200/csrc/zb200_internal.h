@@ -38,6 +38,11 @@ int  zb200i_inflate_mode(const zb200i_inflater *h);         /* InfMode of the de
 size_t zb200i_inflate_pending_input(const zb200i_inflater *h);
 const uint8_t *zb200i_inflate_pending_bytes(const zb200i_inflater *h);
 
+/* One call holding the whole stream and the whole output buffer: 0 = decoded by the segment-parallel decoder
+ * (wrap 0 raw / 1 zlib; *check = Adler-32 of the output), 1 = not taken, use the streaming decoder. */
+int  zb200i_inflate_try_parallel(const uint8_t *in, size_t in_len, uint8_t *out, size_t cap, int wrap,
+                                 size_t *in_used, size_t *out_len, uint32_t *check);
+
 const char *zb200i_inflate_msg(int msg);
 
 #ifdef __cplusplus

@@ -1180,7 +1180,7 @@ __global__ void __launch_bounds__(256) k_resolve_rest(const uint16_t* __restrict
 // Returns 0 when the stream was decoded here (*status, *out_len set), 1 when the caller should use the serial decoder
 // (no usable boundaries, a candidate that was not one, output that does not fit, damaged data), negative on CUDA errors.
 int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t* d_dst, uint64_t cap, int wrap,
-                            uint64_t* out_len, int32_t* status, cudaStream_t s)
+                            uint64_t* out_len, int32_t* status, cudaStream_t s, uint64_t* in_used = nullptr, uint32_t* adler = nullptr)
 {
     if (len < kParMinInput || (wrap != ZB200_WRAP_ZLIB && wrap != ZB200_WRAP_RAW)) return 1;
     uint64_t hdr = 0;
@@ -1261,12 +1261,40 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
     }
     *out_len = total;
     *status = ZB_OK;
+    if (in_used) *in_used = trailer_at + (wrap == ZB200_WRAP_ZLIB ? 4 : 0);
+    if (adler) *adler = sums[1];
     return 0;
 }
 
 }  // namespace zb
 
 using namespace zb;
+
+// inflate(strm, Z_FINISH) with the whole stream and the whole output buffer in one call -- what uncompress() is in the
+// reference (uncompr.c:26-61) -- may take the segment-parallel decoder.  0 = decoded, 1 = use the streaming decoder.
+extern "C" int zb200i_inflate_try_parallel(const uint8_t* in, size_t in_len, uint8_t* out, size_t cap, int wrap,
+                                           size_t* in_used, size_t* out_len, uint32_t* check)
+{
+    if (ensure_init() != 0 || in_len < kParMinInput) return 1;
+    Ctx* c = ctx_acquire_own();
+    if (!c) return 1;
+    cudaStream_t s = c->own_stream;
+    int r = 1;
+    do {
+        if (c->in.ensure(in_len + 64) != 0 || c->out.ensure(cap + 16) != 0) break;
+        if (cudaMemcpyAsync(c->in.p, in, in_len, cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); break; }
+        uint64_t got = 0, used = 0;
+        int32_t st = 0;
+        uint32_t adl = 1;
+        r = inflate_single_parallel(c, c->in.as<uint8_t>(), in_len, c->out.as<uint8_t>(), cap, wrap, &got, &st, s, &used, &adl);
+        if (r != 0) { cudaStreamSynchronize(s); r = 1; break; }
+        if (got && cudaMemcpyAsync(out, c->out.p, got, cudaMemcpyDeviceToHost, s) != cudaSuccess) { cudaGetLastError(); r = 1; break; }
+        if (cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); r = 1; break; }
+        *in_used = (size_t)used; *out_len = (size_t)got; *check = adl;
+    } while (0);
+    ctx_release(c, s);
+    return r;
+}
 
 // ---- one resumable stream behind zlib.h's inflate() ----
 struct zb200i_inflater {
