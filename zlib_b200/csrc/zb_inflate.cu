@@ -625,10 +625,10 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
             if (st->stored_left == 0) { seek_bits(b, in, b.used); mode = kModeBlock; }
             else stop = (c == ain) ? kShortIn : kShortOut;
         } else if (mode == kModeCodes) {
-            if (!streaming) {                             // batch path: lean loop, one careful symbol whenever it stops short
-                if (decode_fast(b, o, t, in) == kDone) { mode = kModeBlock; continue; }
-            }
-            stop = decode_block(b, o, t, st, streaming, !streaming);
+            // lean loop while both buffers have room, one careful symbol whenever it stops short (it leaves at symbol
+            // boundaries with the position and the output count up to date, so a z_stream fed piecewise can use it too)
+            if (decode_fast(b, o, t, in) == kDone) { mode = kModeBlock; continue; }
+            stop = decode_block(b, o, t, st, streaming, true);
             if (stop == kDone) { stop = kRunning; mode = kModeBlock; }
             else if (stop == kShortOut && st->copy_len) mode = kModeCopy;
         } else if (mode == kModeCopy) {
