@@ -265,3 +265,22 @@ def test_long_single_stream_fallbacks(gpu_lib, oracle):
     assert rc == zb.Z_DATA_ERROR
     rc, out = gpu_lib.uncompress(z2[:len(z2) * 2 // 3], n)      # truncated
     assert rc == zb.Z_DATA_ERROR
+
+
+def test_batch_with_a_few_long_streams(gpu_lib):
+    """A call with a handful of streams: the long chunked ones take the segment-parallel decoder one by one, the rest
+    (short, or without boundaries) share the batch kernel; positions, lengths and statuses line up, a damaged long stream
+    fails alone."""
+    datas = [gpu_lib.synth((4 << 20) + 1000 * i, kind=1, seed=60 + i).tobytes() for i in range(3)]
+    datas += [zhelpers.corpus(1, 5000, 3), zhelpers.corpus(3, 700000, 4), b""]
+    streams = [gpu_lib.compress2(d, 1 if i % 2 else 6)[1] for i, d in enumerate(datas[:3])]
+    streams += [zlib.compress(datas[3], 6), zlib.compress(datas[4], 6), zlib.compress(b"")]
+    order = [3, 0, 4, 1, 5, 2]
+    zs, ds = [streams[i] for i in order], [datas[i] for i in order]
+    (outs, st), par, ser = _used_parallel(gpu_lib, lambda: gpu_lib.inflate_batch(zs, [len(d) for d in ds]))
+    assert st == [0] * len(zs) and outs == ds and par and ser
+    bad = bytearray(zs[3])
+    bad[len(bad) // 3] ^= 0x10
+    outs, st = gpu_lib.inflate_batch(zs[:3] + [bytes(bad)] + zs[4:], [len(d) for d in ds])
+    assert st[3] == zb.Z_DATA_ERROR and [x for i, x in enumerate(st) if i != 3] == [0] * 5
+    assert [o for i, o in enumerate(outs) if i != 3] == [d for i, d in enumerate(ds) if i != 3]

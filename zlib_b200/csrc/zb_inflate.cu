@@ -794,6 +794,8 @@ __global__ void __launch_bounds__(1024) k_slide_history(uint8_t* arena, uint64_t
 struct SegDesc { uint64_t start, stop, out_off, out_len; };     // byte range of the segment's blocks; its place in the output
 struct SegResult { uint64_t out_len, end_bit; int32_t status, final; };   // status 0 = arrived exactly, 1 = missed, 2 = invalid data
 constexpr uint32_t kSegMinBytes = 16384;                        // candidates closer than this to the previous boundary are skipped
+constexpr size_t kParFewStreams = 8;                            // with more streams than this in a call, only the really long ones are tried
+constexpr size_t kParLongStream = 32u << 20;
 constexpr size_t kParMinInput = 64u << 10;                      // shorter streams are not worth the extra passes (one warp: ~15 MB/s)
 
 __global__ void k_find_markers(const uint8_t* __restrict__ in, uint64_t first, uint64_t len, uint32_t* __restrict__ count,
@@ -1562,24 +1564,10 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
         const size_t src_total = (size_t)src_off[n], dst_total = (size_t)dst_off[n];
         const bool src_on_host = src_total != 0 && classify(src) != kDevice;
         const bool dst_on_host = classify(dst) != kDevice;
-        // groups of consecutive streams
-        std::vector<size_t> cut(1, 0);
-        if (src_on_host || dst_on_host) {
-            for (size_t i = 1; i < n; i++)
-                if (dst_off[i] - dst_off[cut.back()] >= kInfGroupBytes) cut.push_back(i);
-        }
-        cut.push_back(n);
-        const size_t ng = cut.size() - 1;
-        if (ng > 1 && (c2 = ctx_acquire_own()) == nullptr) { rc = ZB_MEM_ERROR; break; }
-        if ((rc = c->ensure_aux((int)(2 * ng + 4))) != 0) break;
-        cudaStream_t s_in = c->aux[0], s_out = c->aux[1];
-        cudaEvent_t* ev_in = c->evs;
-        cudaEvent_t* ev_done = c->evs + ng;
         const uint8_t* d_src = (const uint8_t*)src;
         if (src_on_host || src_total == 0) {
             if ((rc = c->in.ensure(src_total + 64)) != 0) break;
             d_src = c->in.as<uint8_t>();
-            cudaStreamWaitEvent(s_in, c->idle, 0);               // the staging buffer may still be read by the previous borrower
         }
         uint8_t* d_dst = (uint8_t*)dst;
         if (dst_on_host) {
@@ -1587,27 +1575,51 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             d_dst = c->out.as<uint8_t>();
         }
         cudaError_t e = cudaSuccess;
-        bool staged = false;
-        if (n == 1 && src_off[1] - src_off[0] >= kParMinInput) {
-            // one long stream (uncompress() of a big buffer): try the segment-parallel decoder; the serial one is the fallback
-            const uint64_t a = src_off[0], len = src_off[1] - a;
-            if (src_on_host) {
-                e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + a, len, cudaMemcpyHostToDevice, s);
-                if (e != cudaSuccess) { set_error("input staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
-                staged = true;
-            }
-            uint64_t got = 0;
-            int32_t st = ZB_OK;
-            const int pr = inflate_single_parallel(c, d_src + a, len, d_dst + dst_off[0], dst_off[1] - dst_off[0], wrap, &got, &st, s);
-            if (pr < 0) { rc = pr; break; }
-            if (pr == 0) {
-                if (dst_on_host && got) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[0], d_dst + dst_off[0], got, cudaMemcpyDeviceToHost, s);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        // ---- long streams first: a stream of its own is serial (one warp, ~15 MB/s), so the few long ones of a call --
+        // uncompress() of a big buffer is the case n == 1 -- try the segment-parallel decoder; whatever it does not take
+        // stays in the batch below.  Many medium streams are better off side by side in the batch kernel.
+        std::vector<uint8_t> handled(n, 0);
+        size_t nhandled = 0;
+        if (wrap == ZB200_WRAP_ZLIB || wrap == ZB200_WRAP_RAW) {
+            for (size_t i = 0; i < n && !rc; i++) {
+                const uint64_t a = src_off[i], len = src_off[i + 1] - a;
+                if (len < kParMinInput || (n > kParFewStreams && len < kParLongStream)) continue;
+                if (src_on_host) {
+                    e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + a, len, cudaMemcpyHostToDevice, s);
+                    if (e != cudaSuccess) { set_error("input staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+                }
+                uint64_t got = 0;
+                int32_t st = ZB_OK;
+                const int pr = inflate_single_parallel(c, d_src + a, len, d_dst + dst_off[i], dst_off[i + 1] - dst_off[i], wrap, &got, &st, s);
+                if (pr < 0) { rc = pr; break; }
+                if (pr != 0) continue;
+                if (dst_on_host && got) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[i], d_dst + dst_off[i], got, cudaMemcpyDeviceToHost, s);
                 if (e != cudaSuccess) { set_error("inflate readback failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
-                dst_len[0] = got; status[0] = st;
-                break;
+                dst_len[i] = got; status[i] = st;
+                handled[i] = 1; nhandled++;
             }
+            if (rc) { cudaStreamSynchronize(s); break; }
         }
+        if (nhandled == n) {
+            if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("inflate readback failed: %s", cudaGetErrorString(cudaGetLastError())); rc = ZB_STREAM_ERROR; }
+            break;
+        }
+        // ---- groups of consecutive streams that are still to do ----
+        std::vector<size_t> g0, g1;                              // group k = streams [g0[k], g1[k])
+        const bool pipelined = src_on_host || dst_on_host;
+        for (size_t i = 0; i < n;) {
+            if (handled[i]) { i++; continue; }
+            size_t j = i + 1;
+            while (j < n && !handled[j] && !(pipelined && dst_off[j] - dst_off[i] >= kInfGroupBytes)) j++;
+            g0.push_back(i); g1.push_back(j);
+            i = j;
+        }
+        const size_t ng = g0.size();
+        if (ng > 1 && (c2 = ctx_acquire_own()) == nullptr) { rc = ZB_MEM_ERROR; break; }
+        if ((rc = c->ensure_aux((int)(2 * ng + 4))) != 0) break;
+        cudaStream_t s_in = c->aux[0], s_out = c->aux[1];
+        cudaEvent_t* ev_in = c->evs;
+        cudaEvent_t* ev_done = c->evs + ng;
         // descriptors: [src_off n+1][dst_off n+1][dst_len n][status n][gzip trailer values 3n]
         const size_t desc_bytes = (size_t)(3 * n + 2) * 8 + n * 4 + n * 12;
         if ((rc = c->ws[0].ensure(desc_bytes)) != 0) break;
@@ -1616,19 +1628,23 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
         uint64_t* d_len = d_dst_off + (n + 1);
         int32_t* d_status = (int32_t*)(d_len + n);
         uint32_t* d_expect = (uint32_t*)(d_status + n);
+        if ((rc = c->ensure_pinned(n * 12 + 16)) != 0) break;
+        uint64_t* h_len = (uint64_t*)c->pinned;
+        int32_t* h_status = (int32_t*)(h_len + n);
         e = cudaMemcpyAsync(d_src_off, src_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_dst_off, dst_off, (n + 1) * 8, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess && c2) {                            // the second stream starts once the descriptors are up
+        if (e == cudaSuccess) {                                  // the copy streams and the second decode stream start here
             e = cudaEventRecord(c->evs[2 * ng], s);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(c2->own_stream, c->evs[2 * ng], 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s_in, c->evs[2 * ng], 0);
+            if (e == cudaSuccess && c2) e = cudaStreamWaitEvent(c2->own_stream, c->evs[2 * ng], 0);
         }
         if (e != cudaSuccess) { set_error("descriptor upload failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         cudaStream_t s_main = s;
         for (size_t k = 0; k < ng && !rc; k++) {
-            const size_t i0 = cut[k], i1 = cut[k + 1];
+            const size_t i0 = g0[k], i1 = g1[k];
             const uint64_t a = src_off[i0], b = src_off[i1];
             cudaStream_t s = (c2 && (k & 1)) ? c2->own_stream : s_main;
-            if (src_on_host && b > a && !staged) {
+            if (src_on_host && b > a) {
                 e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + a, b - a, cudaMemcpyHostToDevice, s_in);
                 if (e == cudaSuccess) e = cudaEventRecord(ev_in[k], s_in);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev_in[k], 0);
@@ -1636,23 +1652,26 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             }
             if ((rc = inflate_batch_launch(d_src, d_src_off + i0, i1 - i0, d_dst, d_dst_off + i0, d_len + i0, d_status + i0, wrap,
                                            d_expect + 3 * i0, s)) != 0) break;
-            if (dst_on_host && dst_off[i1] > dst_off[i0]) {
+            // results go to pinned memory (a copy to the caller's pageable arrays would block the host until this group is done)
+            e = cudaMemcpyAsync(h_len + i0, d_len + i0, (i1 - i0) * 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_status + i0, d_status + i0, (i1 - i0) * 4, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && dst_on_host && dst_off[i1] > dst_off[i0]) {
                 e = cudaEventRecord(ev_done[k], s);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, ev_done[k], 0);
                 if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[i0], d_dst + dst_off[i0], dst_off[i1] - dst_off[i0], cudaMemcpyDeviceToHost, s_out);
-                if (e != cudaSuccess) { set_error("output copy failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
             }
+            if (e != cudaSuccess) { set_error("output copy failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         }
         if (c2) {                                                // join the second stream
             cudaEventRecord(c->evs[2 * ng + 1], c2->own_stream);
             cudaStreamWaitEvent(s, c->evs[2 * ng + 1], 0);
         }
         if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(s_in); cudaStreamSynchronize(s_out); break; }
-        e = cudaMemcpyAsync(dst_len, d_len, n * 8, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        e = cudaStreamSynchronize(s);
         if (e == cudaSuccess && dst_on_host) e = cudaStreamSynchronize(s_out);
         if (e != cudaSuccess) { set_error("inflate batch readback failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        for (size_t k = 0; k < ng; k++)
+            for (size_t i = g0[k]; i < g1[k]; i++) { dst_len[i] = h_len[i]; status[i] = h_status[i]; }
     } while (0);
     if (c2) ctx_release(c2, c2->own_stream);
     ctx_release(c, s);
