@@ -232,8 +232,8 @@ def test_long_single_stream_decodes_in_parallel(gpu_lib, oracle):
 def test_long_single_stream_fallbacks(gpu_lib, oracle):
     """What the parallel scheme must leave to the serial decoder: no boundaries at all, the marker pattern occurring as
     DATA (inside stored blocks), and damage -- results and return codes are those of the reference's uncompress()."""
-    data = zhelpers.corpus(1, 1500000, 9)
-    z = zlib.compress(data, 6)                                  # one block sequence, no flush points
+    data = zhelpers.corpus(0, 300000, 9)                        # noise: stored blocks only, nothing to find
+    z = zlib.compress(data, 6)
     (rc, out), par, ser = _used_parallel(gpu_lib, lambda: gpu_lib.uncompress(z, len(data)))
     assert rc == zb.Z_OK and out == data and ser
     # level 0: the stream shows its input, so 00 00 FF FF in the input is a false candidate every time
@@ -284,3 +284,28 @@ def test_batch_with_a_few_long_streams(gpu_lib):
     outs, st = gpu_lib.inflate_batch(zs[:3] + [bytes(bad)] + zs[4:], [len(d) for d in ds])
     assert st[3] == zb.Z_DATA_ERROR and [x for i, x in enumerate(st) if i != 3] == [0] * 5
     assert [o for i, o in enumerate(outs) if i != 3] == [d for i, d in enumerate(ds) if i != 3]
+
+
+def test_long_stream_without_flush_points_uses_the_block_finder(gpu_lib, oracle):
+    """The reference's own one-shot output (config 1's direction (b)): no markers, so block starts are FOUND -- every bit
+    position that could open a non-final dynamic block is probed, survivors are checked with the decoder's own header
+    code, and the counting pass keeps the ones the true decode arrives at.  Levels 1, 6, 9 of system zlib and the CPU
+    oracle's streams decode bit-exact through the parallel path."""
+    n = 12 << 20
+    data = gpu_lib.synth(n, kind=1, seed=41).tobytes()
+    for z in (zlib.compress(data, 1), zlib.compress(data, 6), zlib.compress(data[:4 << 20], 9), oracle.deflate(data[: 6 << 20], 6)):
+        want = zlib.decompress(z)
+        (rc, out), par, ser = _used_parallel(gpu_lib, lambda: gpu_lib.uncompress(z, len(want)))
+        assert rc == zb.Z_OK and out == want and par and not ser
+    # text only (long dynamic blocks), raw wrap
+    text = gpu_lib.synth(8 << 20, kind=0, seed=42).tobytes()
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    zr = co.compress(text) + co.flush()
+    outs, st = gpu_lib.inflate_batch([zr], [len(text)], wrap=zb.WRAP_RAW)
+    assert st == [0] and outs[0] == text
+    # damage in such a stream still comes out as the reference's error
+    bad = bytearray(zlib.compress(data[:3 << 20], 6))
+    bad[len(bad) // 2] ^= 0x04
+    rc, out = gpu_lib.uncompress(bytes(bad), 3 << 20)
+    want_rc, _, _ = oracle.inflate(bytes(bad), 3 << 20)
+    assert rc == want_rc and rc != zb.Z_OK

@@ -791,9 +791,9 @@ __global__ void __launch_bounds__(1024) k_slide_history(uint8_t* arena, uint64_t
 //   tails    one CTA walks the segments in order and resolves the last 32 KiB of each against the 32 KiB in front of it
 //            (already final by then): the only sequential part, ~64 KiB of traffic per segment;
 //   rest     every other symbol of every segment resolves in parallel against the final bytes in front of its segment.
-struct SegDesc { uint64_t start, stop, out_off, out_len; };     // byte range of the segment's blocks; its place in the output
-struct SegResult { uint64_t out_len, end_bit; int32_t status, final; };   // status 0 = arrived exactly, 1 = missed, 2 = invalid data
-constexpr uint32_t kSegMinBytes = 16384;                        // candidates closer than this to the previous boundary are skipped
+struct SegDesc { uint64_t start, stop, out_off, out_len; };     // BIT range of the segment's blocks; its place in the output
+struct SegResult { uint64_t out_len, end_bit; int32_t status, final; uint32_t arrive, pad; };   // status 0 = ok, 1 = missed, 2 = invalid data
+constexpr uint64_t kSegMinOut = 128u << 10;                     // accepted segments are merged up to this much output (less for short streams)
 constexpr size_t kParFewStreams = 8;                            // with more streams than this in a call, only the really long ones are tried
 constexpr size_t kParLongStream = 32u << 20;
 constexpr size_t kParMinInput = 64u << 10;                      // shorter streams are not worth the extra passes (one warp: ~15 MB/s)
@@ -808,6 +808,54 @@ __global__ void k_find_markers(const uint8_t* __restrict__ in, uint64_t first, u
             if (k < cap) pos[k] = p + 4;
         }
     }
+}
+
+// Header of a dynamic block (inflate.c:837-949) into t->lens: HLIT / HDIST / HCLEN, the code-length code, the run-length
+// coded lengths.  All lanes run it; false on anything the reference rejects (or on running out of input).
+__device__ bool seg_read_dynamic(Bits& b, WarpTables* t, int& nlen, int& ndist)
+{
+    const int lane = threadIdx.x & 31;
+    if (!have(b, 14)) return false;
+    refill(b);
+    nlen = (int)peek(b, 5) + 257; drop(b, 5);
+    ndist = (int)peek(b, 5) + 1; drop(b, 5);
+    const int ncode = (int)peek(b, 4) + 4; drop(b, 4);
+    if (nlen > 286 || ndist > 30) return false;
+    if (lane < 20) t->cl_lens[lane] = 0;
+    __syncwarp();
+    if (!have(b, 3 * ncode)) return false;
+    for (int i = 0; i < ncode; i++) {
+        refill(b);
+        const uint32_t v = peek(b, 3); drop(b, 3);
+        if (lane == 0) t->cl_lens[c_cl_order[i]] = (uint8_t)v;
+    }
+    __syncwarp();
+    if (build_table(t->cl_lens, 19, 0, t->dist, kClBits, nullptr, t->dist_count, t, &t->dist_max)) return false;
+    __syncwarp();
+    const int cl_max = t->dist_max, total = nlen + ndist;
+    int idx = 0;
+    uint32_t prev = 0;
+    while (idx < total) {
+        refill(b);
+        uint32_t s;
+        if (cl_max == 0) { if (!have(b, 1)) return false; drop(b, 1); s = 0; }
+        else {
+            const uint32_t e = t->dist[peek(b, kClBits)];
+            const int l = (int)ent_len(e);
+            if (l == 0 || !have(b, l)) return false;
+            drop(b, l); s = ent_val(e);
+        }
+        if (s < 16) { if (lane == 0) t->lens[idx] = (uint8_t)s; prev = s; idx++; continue; }
+        uint32_t rep, val = 0;
+        if (s == 16) { if (!have(b, 2) || idx == 0) return false; val = prev; rep = 3 + peek(b, 2); drop(b, 2); }
+        else if (s == 17) { if (!have(b, 3)) return false; rep = 3 + peek(b, 3); drop(b, 3); }
+        else { if (!have(b, 7)) return false; rep = 11 + peek(b, 7); drop(b, 7); }
+        if (idx + (int)rep > total) return false;
+        store_lens(t, idx, (int)rep, (uint8_t)val);
+        idx += (int)rep; prev = val;
+    }
+    __syncwarp();
+    return true;
 }
 
 // The lean in-bounds loop of decode_fast for a segment: same bit handling, but the output is counted (kEmit == false)
@@ -897,25 +945,35 @@ __device__ bool seg_fast(Bits& b, const WarpTables* t, const uint8_t* in, uint16
 }
 
 // kEmit == false: count only.  kEmit == true: 16-bit symbols to sym[sd.out_off ...), exactly sd.out_len of them.
+// Count mode also gets the sorted list of ALL candidate positions: the decoder stops at the first one it arrives at (at the
+// end of a block) and reports its index -- a candidate that is not a block boundary of the true decode is simply never
+// arrived at.  Emit mode stops at sd.stop.
 template <bool kEmit>
 __device__ void seg_decode(const uint8_t* in, uint64_t in_len, const SegDesc sd, bool first_seg, bool last_seg,
-                           uint16_t* __restrict__ sym, WarpTables* t, SegResult* res)
+                           uint16_t* __restrict__ sym, WarpTables* t, SegResult* res, const uint64_t* __restrict__ cand,
+                           uint32_t ncand, uint32_t self)
 {
     const int lane = threadIdx.x & 31;
     Bits b;
     b.words = reinterpret_cast<const uint32_t*>((uintptr_t)in & ~(uintptr_t)3);
     b.nwords = (uint32_t)(((((uintptr_t)in + in_len + 3) & ~(uintptr_t)3) - (uintptr_t)b.words) >> 2);
     b.total = in_len * 8;
-    seek_bits(b, in, sd.start * 8);
+    seek_bits(b, in, sd.start);
     uint16_t* out = kEmit ? sym + sd.out_off : nullptr;
     uint64_t produced = 0;
     int status = 2, last = 0;
+    uint32_t nx = self + 1, arrive = 0xffffffffu;
     for (;;) {
         // ---- at a block boundary ----
-        if (last) { status = last_seg ? 0 : 1; break; }
-        if (!last_seg) {
-            if (b.used == sd.stop * 8) { status = 0; break; }
-            if (b.used > sd.stop * 8) { status = 1; break; }
+        if (last) { status = (kEmit && !last_seg) ? 1 : 0; break; }
+        if (kEmit) {
+            if (!last_seg) {
+                if (b.used == sd.stop) { status = 0; break; }
+                if (b.used > sd.stop) { status = 1; break; }
+            }
+        } else if (b.used != sd.start) {
+            while (nx < ncand && cand[nx] < b.used) nx++;
+            if (nx < ncand && cand[nx] == b.used) { arrive = nx; status = 0; break; }
         }
         if (!have(b, 3)) break;
         refill(b);
@@ -948,50 +1006,7 @@ __device__ void seg_decode(const uint8_t* in, uint64_t in_len, const SegDesc sd,
             store_lens(t, 0, 144, 8); store_lens(t, 144, 112, 9); store_lens(t, 256, 24, 7);
             store_lens(t, 280, 8, 8); store_lens(t, 288, 32, 5);
             __syncwarp();
-        } else {                                                // dynamic, inflate.c:837-949
-            if (!have(b, 14)) break;
-            refill(b);
-            nlen = (int)peek(b, 5) + 257; drop(b, 5);
-            ndist = (int)peek(b, 5) + 1; drop(b, 5);
-            const int ncode = (int)peek(b, 4) + 4; drop(b, 4);
-            if (nlen > 286 || ndist > 30) break;
-            if (lane < 20) t->cl_lens[lane] = 0;
-            __syncwarp();
-            if (!have(b, 3 * ncode)) break;
-            for (int i = 0; i < ncode; i++) {
-                refill(b);
-                const uint32_t v = peek(b, 3); drop(b, 3);
-                if (lane == 0) t->cl_lens[c_cl_order[i]] = (uint8_t)v;
-            }
-            __syncwarp();
-            if (build_table(t->cl_lens, 19, 0, t->dist, kClBits, nullptr, t->dist_count, t, &t->dist_max)) break;
-            __syncwarp();
-            const int cl_max = t->dist_max, total = nlen + ndist;
-            int idx = 0;
-            bool bad = false;
-            uint32_t prev = 0;
-            while (idx < total) {
-                refill(b);
-                uint32_t s;
-                if (cl_max == 0) { if (!have(b, 1)) { bad = true; break; } drop(b, 1); s = 0; }
-                else {
-                    const uint32_t e = t->dist[peek(b, kClBits)];
-                    const int l = (int)ent_len(e);
-                    if (l == 0 || !have(b, l)) { bad = true; break; }
-                    drop(b, l); s = ent_val(e);
-                }
-                if (s < 16) { if (lane == 0) t->lens[idx] = (uint8_t)s; prev = s; idx++; continue; }
-                uint32_t rep, val = 0;
-                if (s == 16) { if (!have(b, 2) || idx == 0) { bad = true; break; } val = prev; rep = 3 + peek(b, 2); drop(b, 2); }
-                else if (s == 17) { if (!have(b, 3)) { bad = true; break; } rep = 3 + peek(b, 3); drop(b, 3); }
-                else { if (!have(b, 7)) { bad = true; break; } rep = 11 + peek(b, 7); drop(b, 7); }
-                if (idx + (int)rep > total) { bad = true; break; }
-                store_lens(t, idx, (int)rep, (uint8_t)val);
-                idx += (int)rep; prev = val;
-            }
-            if (bad) break;
-            __syncwarp();
-        }
+        } else if (!seg_read_dynamic(b, t, nlen, ndist)) break;     // dynamic, inflate.c:837-949
         if (build_table(t->lens, nlen, 1, t->lit, kLitBits, t->lit_sorted, t->lit_count, t, &t->lit_max)) break;
         if (build_table(t->lens + nlen, ndist, 2, t->dist, kDistBits, t->dist_sorted, t->dist_count, t, &t->dist_max)) break;
         // ---- symbols of the block: the lean loop while both buffers have room, one careful symbol whenever it stops ----
@@ -1052,18 +1067,19 @@ __device__ void seg_decode(const uint8_t* in, uint64_t in_len, const SegDesc sd,
         }
         if (bad) break;
     }
-    if (lane == 0) { res->out_len = produced; res->end_bit = b.used; res->status = status; res->final = last; }
+    if (lane == 0) { res->out_len = produced; res->end_bit = b.used; res->status = status; res->final = last; res->arrive = arrive; res->pad = 0; }
 }
 
 template <bool kEmit>
 __global__ void __launch_bounds__(kInfWarps * 32)
 k_inflate_segments(const uint8_t* __restrict__ in, uint64_t in_len, const SegDesc* __restrict__ segs, uint32_t nseg,
-                   uint16_t* __restrict__ sym, SegResult* __restrict__ res)
+                   uint16_t* __restrict__ sym, SegResult* __restrict__ res, const uint64_t* __restrict__ cand)
 {
     __shared__ WarpTables s_tab[kInfWarps];
     const uint32_t j = blockIdx.x * kInfWarps + (threadIdx.x >> 5);
     if (j >= nseg) return;
-    seg_decode<kEmit>(in, in_len, segs[j], j == 0, j == nseg - 1, sym, &s_tab[threadIdx.x >> 5], &res[j]);
+    if (kEmit) seg_decode<true>(in, in_len, segs[j], j == 0, j == nseg - 1, sym, &s_tab[threadIdx.x >> 5], &res[j], nullptr, 0, 0);
+    else seg_decode<false>(in, in_len, SegDesc{cand[j], 0, 0, 0}, j == 0, false, nullptr, &s_tab[threadIdx.x >> 5], &res[j], cand, nseg, j);
 }
 
 // The sequential part: segment by segment, the last 32 KiB of symbols become bytes; a window symbol reads the 32 KiB in
@@ -1179,8 +1195,72 @@ __global__ void __launch_bounds__(256) k_resolve_rest(const uint16_t* __restrict
     }
 }
 
+// ---- block finder: for streams without markers (the reference's own one-shot output) ----
+// Stage 1, a thread per BIT position: could a non-final dynamic block start here?  BFINAL = 0, BTYPE = 10, HLIT <= 29,
+// HDIST <= 29, and the code-length code complete (Kraft sum exactly one: inftrees.c:130-138 rejects anything else).
+// Stage 2, a warp per survivor: the whole header the way the decoder reads it -- both codes must build and the block
+// must be able to end (a length for symbol 256).  What passes both is almost always a real block start; what is not is
+// never ARRIVED AT by the counting pass and drops out there.
+__global__ void k_find_blocks_probe(const uint8_t* __restrict__ in, uint64_t in_len, uint64_t first_bit, uint64_t last_bit,
+                                    uint32_t* __restrict__ count, uint64_t* __restrict__ pos, uint32_t cap)
+{
+    const uint32_t* words = reinterpret_cast<const uint32_t*>((uintptr_t)in & ~(uintptr_t)3);
+    const uint64_t skew = ((uintptr_t)in & 3) * 8;
+    const uint64_t nwords = ((((uintptr_t)in + in_len + 3) & ~(uintptr_t)3) - (uintptr_t)words) >> 2;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = first_bit + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < last_bit; p += stride) {
+        const uint64_t q = p + skew, wi = q >> 5;
+        const uint32_t sh = (uint32_t)q & 31;
+        if (wi + 3 >= nwords) continue;
+        const uint32_t w0 = __ldg(words + wi), w1 = __ldg(words + wi + 1);
+        const uint32_t lo = __funnelshift_r(w0, w1, sh);
+        if ((lo & 7u) != 4u) continue;                          // BFINAL 0, BTYPE 2
+        if (((lo >> 3) & 31u) > 29u || ((lo >> 8) & 31u) > 29u) continue;
+        const uint32_t w2 = __ldg(words + wi + 2), w3 = __ldg(words + wi + 3);
+        const uint64_t mid = ((uint64_t)__funnelshift_r(w2, w3, sh) << 32) | __funnelshift_r(w1, w2, sh);   // bits 32..95
+        const int ncode = (int)((lo >> 13) & 15u) + 4;
+        uint64_t bits = ((uint64_t)(lo >> 17)) | (mid << 15);   // from bit 17 on: 15 bits of lo, then mid (64 - 15 = 49 more)
+        uint32_t kraft = 0;
+        // 3 * 19 = 57 bits <= 64 available
+#pragma unroll
+        for (int i = 0; i < 19; i++) {
+            const uint32_t l = (uint32_t)(bits >> (3 * i)) & 7u;
+            if (i < ncode && l) kraft += 128u >> l;
+        }
+        if (kraft != 128u) continue;
+        const uint32_t k = atomicAdd(count, 1u);
+        if (k < cap) pos[k] = p;
+    }
+}
+
+__global__ void __launch_bounds__(kInfWarps * 32)
+k_find_blocks_check(const uint8_t* __restrict__ in, uint64_t in_len, const uint64_t* __restrict__ probe, uint32_t nprobe,
+                    uint32_t* __restrict__ count, uint64_t* __restrict__ pos, uint32_t cap)
+{
+    __shared__ WarpTables s_tab[kInfWarps];
+    const uint32_t j = blockIdx.x * kInfWarps + (threadIdx.x >> 5);
+    if (j >= nprobe) return;
+    WarpTables* t = &s_tab[threadIdx.x >> 5];
+    Bits b;
+    b.words = reinterpret_cast<const uint32_t*>((uintptr_t)in & ~(uintptr_t)3);
+    b.nwords = (uint32_t)(((((uintptr_t)in + in_len + 3) & ~(uintptr_t)3) - (uintptr_t)b.words) >> 2);
+    b.total = in_len * 8;
+    seek_bits(b, in, probe[j]);
+    refill(b);
+    drop(b, 3);
+    int nlen = 0, ndist = 0;
+    if (!seg_read_dynamic(b, t, nlen, ndist)) return;
+    if (t->lens[256] == 0) return;                              // no end-of-block code: not a block a compressor wrote
+    if (build_table(t->lens, nlen, 1, t->lit, kLitBits, t->lit_sorted, t->lit_count, t, &t->lit_max)) return;
+    if (build_table(t->lens + nlen, ndist, 2, t->dist, kDistBits, t->dist_sorted, t->dist_count, t, &t->dist_max)) return;
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t k = atomicAdd(count, 1u);
+        if (k < cap) pos[k] = probe[j];
+    }
+}
+
 // Returns 0 when the stream was decoded here (*status, *out_len set), 1 when the caller should use the serial decoder
-// (no usable boundaries, a candidate that was not one, output that does not fit, damaged data), negative on CUDA errors.
+// (no usable boundaries, output that does not fit, damaged data), negative on CUDA errors.
 int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t* d_dst, uint64_t cap, int wrap,
                             uint64_t* out_len, int32_t* status, cudaStream_t s, uint64_t* in_used = nullptr, uint32_t* adler = nullptr)
 {
@@ -1193,54 +1273,93 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
         if (((h2[0] << 8) + h2[1]) % 31 || (h2[0] & 15) != 8 || (h2[0] >> 4) + 8 > 15 || (h2[1] & 0x20)) return 1;
         hdr = 2;
     }
-    const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(len / 1024 + 16, 1u << 22);
+    const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(len / 32 + 4096, 1u << 26);
     int rc;
     if ((rc = c->small.ensure(256)) != 0) return rc;
     if ((rc = c->ws[1].ensure((size_t)cand_cap * 8 + 64)) != 0) return rc;
+    if ((rc = c->ws[5].ensure((size_t)cand_cap * 8 + 64)) != 0) return rc;
     uint32_t* d_count = c->small.as<uint32_t>() + 16;
     uint32_t* d_err = d_count + 1;
     uint64_t* d_pos = c->ws[1].as<uint64_t>();
-    ZB_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
-    ZB_LAUNCH(k_find_markers, kSMs * 8, 256, 0, s, d_src, hdr, len, d_count, d_pos, cand_cap);
-    uint32_t ncand = 0;
-    ZB_CUDA(cudaMemcpyAsync(&ncand, d_count, 4, cudaMemcpyDeviceToHost, s));
-    ZB_CUDA(cudaStreamSynchronize(s));
-    if (ncand == 0 || ncand > cand_cap) return 1;
-    std::vector<uint64_t> pos(ncand);
-    ZB_CUDA(cudaMemcpyAsync(pos.data(), d_pos, (size_t)ncand * 8, cudaMemcpyDeviceToHost, s));
-    ZB_CUDA(cudaStreamSynchronize(s));
-    std::sort(pos.begin(), pos.end());
+    uint64_t* d_probe = c->ws[5].as<uint64_t>();
+    std::vector<uint64_t> cand;
+    std::vector<SegResult> res;
     std::vector<SegDesc> segs;
-    segs.push_back(SegDesc{hdr, len, 0, 0});
-    for (uint64_t p : pos)
-        if (p >= segs.back().start + kSegMinBytes && p + 8 <= len) { segs.back().stop = p; segs.push_back(SegDesc{p, len, 0, 0}); }
+    uint64_t total = 0, final_end = 0;
+    // enough segments to fill the GPU with warps, not more than the sequential tail pass likes (3 us per segment)
+    const uint64_t seg_min = std::min<uint64_t>(kSegMinOut, std::max<uint64_t>(32768, len * 2 / 4096));
+    // Two sources of candidates, the cheap one first: sync markers (bytes), then block headers (bits).
+    for (int source = 0; source < 2 && segs.empty(); source++) {
+        uint32_t ncand = 0;
+        ZB_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+        if (source == 0) {
+            ZB_LAUNCH(k_find_markers, kSMs * 8, 256, 0, s, d_src, hdr, len, d_count, d_pos, cand_cap);
+        } else {
+            uint32_t nprobe = 0;
+            ZB_LAUNCH(k_find_blocks_probe, kSMs * 16, 256, 0, s, d_src, len, hdr * 8 + 1, len * 8, d_count, d_probe, cand_cap);
+            ZB_CUDA(cudaMemcpyAsync(&nprobe, d_count, 4, cudaMemcpyDeviceToHost, s));
+            ZB_CUDA(cudaStreamSynchronize(s));
+            if (nprobe == 0 || nprobe > cand_cap) return 1;
+            ZB_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+            ZB_LAUNCH(k_find_blocks_check, (nprobe + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s, d_src, len, d_probe, nprobe, d_count,
+                      d_pos, cand_cap);
+        }
+        ZB_CUDA(cudaMemcpyAsync(&ncand, d_count, 4, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaStreamSynchronize(s));
+        if (ncand == 0 || ncand > cand_cap) continue;
+        cand.assign((size_t)ncand + 1, 0);
+        ZB_CUDA(cudaMemcpyAsync(cand.data() + 1, d_pos, (size_t)ncand * 8, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaStreamSynchronize(s));
+        if (source == 0) for (size_t k = 1; k < cand.size(); k++) cand[k] *= 8;       // marker positions are bytes
+        cand[0] = hdr * 8;                                      // the stream's first block: the one certain boundary
+        std::sort(cand.begin() + 1, cand.end());
+        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+        while (!cand.empty() && cand.back() + 64 > len * 8) cand.pop_back();
+        const uint32_t nc = (uint32_t)cand.size();
+        if (nc < 2) continue;
+        // ---- count: every candidate decodes to the first candidate it arrives at ----
+        if ((rc = c->ws[3].ensure((size_t)nc * sizeof(SegResult))) != 0) return rc;
+        SegResult* d_res = c->ws[3].as<SegResult>();
+        ZB_CUDA(cudaMemcpyAsync(d_pos, cand.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, s));
+        ZB_LAUNCH((k_inflate_segments<false>), (nc + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s, d_src, len, (const SegDesc*)nullptr, nc,
+                  (uint16_t*)nullptr, d_res, d_pos);
+        res.resize(nc);
+        ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nc * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaStreamSynchronize(s));
+        // ---- the true decode's path through the candidates; short hops merge ----
+        bool ok = true;
+        uint64_t seg_out = 0, seg_start = cand[0];
+        total = 0;
+        for (uint32_t j = 0;;) {
+            const SegResult& r = res[j];
+            if (r.status != 0) { ok = false; break; }
+            seg_out += r.out_len;
+            if (r.final) { segs.push_back(SegDesc{seg_start, r.end_bit, total, seg_out}); total += seg_out; final_end = r.end_bit; break; }
+            if (r.arrive <= j || r.arrive >= nc) { ok = false; break; }
+            if (seg_out >= seg_min) {
+                segs.push_back(SegDesc{seg_start, cand[r.arrive], total, seg_out});
+                total += seg_out; seg_out = 0; seg_start = cand[r.arrive];
+            }
+            j = r.arrive;
+        }
+        if (!ok) return 1;                                      // damage on the true path: the serial decoder names it
+        if (segs.size() < 2) segs.clear();                      // nothing gained; try the other source
+    }
+    if (segs.empty()) return 1;
     const uint32_t nseg = (uint32_t)segs.size();
-    if (nseg < 2) return 1;
+    if (total > cap) return 1;                                  // the serial decoder reports Z_BUF_ERROR the reference's way
+    const uint64_t trailer_at = (final_end + 7) >> 3;
+    if (wrap == ZB200_WRAP_ZLIB && trailer_at + 4 > len) return 1;
+    // ---- emit, tails, rest ----
     if ((rc = c->ws[2].ensure((size_t)nseg * sizeof(SegDesc))) != 0) return rc;
     if ((rc = c->ws[3].ensure((size_t)nseg * sizeof(SegResult))) != 0) return rc;
+    if ((rc = c->ws[4].ensure((size_t)total * 2 + 64)) != 0) return rc;
     SegDesc* d_segs = c->ws[2].as<SegDesc>();
     SegResult* d_res = c->ws[3].as<SegResult>();
-    const unsigned blocks = (nseg + kInfWarps - 1) / kInfWarps;
-    // ---- count ----
-    ZB_CUDA(cudaMemcpyAsync(d_segs, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
-    ZB_LAUNCH(k_inflate_segments<false>, blocks, kInfWarps * 32, 0, s, d_src, len, d_segs, nseg, (uint16_t*)nullptr, d_res);
-    std::vector<SegResult> res(nseg);
-    ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nseg * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
-    ZB_CUDA(cudaStreamSynchronize(s));
-    uint64_t total = 0;
-    for (uint32_t j = 0; j < nseg; j++) {
-        if (res[j].status != 0 || (res[j].final != 0) != (j == nseg - 1)) return 1;
-        segs[j].out_off = total; segs[j].out_len = res[j].out_len;
-        total += res[j].out_len;
-    }
-    if (total > cap) return 1;                                  // the serial decoder reports Z_BUF_ERROR the reference's way
-    const uint64_t trailer_at = (res[nseg - 1].end_bit + 7) >> 3;
-    if (wrap == ZB200_WRAP_ZLIB && trailer_at + 4 > len) return 1;
-    // ---- decode, tails, rest ----
-    if ((rc = c->ws[4].ensure((size_t)total * 2 + 64)) != 0) return rc;
     uint16_t* d_sym = c->ws[4].as<uint16_t>();
     ZB_CUDA(cudaMemcpyAsync(d_segs, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
-    ZB_LAUNCH(k_inflate_segments<true>, blocks, kInfWarps * 32, 0, s, d_src, len, d_segs, nseg, d_sym, d_res);
+    ZB_LAUNCH((k_inflate_segments<true>), (nseg + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s, d_src, len, d_segs, nseg, d_sym, d_res,
+              (const uint64_t*)nullptr);
     ZB_LAUNCH(k_resolve_tails, kTailCtas, kTailThreads, 0, s, d_sym, d_dst, d_segs, nseg, d_err);
     ZB_LAUNCH(k_resolve_rest, nseg, 256, 0, s, d_sym, d_dst, d_segs, d_err);
     ZB_CHECK_LAUNCH();
@@ -1251,6 +1370,7 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
         ZB_CUDA(cudaMemcpyAsync(sums, c->small.p, 8, cudaMemcpyDeviceToHost, s));
         ZB_CUDA(cudaMemcpyAsync(tr, d_src + trailer_at, 4, cudaMemcpyDeviceToHost, s));
     }
+    res.resize(nseg);
     ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nseg * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaMemcpyAsync(&nerr, d_err, 4, cudaMemcpyDeviceToHost, s));
     ZB_CUDA(cudaStreamSynchronize(s));
