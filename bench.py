@@ -465,6 +465,33 @@ def main():
         extra["uncompress_one_stream"] = {"GBps": round(n / min(tu) / 1e9, 3), "ms": round(min(tu) * 1e3, 1), "stream_bytes": zlen1,
                                           "host_buffers": "pinned", "round_trip_exact": rt_ok}
         lib.dll.zb200_free_pinned(C.c_void_p(pin_rt))
+        # BASELINE config 1, direction (b): ONE 64 MiB text buffer compressed by the REFERENCE at level 6 (no flush points in
+        # that stream: block starts are found), decoded by uncompress() of this library; the reference's own uncompress beside it
+        if os.path.exists(zhelpers.REF_PATH):
+            n1 = 64 << 20
+            text = lib.synth(n1, kind=0, seed=7)
+            refz = zhelpers.Ref()
+            t0 = time.perf_counter()
+            z1 = refz.compress2(text, 6)
+            t_refc = time.perf_counter() - t0
+            ob = C.create_string_buffer(n1)
+            ul = C.c_ulong(n1)
+            t0 = time.perf_counter()
+            assert refz.dll.uncompress(ob, C.byref(ul), z1, len(z1)) == 0
+            t_refu = time.perf_counter() - t0
+            tz = []
+            for _ in range(3):
+                ul = C.c_ulong(n1)
+                t0 = time.perf_counter()
+                rc = lib.dll.uncompress(ob, C.byref(ul), z1, len(z1))
+                tz.append(time.perf_counter() - t0)
+                assert rc == 0 and ul.value == n1
+            ok1 = ob.raw == text.tobytes()
+            assert ok1, "uncompress(reference stream) differs"
+            extra["uncompress_reference_stream_64MiB"] = {"GBps": round(n1 / min(tz) / 1e9, 3), "ms": round(min(tz) * 1e3, 1),
+                                                          "stream_bytes": len(z1), "host_buffers": "pageable", "bit_exact": ok1,
+                                                          "reference_uncompress_ms_one_core": round(t_refu * 1e3, 1),
+                                                          "reference_compress2_level6_s_one_core": round(t_refc, 2)}
         # the full shape of BASELINE config 3: 100 000 streams of 64 KiB (the 2048 distinct ones repeated), 6.1 GiB out
         ns3 = 100000
         zs3 = (zs[:distinct] * ((ns3 + distinct - 1) // distinct))[:ns3]
