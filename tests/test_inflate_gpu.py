@@ -309,3 +309,22 @@ def test_long_stream_without_flush_points_uses_the_block_finder(gpu_lib, oracle)
     rc, out = gpu_lib.uncompress(bytes(bad), 3 << 20)
     want_rc, _, _ = oracle.inflate(bytes(bad), 3 << 20)
     assert rc == want_rc and rc != zb.Z_OK
+
+
+def test_long_gzip_member_decodes_in_parallel(gpu_lib):
+    """A long gzip member (windowBits + 16, and + 32 = auto-detect): header walked on the host, blocks found, CRC-32 and
+    ISIZE of the output checked against the trailer (inflate.c:1099-1112); a wrong CRC is the serial decoder's error."""
+    import gzip
+    import io
+    data = gpu_lib.synth(10 << 20, kind=1, seed=51).tobytes()
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="corpus.bin", mode="wb", fileobj=buf, compresslevel=6, mtime=1) as f:
+        f.write(data)
+    member = buf.getvalue()
+    for wrap in (zb.WRAP_GZIP, 3):
+        (outs, st), par, ser = _used_parallel(gpu_lib, lambda: gpu_lib.inflate_batch([member], [len(data)], wrap=wrap))
+        assert st == [0] and outs[0] == data and par and not ser
+    bad = bytearray(member)
+    bad[-6] ^= 0x80                                             # CRC-32 in the trailer
+    outs, st = gpu_lib.inflate_batch([bytes(bad)], [len(data)], wrap=zb.WRAP_GZIP)
+    assert st == [zb.Z_DATA_ERROR]

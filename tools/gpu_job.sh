@@ -1,1 +1,1 @@
-timeout 600 python tools/probe_single_ref.py 2>&1 | tail -12
+timeout 900 python -m pytest tests/test_inflate_gpu.py -m gpu -x -q 2>&1 | tail -6

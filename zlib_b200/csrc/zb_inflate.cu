@@ -1264,14 +1264,32 @@ k_find_blocks_check(const uint8_t* __restrict__ in, uint64_t in_len, const uint6
 int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t* d_dst, uint64_t cap, int wrap,
                             uint64_t* out_len, int32_t* status, cudaStream_t s, uint64_t* in_used = nullptr, uint32_t* adler = nullptr)
 {
-    if (len < kParMinInput || (wrap != ZB200_WRAP_ZLIB && wrap != ZB200_WRAP_RAW)) return 1;
+    if (len < kParMinInput || wrap < 0 || wrap > kWrapAuto) return 1;
     uint64_t hdr = 0;
-    uint8_t h2[2];
-    if (wrap == ZB200_WRAP_ZLIB) {                              // inflate.c:589-632; a preset dictionary goes the serial way
-        ZB_CUDA(cudaMemcpyAsync(h2, d_src, 2, cudaMemcpyDeviceToHost, s));
+    if (wrap != ZB200_WRAP_RAW) {
+        // the wrapper's header is read on the host; anything unusual about it goes the serial way, which names the problem
+        uint8_t hb[4096];
+        const size_t hn = (size_t)std::min<uint64_t>(len, sizeof(hb));
+        ZB_CUDA(cudaMemcpyAsync(hb, d_src, hn, cudaMemcpyDeviceToHost, s));
         ZB_CUDA(cudaStreamSynchronize(s));
-        if (((h2[0] << 8) + h2[1]) % 31 || (h2[0] & 15) != 8 || (h2[0] >> 4) + 8 > 15 || (h2[1] & 0x20)) return 1;
-        hdr = 2;
+        if (wrap == kWrapAuto) wrap = (hb[0] == 0x1f && hb[1] == 0x8b) ? ZB200_WRAP_GZIP : ZB200_WRAP_ZLIB;   // inflate.c:596
+        if (wrap == ZB200_WRAP_ZLIB) {                          // inflate.c:589-632; a preset dictionary goes the serial way
+            if (((hb[0] << 8) + hb[1]) % 31 || (hb[0] & 15) != 8 || (hb[0] >> 4) + 8 > 15 || (hb[1] & 0x20)) return 1;
+            hdr = 2;
+        } else {                                                // gzip, inflate.c:634-759
+            if (hb[0] != 0x1f || hb[1] != 0x8b || hb[2] != 8 || (hb[3] & 0xe0)) return 1;
+            const unsigned flg = hb[3];
+            size_t need = 10;
+            if (flg & 4) { if (need + 2 > hn) return 1; need += 2 + ((size_t)hb[need] | ((size_t)hb[need + 1] << 8)); }
+            for (unsigned f = 8; f <= 16; f <<= 1) {
+                if (!(flg & f)) continue;
+                while (need < hn && hb[need] != 0) need++;
+                need++;
+            }
+            if (flg & 2) need += 2;                             // FHCRC: left unchecked here; a mismatch there is the serial decoder's to report
+            if (need + 64 > hn || (flg & 2)) return 1;
+            hdr = need;
+        }
     }
     const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(len / 32 + 4096, 1u << 26);
     int rc;
@@ -1349,7 +1367,8 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
     const uint32_t nseg = (uint32_t)segs.size();
     if (total > cap) return 1;                                  // the serial decoder reports Z_BUF_ERROR the reference's way
     const uint64_t trailer_at = (final_end + 7) >> 3;
-    if (wrap == ZB200_WRAP_ZLIB && trailer_at + 4 > len) return 1;
+    const uint64_t trailer_len = wrap == ZB200_WRAP_ZLIB ? 4 : wrap == ZB200_WRAP_GZIP ? 8 : 0;
+    if (trailer_at + trailer_len > len) return 1;
     // ---- emit, tails, rest ----
     if ((rc = c->ws[2].ensure((size_t)nseg * sizeof(SegDesc))) != 0) return rc;
     if ((rc = c->ws[3].ensure((size_t)nseg * sizeof(SegResult))) != 0) return rc;
@@ -1364,11 +1383,11 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
     ZB_LAUNCH(k_resolve_rest, nseg, 256, 0, s, d_sym, d_dst, d_segs, d_err);
     ZB_CHECK_LAUNCH();
     uint32_t sums[2] = {0, 1}, nerr = 0;
-    uint8_t tr[4] = {0, 0, 0, 0};
-    if (wrap == ZB200_WRAP_ZLIB) {
+    uint8_t tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (trailer_len) {
         if ((rc = checksum_launch(c, d_dst, (size_t)total, c->small.as<uint32_t>(), s)) != 0) return rc;
         ZB_CUDA(cudaMemcpyAsync(sums, c->small.p, 8, cudaMemcpyDeviceToHost, s));
-        ZB_CUDA(cudaMemcpyAsync(tr, d_src + trailer_at, 4, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaMemcpyAsync(tr, d_src + trailer_at, trailer_len, cudaMemcpyDeviceToHost, s));
     }
     res.resize(nseg);
     ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nseg * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
@@ -1380,10 +1399,14 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
     if (wrap == ZB200_WRAP_ZLIB) {                              // inflate.c:1077-1098
         const uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
         if (want != sums[1]) return 1;                          // let the serial decoder find and name the damage
+    } else if (wrap == ZB200_WRAP_GZIP) {                       // inflate.c:1099-1112: CRC-32, then the length mod 2^32
+        const uint32_t want = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+        const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+        if (want != sums[0] || isize != (uint32_t)total) return 1;
     }
     *out_len = total;
     *status = ZB_OK;
-    if (in_used) *in_used = trailer_at + (wrap == ZB200_WRAP_ZLIB ? 4 : 0);
+    if (in_used) *in_used = trailer_at + trailer_len;
     if (adler) *adler = sums[1];
     return 0;
 }
@@ -1700,7 +1723,7 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
         // stays in the batch below.  Many medium streams are better off side by side in the batch kernel.
         std::vector<uint8_t> handled(n, 0);
         size_t nhandled = 0;
-        if (wrap == ZB200_WRAP_ZLIB || wrap == ZB200_WRAP_RAW) {
+        {
             for (size_t i = 0; i < n && !rc; i++) {
                 const uint64_t a = src_off[i], len = src_off[i + 1] - a;
                 if (len < kParMinInput || (n > kParFewStreams && len < kParLongStream)) continue;
