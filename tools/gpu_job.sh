@@ -1,1 +1,3 @@
-timeout 900 python -m pytest tests/test_inflate_gpu.py -m gpu -x -q 2>&1 | tail -6
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/bench14.json 2> gpurun_out/bench14.log; tail -1 gpurun_out/bench14.log | cut -c1-3500
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
