@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/bench14.json 2> gpurun_out/bench14.log; tail -1 gpurun_out/bench14.log | cut -c1-3500
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python tools/probe_single.py 256 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_inflate_segments|k_resolve_tails|k_find_blocks" -c 3 -o gpurun_out/r1_single python tools/probe_single.py 256 > gpurun_out/ncu_single.log 2>&1
+tail -2 gpurun_out/ncu_single.log
