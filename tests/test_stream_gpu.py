@@ -224,7 +224,9 @@ def test_inflate_finish_whole_buffer_takes_parallel_decoder(gpu_lib):
     data = gpu_lib.synth(n, kind=1, seed=31).tobytes()
     rc, z = gpu_lib.compress2(data, 1)
     assert rc == zb.Z_OK
-    for wbits, stream in ((15, z + b"trailing"), (-15, z[2:-4] + b"xy")):
+    import struct
+    gz = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" + z[2:-4] + struct.pack("<II", zlib.crc32(data), n) + b"more"
+    for wbits, stream in ((15, z + b"trailing"), (-15, z[2:-4] + b"xy"), (31, gz), (47, gz)):
         strm = zb.z_stream()
         assert gpu_lib.dll.inflateInit2_(C.byref(strm), wbits, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
         src = C.create_string_buffer(stream, len(stream))
@@ -236,10 +238,12 @@ def test_inflate_finish_whole_buffer_takes_parallel_decoder(gpu_lib):
         gpu_lib.profile(False)
         assert rc == zb.Z_STREAM_END and any("k_inflate_segments" in k for k in rep)
         assert out.raw[:n] == data and strm.total_out == n and strm.avail_out == 100
-        extra = 8 if wbits > 0 else 2
+        extra = 8 if wbits == 15 else 2 if wbits < 0 else 4
         assert strm.avail_in == extra and strm.total_in == len(stream) - extra
-        if wbits > 0:
+        if wbits == 15:
             assert strm.adler == zlib.adler32(data)
+        elif wbits > 15:
+            assert strm.adler == zlib.crc32(data)
         assert gpu_lib.dll.inflate(C.byref(strm), zb.Z_FINISH) == zb.Z_STREAM_END
         gpu_lib.dll.inflateEnd(C.byref(strm))
 

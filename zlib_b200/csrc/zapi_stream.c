@@ -565,7 +565,7 @@ ZAPI int inflate(z_streamp strm, int flush)                     /* inflate.c:554
     in0 = strm->avail_in; out0 = strm->avail_out;
     if (zb200i_inflate_mode(s->inf) == 8 /* awaiting dictionary */) { strm->adler = s->inf_dict_id; return Z_NEED_DICT; }
     if (out0 == 0 && in0 == 0) return Z_BUF_ERROR;
-    if (!s->inf_started && flush == Z_FINISH && s->inf_wrap <= 1 && in0 >= 65536u) {
+    if (!s->inf_started && flush == Z_FINISH && s->gz_head == Z_NULL && in0 >= 65536u) {
         /* uncompress() spelled out: the whole stream and the whole buffer in the first call */
         if (zb200i_inflate_try_parallel(strm->next_in, in0, strm->next_out, out0, s->inf_wrap, &in_used, &out_len, &check) == 0) {
             strm->next_in += in_used; strm->avail_in -= (uInt)in_used; strm->total_in += in_used;

@@ -39,7 +39,7 @@ size_t zb200i_inflate_pending_input(const zb200i_inflater *h);
 const uint8_t *zb200i_inflate_pending_bytes(const zb200i_inflater *h);
 
 /* One call holding the whole stream and the whole output buffer: 0 = decoded by the segment-parallel decoder
- * (wrap 0 raw / 1 zlib; *check = Adler-32 of the output), 1 = not taken, use the streaming decoder. */
+ * (wrap 0 raw / 1 zlib / 2 gzip / 3 either; *check = Adler-32 of the output, CRC-32 for gzip), 1 = not taken, use the streaming decoder. */
 int  zb200i_inflate_try_parallel(const uint8_t *in, size_t in_len, uint8_t *out, size_t cap, int wrap,
                                  size_t *in_used, size_t *out_len, uint32_t *check);
 

@@ -1262,7 +1262,8 @@ k_find_blocks_check(const uint8_t* __restrict__ in, uint64_t in_len, const uint6
 // Returns 0 when the stream was decoded here (*status, *out_len set), 1 when the caller should use the serial decoder
 // (no usable boundaries, output that does not fit, damaged data), negative on CUDA errors.
 int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t* d_dst, uint64_t cap, int wrap,
-                            uint64_t* out_len, int32_t* status, cudaStream_t s, uint64_t* in_used = nullptr, uint32_t* adler = nullptr)
+                            uint64_t* out_len, int32_t* status, cudaStream_t s, uint64_t* in_used = nullptr, uint32_t* adler = nullptr,
+                            int* wrap_found = nullptr)
 {
     if (len < kParMinInput || wrap < 0 || wrap > kWrapAuto) return 1;
     uint64_t hdr = 0;
@@ -1407,7 +1408,8 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
     *out_len = total;
     *status = ZB_OK;
     if (in_used) *in_used = trailer_at + trailer_len;
-    if (adler) *adler = sums[1];
+    if (adler) *adler = wrap == ZB200_WRAP_GZIP ? sums[0] : sums[1];   // what strm->adler holds at the end: CRC-32 for gzip
+    if (wrap_found) *wrap_found = wrap;
     return 0;
 }
 
