@@ -248,3 +248,23 @@ def test_concurrent_host_threads(gpu_lib, oracle):
     for th in threads:
         th.join()
     assert results == [True] * len(datas)
+
+
+def test_large_pageable_source_goes_through_the_staging_threads(gpu_lib):
+    """compress2() from a malloc'ed (pageable) buffer of 64 MiB or more: host threads copy pieces into pinned slots and
+    send them on their own streams (HostStager); the stream is the same as from a pinned buffer and round-trips."""
+    import ctypes as C
+    n = (150 << 20) + 4321                                      # two slabs, a ragged last piece
+    data = gpu_lib.synth(n, kind=1, seed=71)                    # numpy array: pageable
+    rc, z = gpu_lib.compress2(data, 1)
+    assert rc == zb.Z_OK
+    pin = gpu_lib.dll.zb200_alloc_pinned(n)
+    C.memmove(C.c_void_p(pin), C.c_void_p(data.ctypes.data), n)
+    cap = gpu_lib.compress_bound(n)
+    out = C.create_string_buffer(cap)
+    ol = C.c_ulong(cap)
+    assert gpu_lib.dll.compress2(out, C.byref(ol), C.c_void_p(pin), n, 1) == zb.Z_OK
+    gpu_lib.dll.zb200_free_pinned(C.c_void_p(pin))
+    assert out.raw[:ol.value] == z
+    rc, back = gpu_lib.uncompress(z, n)
+    assert rc == zb.Z_OK and back == data.tobytes()

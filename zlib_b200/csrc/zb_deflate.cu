@@ -1411,6 +1411,8 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
     Ctx* c2 = nullptr;
     cudaStream_t s = pick_stream(c, stream);
     const size_t cap = *dst_len;
+    HostStager stager;                                          // pageable sources of 64 MiB and more (joined before the contexts go back)
+    HostDrainer drainer;                                        // and pageable destinations
     do {
         const bool src_on_host = n != 0 && classify(src) != kDevice;
         const bool dst_on_host = classify(dst) != kDevice;
@@ -1472,6 +1474,8 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
 
         // ---- slabs: copy in (own stream) -> kernels (s) -> slab end to the host ----
         const uint8_t* d_src = d_buf + dict_len;
+        const bool threaded = stage_slabs && n >= HostStager::kMinBytes && classify(src) == kHostPageable;
+        if (threaded && (rc = stager.start(src, (uint8_t*)d_src, n, s_in)) != 0) break;
         if (n == 0) {
             ZB_LAUNCH(k_empty_payload, 1, 32, 0, s, d_out, cap, hdr_len, !last_is_final, force_mark, d_pos);
         }
@@ -1479,7 +1483,11 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
             const uint64_t off = cut[i], len = cut[i + 1] - cut[i];
             Ctx* cl = (c2 && (i & 1)) ? c2 : c;
             cudaStream_t sl = (c2 && (i & 1)) ? c2->own_stream : s;
-            if (stage_slabs) {
+            if (stage_slabs && threaded) {                       // pageable source: pieces arrive from the staging threads
+                if ((rc = stager.wait_range(off, len, sl)) != 0) break;
+                if (c2 && i + 1 < nslabs && (rc = stager.wait_range(off + len - std::min<uint64_t>(len, kWindow), std::min<uint64_t>(len, kWindow),
+                                                                    (i & 1) ? s : c2->own_stream)) != 0) break;   // its tail is the next slab's dictionary
+            } else if (stage_slabs) {
                 e = cudaMemcpyAsync((uint8_t*)d_src + off, (const uint8_t*)src + off, len, cudaMemcpyDefault, s_in);
                 if (e == cudaSuccess) e = cudaEventRecord(ev_in[i], s_in);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(sl, ev_in[i], 0);
@@ -1512,16 +1520,21 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
 
         // ---- copy out finished slabs while later ones are still running ----
         uint64_t copied = hdr_len;                              // out[0, hdr_len) is written last, by k_frame
+        const bool drain_threads = dst_on_host && n >= HostStager::kMinBytes && classify(dst) == kHostPageable;
         if (dst_on_host) {
             for (uint64_t i = 0; i + 1 < nslabs; i++) {
                 if ((e = cudaEventSynchronize(ev_done[i])) != cudaSuccess) break;
                 const uint64_t end = h_pos[i];
                 if (end > cap) break;                           // does not fit: reported below from the total
-                if (end > copied) e = cudaMemcpyAsync((uint8_t*)dst + copied, d_out + copied, end - copied, cudaMemcpyDeviceToHost, s_out);
+                if (end > copied) {
+                    if (drain_threads) { if ((rc = drainer.drain((uint8_t*)dst + copied, d_out + copied, end - copied)) != 0) break; }
+                    else e = cudaMemcpyAsync((uint8_t*)dst + copied, d_out + copied, end - copied, cudaMemcpyDeviceToHost, s_out);
+                }
                 if (e != cudaSuccess) break;
                 copied = end;
             }
         }
+        if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(s_out); break; }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) { set_error("deflate failed: %s", cudaGetErrorString(e)); cudaStreamSynchronize(s_out); rc = ZB_STREAM_ERROR; break; }
         const uint64_t total = h_res[0];
@@ -1536,12 +1549,17 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
             break;
         }
         if (dst_on_host && total) {
-            if (total > copied) e = cudaMemcpyAsync((uint8_t*)dst + copied, d_out + copied, total - copied, cudaMemcpyDeviceToHost, s_out);
+            if (total > copied) {
+                if (drain_threads) { if ((rc = drainer.drain((uint8_t*)dst + copied, d_out + copied, total - copied)) != 0) break; }
+                else e = cudaMemcpyAsync((uint8_t*)dst + copied, d_out + copied, total - copied, cudaMemcpyDeviceToHost, s_out);
+            }
             if (e == cudaSuccess && hdr_len) e = cudaMemcpyAsync(dst, d_out, hdr_len, cudaMemcpyDeviceToHost, s_out);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s_out);
             if (e != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         }
     } while (0);
+    stager.finish();
+    drainer.finish();
     if (c2) ctx_release(c2, c2->own_stream);
     ctx_release(c, s);
     return rc;

@@ -1729,7 +1729,12 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             for (size_t i = 0; i < n && !rc; i++) {
                 const uint64_t a = src_off[i], len = src_off[i + 1] - a;
                 if (len < kParMinInput || (n > kParFewStreams && len < kParLongStream)) continue;
-                if (src_on_host) {
+                if (src_on_host && len >= HostStager::kMinBytes && classify(src) == kHostPageable) {
+                    HostStager stager;                          // pageable and long: host threads feed pinned slots
+                    if ((rc = stager.start((const uint8_t*)src + a, (uint8_t*)d_src + a, len, s)) != 0) break;
+                    if ((rc = stager.wait_range(0, len, s)) != 0) break;
+                    stager.finish();
+                } else if (src_on_host) {
                     e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + a, len, cudaMemcpyHostToDevice, s);
                     if (e != cudaSuccess) { set_error("input staging failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
                 }
@@ -1738,7 +1743,10 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
                 const int pr = inflate_single_parallel(c, d_src + a, len, d_dst + dst_off[i], dst_off[i + 1] - dst_off[i], wrap, &got, &st, s);
                 if (pr < 0) { rc = pr; break; }
                 if (pr != 0) continue;
-                if (dst_on_host && got) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[i], d_dst + dst_off[i], got, cudaMemcpyDeviceToHost, s);
+                if (dst_on_host && got >= HostStager::kMinBytes && classify(dst) == kHostPageable) {
+                    HostDrainer drainer;                        // the decoder has synchronised: the output is complete
+                    if ((rc = drainer.drain((uint8_t*)dst + dst_off[i], d_dst + dst_off[i], got)) != 0) break;
+                } else if (dst_on_host && got) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[i], d_dst + dst_off[i], got, cudaMemcpyDeviceToHost, s);
                 if (e != cudaSuccess) { set_error("inflate readback failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
                 dst_len[i] = got; status[i] = st;
                 handled[i] = 1; nhandled++;

@@ -4,6 +4,9 @@
 #include "zb_common.cuh"
 
 #include <mutex>
+#include <thread>
+#include <atomic>
+#include <memory>
 #include <vector>
 #include <string>
 #include <map>
@@ -199,6 +202,145 @@ const uint8_t* to_device(Ctx* c, const void* src, size_t len, cudaStream_t s, in
     cudaError_t e = cudaMemcpyAsync(c->in.p, src, len, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { set_error("H2D copy of %zu bytes failed: %s", len, cudaGetErrorString(e)); *err = ZB_STREAM_ERROR; return nullptr; }
     return c->in.as<uint8_t>();
+}
+
+// ---- HostStager ----
+static std::mutex g_slot_mu;
+static std::vector<void*> g_slot_pool;                          // pinned slot sets (kThreads * kPiece each), reused across calls
+
+struct HostStager::Impl {
+    const uint8_t* src = nullptr;
+    uint8_t* d_dst = nullptr;
+    size_t n = 0, npieces = 0;
+    int device = 0;
+    uint8_t* slots = nullptr;
+    cudaStream_t st[HostStager::kThreads] = {};
+    cudaEvent_t go = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::unique_ptr<std::atomic<int>[]> issued;
+    std::atomic<int> failed{0};
+    std::vector<std::thread> th;
+
+    void run(int t)
+    {
+        cudaSetDevice(device);
+        uint8_t* slot = slots + (size_t)t * HostStager::kPiece;
+        if (cudaStreamWaitEvent(st[t], go, 0) != cudaSuccess) failed = 1;
+        for (size_t p = (size_t)t; p < npieces; p += HostStager::kThreads) {
+            const size_t off = p * HostStager::kPiece, len = std::min(HostStager::kPiece, n - off);
+            if (!failed) {
+                if (p >= (size_t)HostStager::kThreads && cudaEventSynchronize(ev[p - HostStager::kThreads]) != cudaSuccess) failed = 1;   // the slot's last send
+                memcpy(slot, src + off, len);
+                if (cudaMemcpyAsync(d_dst + off, slot, len, cudaMemcpyHostToDevice, st[t]) != cudaSuccess) failed = 1;
+                if (cudaEventRecord(ev[p], st[t]) != cudaSuccess) failed = 1;
+            }
+            issued[p].store(1, std::memory_order_release);
+        }
+    }
+};
+
+int HostStager::start(const void* src, void* d_dst, size_t n, cudaStream_t after)
+{
+    impl = new Impl();
+    Impl& m = *impl;
+    m.src = (const uint8_t*)src; m.d_dst = (uint8_t*)d_dst; m.n = n;
+    m.npieces = (n + kPiece - 1) / kPiece;
+    cudaGetDevice(&m.device);
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mu);
+        if (!g_slot_pool.empty()) { m.slots = (uint8_t*)g_slot_pool.back(); g_slot_pool.pop_back(); }
+    }
+    if (!m.slots && cudaMallocHost((void**)&m.slots, (size_t)kThreads * kPiece) != cudaSuccess) {
+        cudaGetLastError(); m.slots = nullptr;
+        delete impl; impl = nullptr;
+        set_error("pinned staging slots could not be allocated");
+        return ZB_MEM_ERROR;
+    }
+    bool ok = cudaEventCreateWithFlags(&m.go, cudaEventDisableTiming) == cudaSuccess && cudaEventRecord(m.go, after) == cudaSuccess;
+    for (int t = 0; t < kThreads && ok; t++) ok = cudaStreamCreateWithFlags(&m.st[t], cudaStreamNonBlocking) == cudaSuccess;
+    m.ev.assign(m.npieces, nullptr);
+    for (size_t p = 0; p < m.npieces && ok; p++) ok = cudaEventCreateWithFlags(&m.ev[p], cudaEventDisableTiming) == cudaSuccess;
+    m.issued.reset(new std::atomic<int>[m.npieces]);
+    for (size_t p = 0; p < m.npieces; p++) m.issued[p].store(0, std::memory_order_relaxed);
+    if (!ok) { cudaGetLastError(); finish(); set_error("staging streams or events could not be created"); return ZB_MEM_ERROR; }
+    for (int t = 0; t < kThreads; t++) m.th.emplace_back([this, t]() { impl->run(t); });
+    return 0;
+}
+
+int HostStager::wait_range(size_t off, size_t len, cudaStream_t consumer)
+{
+    if (!impl || len == 0) return 0;
+    Impl& m = *impl;
+    for (size_t p = off / kPiece; p <= (off + len - 1) / kPiece && p < m.npieces; p++) {
+        while (!m.issued[p].load(std::memory_order_acquire)) std::this_thread::yield();
+        if (m.failed) { set_error("host staging failed"); return ZB_STREAM_ERROR; }
+        if (cudaStreamWaitEvent(consumer, m.ev[p], 0) != cudaSuccess) { set_error("host staging wait failed"); return ZB_STREAM_ERROR; }
+    }
+    return 0;
+}
+
+void HostStager::finish()
+{
+    if (!impl) return;
+    Impl& m = *impl;
+    for (auto& t : m.th) if (t.joinable()) t.join();
+    for (int t = 0; t < kThreads; t++) if (m.st[t]) { cudaStreamSynchronize(m.st[t]); cudaStreamDestroy(m.st[t]); }
+    for (cudaEvent_t e : m.ev) if (e) cudaEventDestroy(e);
+    if (m.go) cudaEventDestroy(m.go);
+    if (m.slots) { std::lock_guard<std::mutex> lk(g_slot_mu); g_slot_pool.push_back(m.slots); }
+    delete impl;
+    impl = nullptr;
+}
+
+// ---- HostDrainer ----
+int HostDrainer::drain(void* dst, const void* d_src, size_t n)
+{
+    constexpr size_t kPiece = HostStager::kPiece;
+    constexpr int kThreads = HostStager::kThreads;
+    if (n == 0) return 0;
+    if (n < 2 * kPiece) {
+        if (cudaMemcpy(dst, d_src, n, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError())); return ZB_STREAM_ERROR; }
+        return 0;
+    }
+    if (!slots) {
+        {
+            std::lock_guard<std::mutex> lk(g_slot_mu);
+            if (!g_slot_pool.empty()) { slots = (uint8_t*)g_slot_pool.back(); g_slot_pool.pop_back(); }
+        }
+        if (!slots && cudaMallocHost((void**)&slots, (size_t)kThreads * kPiece) != cudaSuccess) {
+            cudaGetLastError(); slots = nullptr;
+            set_error("pinned staging slots could not be allocated");
+            return ZB_MEM_ERROR;
+        }
+        for (int t = 0; t < kThreads; t++)
+            if (cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); st[t] = nullptr; set_error("staging stream creation failed"); return ZB_MEM_ERROR; }
+    }
+    int device = 0;
+    cudaGetDevice(&device);
+    const size_t npieces = (n + kPiece - 1) / kPiece;
+    std::atomic<int> failed{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < kThreads; t++) {
+        th.emplace_back([&, t]() {
+            cudaSetDevice(device);
+            uint8_t* slot = slots + (size_t)t * kPiece;
+            for (size_t p = (size_t)t; p < npieces; p += kThreads) {
+                const size_t off = p * kPiece, len = std::min(kPiece, n - off);
+                if (cudaMemcpyAsync(slot, (const uint8_t*)d_src + off, len, cudaMemcpyDeviceToHost, st[t]) != cudaSuccess ||
+                    cudaStreamSynchronize(st[t]) != cudaSuccess) { failed = 1; return; }
+                memcpy((uint8_t*)dst + off, slot, len);
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    if (failed) { set_error("D2H staging failed: %s", cudaGetErrorString(cudaGetLastError())); return ZB_STREAM_ERROR; }
+    return 0;
+}
+
+void HostDrainer::finish()
+{
+    for (int t = 0; t < HostStager::kThreads; t++) if (st[t]) { cudaStreamDestroy(st[t]); st[t] = nullptr; }
+    if (slots) { std::lock_guard<std::mutex> lk(g_slot_mu); g_slot_pool.push_back(slots); slots = nullptr; }
 }
 
 }  // namespace zb
