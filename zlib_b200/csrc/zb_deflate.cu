@@ -1637,6 +1637,8 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
     if (!c0) return ZB_MEM_ERROR;
     Ctx* lane[kLanes] = {nullptr, nullptr, nullptr};
     int nl = 0;
+    HostStager stager;                                          // pageable arenas of 64 MiB and more
+    HostDrainer drainer;
     do {
         if ((rc = c0->ensure_aux((int)(2 * nslabs + kLanes + 4))) != 0) break;
         cudaStream_t s_in = c0->aux[0], s_out = c0->aux[1];
@@ -1684,6 +1686,9 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
         if (e != cudaSuccess) { set_error("batch setup failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
 
         // ---- enqueue: copy in (s_in) -> kernels (lane) -> result words to the host ----
+        const bool threaded = src_on_host && src_total >= HostStager::kMinBytes && classify(src) == kHostPageable;
+        const bool drain_threads = dst_on_host && src_total >= HostStager::kMinBytes && classify(dst) == kHostPageable;
+        if (threaded && (rc = stager.start(src, (uint8_t*)d_src + src_off[0], src_total, s_in)) != 0) break;
         JobResult* h_res = (JobResult*)c0->pinned;
         size_t enq = 0;
         for (; enq < nslabs; enq++) {
@@ -1691,7 +1696,9 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
             Ctx* ck = lane[enq % nl];
             cudaStream_t sk = ck->own_stream;
             const uint64_t a = src_off[sl.j0], span = src_off[sl.j1] - a;
-            if (src_on_host && span) {
+            if (src_on_host && span && threaded) {               // pageable arena: pieces arrive from the staging threads
+                if ((rc = stager.wait_range(a - src_off[0], span, sk)) != 0) break;
+            } else if (src_on_host && span) {
                 e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + (a - src_off[0]), span, cudaMemcpyHostToDevice, s_in);
                 if (e == cudaSuccess) e = cudaEventRecord(ev_in[enq], s_in);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(sk, ev_in[enq], 0);
@@ -1718,7 +1725,10 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
         // A copy covers neighbouring slots and the short gaps between them (bytes past a stream's length in its own slot).
         uint64_t ra = 0, rb = 0;
         auto flush_copy = [&]() {
-            if (rb > ra && cudaMemcpyAsync((uint8_t*)dst + ra, d_dst + ra, rb - ra, cudaMemcpyDeviceToHost, s_out) != cudaSuccess) rc = ZB_STREAM_ERROR;
+            if (rb > ra) {
+                if (drain_threads) { if (drainer.drain((uint8_t*)dst + ra, d_dst + ra, rb - ra) != 0) rc = ZB_STREAM_ERROR; }
+                else if (cudaMemcpyAsync((uint8_t*)dst + ra, d_dst + ra, rb - ra, cudaMemcpyDeviceToHost, s_out) != cudaSuccess) rc = ZB_STREAM_ERROR;
+            }
             ra = rb = 0;
         };
         for (size_t k = 0; k < nslabs && !rc; k++) {
@@ -1742,6 +1752,8 @@ ZB_API int zb200_deflate_batch(const void* src, const uint64_t* src_off, size_t 
         if (dst_on_host && cudaStreamSynchronize(s_out) != cudaSuccess) rc = ZB_STREAM_ERROR;
         if (rc) set_error("deflate batch readback failed: %s", cudaGetErrorString(cudaGetLastError()));
     } while (0);
+    stager.finish();
+    drainer.finish();
     for (int k = 0; k < nl; k++) if (lane[k]) ctx_release(lane[k], lane[k]->own_stream);
     ctx_release(c0, s0);
     return rc;

@@ -149,9 +149,14 @@ ZB_API int zb200_zip_segment(const char* const* names, const void* src, const ui
         if (e != cudaSuccess) { set_error("zip table upload failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         ZB_LAUNCH(k_zip_gather, (unsigned)k, kGatherThreads, 0, s, reinterpret_cast<const Piece*>(d_up + tab_at));
         e = cudaGetLastError();
-        if (e == cudaSuccess && dst_on_host) e = cudaMemcpyAsync(dst, d_arc, pos, cudaMemcpyDeviceToHost, s);
+        const bool drain_threads = dst_on_host && pos >= HostStager::kMinBytes && classify(dst) == kHostPageable;
+        if (e == cudaSuccess && dst_on_host && !drain_threads) e = cudaMemcpyAsync(dst, d_arc, pos, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) { set_error("zip assembly failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        if (drain_threads) {                                    // malloc'ed archive buffer: host threads pull it through pinned slots
+            HostDrainer drainer;
+            if ((rc = drainer.drain(dst, d_arc, pos)) != 0) break;
+        }
         *dst_len = (size_t)pos;
     } while (0);
     ctx_release(c, s);
