@@ -21,6 +21,14 @@ for rep in range(4):
     dt = time.perf_counter() - t0
     assert rc == 0 and not st.any() and (dl == sz).all()
     print(f"inflate_batch pinned host arenas: {ns} x 64 KiB in {dt * 1e3:.1f} ms = {ns * sz / dt / 1e9:.2f} GB/s (in {int(so[-1]) / 1e6:.0f} MB)", flush=True)
+src_p = src.numpy().copy(); dst_p = np.zeros(ns * sz, dtype=np.uint8)            # pageable arenas
+for rep in range(3):
+    t0 = time.perf_counter()
+    rc = L.dll.zb200_inflate_batch(src_p.ctypes.data, so.ctypes.data, ns, dst_p.ctypes.data, do.ctypes.data, dl.ctypes.data, st.ctypes.data, zb.WRAP_ZLIB, None)
+    dt = time.perf_counter() - t0
+    assert rc == 0 and not st.any() and (dl == sz).all()
+    print(f"inflate_batch pageable host arenas: {dt * 1e3:.1f} ms = {ns * sz / dt / 1e9:.2f} GB/s", flush=True)
+assert np.array_equal(dst_p, dst.numpy())
 out = dst.numpy()
 for i in (0, 1, distinct - 1, distinct, ns - 1):
     assert out[i * sz:(i + 1) * sz].tobytes() == host[(i % distinct) * sz:(i % distinct + 1) * sz].tobytes()

@@ -1705,6 +1705,8 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
     if (!c) return ZB_MEM_ERROR;
     cudaStream_t s = pick_stream(c, stream);
     Ctx* c2 = nullptr;                                           // odd groups decode on a second stream
+    HostStager stager;                                           // pageable arenas of 64 MiB and more
+    HostDrainer drainer;
     do {
         const size_t src_total = (size_t)src_off[n], dst_total = (size_t)dst_off[n];
         const bool src_on_host = src_total != 0 && classify(src) != kDevice;
@@ -1792,12 +1794,17 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             if (e == cudaSuccess && c2) e = cudaStreamWaitEvent(c2->own_stream, c->evs[2 * ng], 0);
         }
         if (e != cudaSuccess) { set_error("descriptor upload failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        const bool threaded = src_on_host && src_total >= HostStager::kMinBytes && classify(src) == kHostPageable;
+        const bool drain_threads = dst_on_host && dst_total >= HostStager::kMinBytes && classify(dst) == kHostPageable;
+        if (threaded && (rc = stager.start(src, (uint8_t*)d_src, src_total, s_in)) != 0) break;
         cudaStream_t s_main = s;
         for (size_t k = 0; k < ng && !rc; k++) {
             const size_t i0 = g0[k], i1 = g1[k];
             const uint64_t a = src_off[i0], b = src_off[i1];
             cudaStream_t s = (c2 && (k & 1)) ? c2->own_stream : s_main;
-            if (src_on_host && b > a) {
+            if (src_on_host && b > a && threaded) {              // pageable arena: pieces arrive from the staging threads
+                if ((rc = stager.wait_range(a, b - a, s)) != 0) break;
+            } else if (src_on_host && b > a) {
                 e = cudaMemcpyAsync((uint8_t*)d_src + a, (const uint8_t*)src + a, b - a, cudaMemcpyHostToDevice, s_in);
                 if (e == cudaSuccess) e = cudaEventRecord(ev_in[k], s_in);
                 if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev_in[k], 0);
@@ -1810,8 +1817,10 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             if (e == cudaSuccess) e = cudaMemcpyAsync(h_status + i0, d_status + i0, (i1 - i0) * 4, cudaMemcpyDeviceToHost, s);
             if (e == cudaSuccess && dst_on_host && dst_off[i1] > dst_off[i0]) {
                 e = cudaEventRecord(ev_done[k], s);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(s_out, ev_done[k], 0);
-                if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[i0], d_dst + dst_off[i0], dst_off[i1] - dst_off[i0], cudaMemcpyDeviceToHost, s_out);
+                if (e == cudaSuccess && !drain_threads) {
+                    e = cudaStreamWaitEvent(s_out, ev_done[k], 0);
+                    if (e == cudaSuccess) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[i0], d_dst + dst_off[i0], dst_off[i1] - dst_off[i0], cudaMemcpyDeviceToHost, s_out);
+                }
             }
             if (e != cudaSuccess) { set_error("output copy failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         }
@@ -1820,12 +1829,22 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
             cudaStreamWaitEvent(s, c->evs[2 * ng + 1], 0);
         }
         if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(s_in); cudaStreamSynchronize(s_out); break; }
+        if (drain_threads) {                                    // malloc'ed output arena: drain group by group while later groups decode
+            for (size_t k = 0; k < ng && !rc; k++) {
+                if (dst_off[g1[k]] == dst_off[g0[k]]) continue;
+                if (cudaEventSynchronize(ev_done[k]) != cudaSuccess) { set_error("inflate batch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = ZB_STREAM_ERROR; break; }
+                rc = drainer.drain((uint8_t*)dst + dst_off[g0[k]], d_dst + dst_off[g0[k]], dst_off[g1[k]] - dst_off[g0[k]]);
+            }
+            if (rc) { cudaStreamSynchronize(s); break; }
+        }
         e = cudaStreamSynchronize(s);
         if (e == cudaSuccess && dst_on_host) e = cudaStreamSynchronize(s_out);
         if (e != cudaSuccess) { set_error("inflate batch readback failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         for (size_t k = 0; k < ng; k++)
             for (size_t i = g0[k]; i < g1[k]; i++) { dst_len[i] = h_len[i]; status[i] = h_status[i]; }
     } while (0);
+    stager.finish();
+    drainer.finish();
     if (c2) ctx_release(c2, c2->own_stream);
     ctx_release(c, s);
     return rc;
