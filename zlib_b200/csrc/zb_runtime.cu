@@ -199,6 +199,12 @@ const uint8_t* to_device(Ctx* c, const void* src, size_t len, cudaStream_t s, in
     MemKind k = classify(src);
     if (k == kDevice) return static_cast<const uint8_t*>(src);
     if ((*err = c->in.ensure(len + 64)) != 0) return nullptr;
+    if (k == kHostPageable && len >= HostStager::kMinBytes) {   // a long malloc'ed buffer: host threads through pinned slots
+        HostStager stager;
+        if ((*err = stager.start(src, c->in.p, len, s)) != 0) return nullptr;
+        if ((*err = stager.wait_range(0, len, s)) != 0) return nullptr;
+        return c->in.as<uint8_t>();
+    }
     cudaError_t e = cudaMemcpyAsync(c->in.p, src, len, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) { set_error("H2D copy of %zu bytes failed: %s", len, cudaGetErrorString(e)); *err = ZB_STREAM_ERROR; return nullptr; }
     return c->in.as<uint8_t>();
