@@ -447,6 +447,20 @@ def main():
         extra["inflate_batch_host_e2e"] = {"GBps": round(ns * sz / min(th) / 1e9, 3), "ms": round(min(th) * 1e3, 2), "host_buffers": "pinned",
                                            "h2d_bytes": zin, "d2h_bytes": ns * sz, "output_matches": okh}
         lib.dll.zb200_free_pinned(C.c_void_p(pin_z))
+        # the e2e call again with malloc'ed (pageable) buffers -- what an unmodified caller of the reference passes
+        pg_src = np.array(host, copy=True)
+        pg_dst = np.empty(cap, dtype=np.uint8)
+        pg_dst[:] = 0
+        tp = []
+        for _ in range(3):
+            ol = C.c_ulong(cap)
+            t0 = time.perf_counter()
+            rc = lib.dll.compress2(C.c_void_p(pg_dst.ctypes.data), C.byref(ol), C.c_void_p(pg_src.ctypes.data), n, 1)
+            tp.append(time.perf_counter() - t0)
+            assert rc == 0 and ol.value == int(state["e2e_len"])
+        extra["compress2_pageable_e2e"] = {"GBps": round(n / min(tp) / 1e9, 3), "ms": round(min(tp) * 1e3, 1), "host_buffers": "pageable (malloc)",
+                                           "staging": "8 host threads, 4 MiB pieces through pinned slots"}
+        del pg_src, pg_dst
         # uncompress() of ONE long stream: the compress2 output of the e2e leg (1 GiB in one zlib stream, pinned host
         # buffers); decoded in parallel at its chunk boundaries (BASELINE config 1's round trip, at config 2's size)
         step_e2e()                                             # pin_dst holds the level-1 stream again
