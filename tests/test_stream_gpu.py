@@ -350,3 +350,28 @@ def test_strategies(gpu_lib, oracle):
                 assert (z[1] >> 6) == 0                               # FLEVEL = fastest (deflate.c:628)
     assert sizes[(2, 6)] > sizes[(3, 6)] > sizes[(0, 6)]              # Huffman only > RLE > default
     assert sizes[(1, 6)] >= sizes[(0, 6)]
+
+
+def test_zip_ten_thousand_files(gpu_lib, tmp_path):
+    """BASELINE config 5 at its file count: 10 000 members (4 KiB .. 256 KiB, log-uniform, ~0.4 GB) in ONE zb200_zip_build
+    call; Python's zipfile checks every member's CRC and the reference's miniunz extracts all of them bit-exact."""
+    import zipfile
+    rng = random.Random(55)
+    sizes = [int(4096 * 2 ** rng.uniform(0, 6)) for _ in range(10000)]
+    blob = gpu_lib.synth(sum(sizes), kind=1, seed=56).tobytes()
+    files, pos = {}, 0
+    for i, n in enumerate(sizes):
+        files[f"f{i:05d}.bin"] = blob[pos:pos + n]
+        pos += n
+    arc = gpu_lib.zip_build(files, level=1)
+    path = tmp_path / "ten_thousand.zip"
+    path.write_bytes(arc)
+    zf = zipfile.ZipFile(path)
+    assert len(zf.namelist()) == 10000 and zf.testzip() is None
+    out = tmp_path / "x"
+    out.mkdir()
+    p = subprocess.run([_need(os.path.join(REFDIR, "miniunz")), "-o", str(path)], cwd=out, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr
+    for name in rng.sample(sorted(files), 500) + ["f00000.bin", "f09999.bin"]:
+        assert (out / name).read_bytes() == files[name], name
+    assert len(os.listdir(out)) == 10000

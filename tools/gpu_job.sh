@@ -1,1 +1,1 @@
-python bench.py > gpurun_out/bench15.json 2> gpurun_out/bench15.log; tail -1 gpurun_out/bench15.log | cut -c1-1200
+timeout 900 python -m pytest tests/test_stream_gpu.py -m gpu -x -q -k "ten_thousand" --durations=3 2>&1 | tail -8
