@@ -1,1 +1,3 @@
-timeout 900 python -m pytest tests/test_stream_gpu.py -m gpu -x -q -k "ten_thousand" --durations=3 2>&1 | tail -8
+python tools/probe_codec.py 1024 2>&1 | head -1
+ZB200_SLAB_LANES=3 python tools/probe_codec.py 1024 2>&1 | head -1
+ZB200_SLAB_LANES=3 python -m pytest tests/test_deflate_gpu.py -m gpu -x -q 2>&1 | tail -2
