@@ -1,1 +1,2 @@
-python tools/sanitize_case.py 2>&1 | tail -2 && timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_case.py > gpurun_out/sanitize.log 2>&1; echo "sanitizer rc=$?"; tail -6 gpurun_out/sanitize.log
+timeout 900 python -m pytest tests/test_inflate_gpu.py tests/test_stream_gpu.py -m gpu -x -q 2>&1 | tail -3
+timeout 600 python tools/probe_single.py 1024 2>&1 | grep -v "^{" | tail -6

@@ -1096,7 +1096,7 @@ constexpr uint32_t kTailSlice = kWindow32 / kTailCtas;          // 4096 position
 struct TailWork { uint64_t grp[2]; uint4 v[2]; };               // up to two groups of 8 symbols per thread and trip
 
 __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads)
-k_resolve_tails(const uint16_t* __restrict__ sym, uint8_t* __restrict__ out, const SegDesc* __restrict__ segs, uint32_t nseg,
+k_resolve_tails(const uint16_t* __restrict__ sym, uint8_t* __restrict__ out, const SegDesc* __restrict__ segs, uint32_t j0, uint32_t nseg,
                 uint32_t* __restrict__ err)
 {
     namespace cg = cooperative_groups;
@@ -1127,10 +1127,20 @@ k_resolve_tails(const uint16_t* __restrict__ sym, uint8_t* __restrict__ out, con
         }
     };
     TailWork cur, nxt;
-    SegDesc sd = segs[0], sn = sd;
+    SegDesc sd = segs[j0], sn = sd;
     fetch(sd, nxt);
+    if (j0 > 0) {
+        // a later launch of the same walk: the ring is the 32 KiB of final output in front of the first segment
+        const uint64_t hi = sd.out_off, lo = hi > kWindow32 ? hi - kWindow32 : 0;
+        for (uint64_t m = lo >> 12; hi && m <= (hi - 1) >> 12; m++) {
+            if ((m & (kTailCtas - 1)) != r) continue;
+            for (uint64_t p = max(lo, m << 12) + threadIdx.x; p < min(hi, (m + 1) << 12); p += kTailThreads)
+                ring[(uint32_t)p & (kTailSlice - 1)] = __ldcg(out + p);
+        }
+        cluster.sync();
+    }
     uint32_t bad = 0;
-    for (uint32_t j = 0; j < nseg; j++) {
+    for (uint32_t j = j0; j < nseg; j++) {
         sd = sn; cur = nxt;
         if (j + 1 < nseg) { sn = segs[j + 1]; fetch(sn, nxt); }
         const uint64_t t = min(sd.out_len, (uint64_t)kWindow32), lo = sd.out_off + sd.out_len - t, hi = lo + t;
@@ -1263,7 +1273,7 @@ k_find_blocks_check(const uint8_t* __restrict__ in, uint64_t in_len, const uint6
 // (no usable boundaries, output that does not fit, damaged data), negative on CUDA errors.
 int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t* d_dst, uint64_t cap, int wrap,
                             uint64_t* out_len, int32_t* status, cudaStream_t s, uint64_t* in_used = nullptr, uint32_t* adler = nullptr,
-                            int* wrap_found = nullptr)
+                            int* wrap_found = nullptr, void* h_dst = nullptr)
 {
     if (len < kParMinInput || wrap < 0 || wrap > kWrapAuto) return 1;
     uint64_t hdr = 0;
@@ -1380,8 +1390,23 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
     ZB_CUDA(cudaMemcpyAsync(d_segs, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
     ZB_LAUNCH((k_inflate_segments<true>), (nseg + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s, d_src, len, d_segs, nseg, d_sym, d_res,
               (const uint64_t*)nullptr);
-    ZB_LAUNCH(k_resolve_tails, kTailCtas, kTailThreads, 0, s, d_sym, d_dst, d_segs, nseg, d_err);
-    ZB_LAUNCH(k_resolve_rest, nseg, 256, 0, s, d_sym, d_dst, d_segs, d_err);
+    // The sequential walk runs in a few launches (the ring is re-read from the output, which is final behind the walk), each
+    // followed by the parallel rest of its segments -- so a pinned host destination receives the finished part of the
+    // output while the walk goes on.
+    const uint32_t nphase = (h_dst && nseg >= 64) ? 8 : 1;
+    if (h_dst && (rc = c->ensure_aux(nphase + 2)) != 0) return rc;
+    for (uint32_t k = 0; k < nphase; k++) {
+        const uint32_t j0 = (uint32_t)((uint64_t)nseg * k / nphase), j1 = (uint32_t)((uint64_t)nseg * (k + 1) / nphase);
+        if (j1 == j0) continue;
+        ZB_LAUNCH(k_resolve_tails, kTailCtas, kTailThreads, 0, s, d_sym, d_dst, d_segs, j0, j1, d_err);
+        ZB_LAUNCH(k_resolve_rest, j1 - j0, 256, 0, s, d_sym, d_dst, d_segs + j0, d_err);
+        if (h_dst) {
+            const uint64_t a = segs[j0].out_off, b = segs[j1 - 1].out_off + segs[j1 - 1].out_len;
+            ZB_CUDA(cudaEventRecord(c->evs[k], s));
+            ZB_CUDA(cudaStreamWaitEvent(c->aux[1], c->evs[k], 0));
+            if (b > a) ZB_CUDA(cudaMemcpyAsync((uint8_t*)h_dst + a, d_dst + a, b - a, cudaMemcpyDeviceToHost, c->aux[1]));
+        }
+    }
     ZB_CHECK_LAUNCH();
     uint32_t sums[2] = {0, 1}, nerr = 0;
     uint8_t tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1405,6 +1430,7 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
         const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
         if (want != sums[0] || isize != (uint32_t)total) return 1;
     }
+    if (h_dst) ZB_CUDA(cudaStreamSynchronize(c->aux[1]));
     *out_len = total;
     *status = ZB_OK;
     if (in_used) *in_used = trailer_at + trailer_len;
@@ -1742,10 +1768,13 @@ ZB_API int zb200_inflate_batch(const void* src, const uint64_t* src_off, size_t 
                 }
                 uint64_t got = 0;
                 int32_t st = ZB_OK;
-                const int pr = inflate_single_parallel(c, d_src + a, len, d_dst + dst_off[i], dst_off[i + 1] - dst_off[i], wrap, &got, &st, s);
+                void* h_out = dst_on_host && classify(dst) == kHostPinned ? (uint8_t*)dst + dst_off[i] : nullptr;   // receives the output as it is finished
+                const int pr = inflate_single_parallel(c, d_src + a, len, d_dst + dst_off[i], dst_off[i + 1] - dst_off[i], wrap, &got, &st, s,
+                                                       nullptr, nullptr, nullptr, h_out);
                 if (pr < 0) { rc = pr; break; }
-                if (pr != 0) continue;
-                if (dst_on_host && got >= HostStager::kMinBytes && classify(dst) == kHostPageable) {
+                if (pr != 0) { if (h_out && c->aux[1]) cudaStreamSynchronize(c->aux[1]); continue; }
+                if (h_out) {                                    // already there: copied phase by phase behind the walk
+                } else if (dst_on_host && got >= HostStager::kMinBytes && classify(dst) == kHostPageable) {
                     HostDrainer drainer;                        // the decoder has synchronised: the output is complete
                     if ((rc = drainer.drain((uint8_t*)dst + dst_off[i], d_dst + dst_off[i], got)) != 0) break;
                 } else if (dst_on_host && got) e = cudaMemcpyAsync((uint8_t*)dst + dst_off[i], d_dst + dst_off[i], got, cudaMemcpyDeviceToHost, s);
