@@ -129,7 +129,9 @@ int zb200_inflate_batch(const void *src, const uint64_t *src_off, size_t n,
                         int32_t *status, int wrap, void *stream);
 
 /* Fully device-resident form: every pointer is device memory, nothing is copied,
- * nothing synchronises. */
+ * nothing synchronises -- and therefore every stream is decoded by one warp, however long
+ * it is.  zb200_inflate_batch (which may synchronise) decodes the long streams of a call in
+ * parallel: at their sync markers, or at block starts it finds. */
 int zb200_inflate_batch_dev(const void *d_src, const uint64_t *d_src_off, size_t n,
                             void *d_dst, const uint64_t *d_dst_off, uint64_t *d_dst_len,
                             int32_t *d_status, int wrap, void *stream);
