@@ -1,2 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 5 --warmup 3 > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.log; cut -c1-260 gpurun_out/bench_n4.json; grep -o '"e2e": {[^}]*}' gpurun_out/bench_n4.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 tools/dist_check.py 2>&1 | tail -1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/bench16.json 2> gpurun_out/bench16.log; tail -1 gpurun_out/bench16.log | cut -c1-1500
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
