@@ -983,9 +983,14 @@ struct Packer {
         for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(kFullMask, x, k); if (lane >= k) x += y; }
         if (lane == 31) warp_sums[warp] = x;
         __syncthreads();
-        uint32_t before = 0, total = 0;
+        // the eight warp sums: every warp scans them with three shuffles (lanes 0..7 hold one each) instead of reading all eight
+        static_assert(kPackThreads / 32 == 8, "the cross-warp scan below is written for eight warps");
+        uint32_t ws = warp_sums[lane & 7];
 #pragma unroll
-        for (int w = 0; w < kPackThreads / 32; w++) { const uint32_t s = warp_sums[w]; if (w < warp) before += s; total += s; }
+        for (int k = 1; k < 8; k <<= 1) { const uint32_t y = __shfl_up_sync(kFullMask, ws, k, 8); if ((lane & 7) >= k) ws += y; }
+        const uint32_t total = __shfl_sync(kFullMask, ws, 7);
+        const uint32_t upto = __shfl_sync(kFullMask, ws, warp ? warp - 1 : 0);
+        const uint32_t before = warp ? upto : 0u;
         const uint32_t off = carry_bits + before + x - nbits;
         if (n0) put(cur, off, v0);
         if (n1) put(cur, off + n0, v1);
