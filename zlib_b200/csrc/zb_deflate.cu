@@ -1102,14 +1102,14 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
                     const uint32_t e = s_codes[tk & 0xff];
                     v = e & 0xffffu; nb = e >> 16;
                 } else {
+                    // length part (<= 20 bits) and distance part (<= 28 bits) are composed in 32 bits each, then joined once
                     const uint32_t l = tk & 0xff, lc = len_code(l), le = len_extra_bits(lc);
                     const uint32_t e = s_codes[257 + lc];
-                    v = e & 0xffffu; nb = e >> 16;
-                    if (le) { v |= (uint64_t)(l & ((1u << le) - 1u)) << nb; nb += le; }
+                    const uint32_t lpart = (e & 0xffffu) | ((l & ((1u << le) - 1u)) << (e >> 16)), lbits = (e >> 16) + le;
                     const uint32_t d = dist - 1, dc = dist_code(d), de = dist_extra_bits(dc);
                     const uint32_t f = s_codes[288 + dc];
-                    v |= (uint64_t)(f & 0xffffu) << nb; nb += f >> 16;
-                    if (de) { v |= (uint64_t)(d & ((1u << de) - 1u)) << nb; nb += de; }
+                    const uint32_t dpart = (f & 0xffffu) | ((d & ((1u << de) - 1u)) << (f >> 16)), dbits = (f >> 16) + de;
+                    v = (uint64_t)lpart | ((uint64_t)dpart << lbits); nb = lbits + dbits;
                 }
             } else if (i == cnt) {
                 const uint32_t e = s_codes[256];                // end of block
