@@ -507,6 +507,8 @@ struct TreeScratch {
     uint16_t llen[288 + 2], dlen[32 + 2];                       // +sentinel slot for the run-length scan
     uint16_t blfreq[20], bllen[20], blcode[20];
     uint16_t lcode[288], dcode[32];
+    uint16_t items[320];                                        // run-length items of both length arrays, in sending order
+    int nitems;
 };
 
 struct BitSink {                                                // serial bit writer into global words
@@ -639,36 +641,43 @@ __device__ int warp_make_code(TreeScratch* t, int nsym, int max_length, uint16_t
     return max_code;
 }
 
-// Run-length walk over code lengths (trees.c:707-797): sink == nullptr tallies blfreq, else emits.
-__device__ void walk_lengths(TreeScratch* t, uint16_t* lens, int max_code, BitSink* sink)
+// Run-length walk over code lengths (scan_tree, trees.c:707-748): tallies blfreq and keeps what it found as items
+// (code-length symbol | extra value << 5), so that sending the trees (send_tree, trees.c:752-797) is a loop over the items
+// instead of a second walk -- both run on one lane, and the walk is the longer of the two.
+__device__ void walk_lengths(TreeScratch* t, uint16_t* lens, int max_code)
 {
     int prevlen = -1, nextlen = lens[0], count = 0, maxc = 7, minc = 4;
+    int ni = t->nitems;
     if (nextlen == 0) { maxc = 138; minc = 3; }
     lens[max_code + 1] = 0xffff;
     for (int n = 0; n <= max_code; n++) {
         const int cur = nextlen; nextlen = lens[n + 1];
         if (++count < maxc && cur == nextlen) continue;
         if (count < minc) {
-            if (sink) { do sink->put(t->blcode[cur], t->bllen[cur]); while (--count); }
-            else t->blfreq[cur] = (uint16_t)(t->blfreq[cur] + count);
+            t->blfreq[cur] = (uint16_t)(t->blfreq[cur] + count);
+            do t->items[ni++] = (uint16_t)cur; while (--count);
         } else if (cur != 0) {
-            if (cur != prevlen) {
-                if (sink) { sink->put(t->blcode[cur], t->bllen[cur]); count--; }
-                else t->blfreq[cur]++;
-            }
-            if (sink) { sink->put(t->blcode[16], t->bllen[16]); sink->put((uint32_t)count - 3, 2); }
-            else t->blfreq[16]++;
+            if (cur != prevlen) { t->blfreq[cur]++; t->items[ni++] = (uint16_t)cur; count--; }
+            t->blfreq[16]++; t->items[ni++] = (uint16_t)(16 | ((count - 3) << 5));
         } else if (count <= 10) {
-            if (sink) { sink->put(t->blcode[17], t->bllen[17]); sink->put((uint32_t)count - 3, 3); }
-            else t->blfreq[17]++;
+            t->blfreq[17]++; t->items[ni++] = (uint16_t)(17 | ((count - 3) << 5));
         } else {
-            if (sink) { sink->put(t->blcode[18], t->bllen[18]); sink->put((uint32_t)count - 11, 7); }
-            else t->blfreq[18]++;
+            t->blfreq[18]++; t->items[ni++] = (uint16_t)(18 | ((count - 11) << 5));
         }
         count = 0; prevlen = cur;
         if (nextlen == 0) { maxc = 138; minc = 3; }
         else if (cur == nextlen) { maxc = 6; minc = 3; }
         else { maxc = 7; minc = 4; }
+    }
+    t->nitems = ni;
+}
+
+__device__ void send_items(const TreeScratch* t, BitSink* sink)
+{
+    for (int i = 0; i < t->nitems; i++) {
+        const uint32_t it = t->items[i], sym = it & 31u;
+        sink->put(t->blcode[sym], t->bllen[sym]);
+        if (sym >= 16) sink->put(it >> 5, sym == 16 ? 2 : sym == 17 ? 3 : 7);
     }
 }
 
@@ -728,8 +737,9 @@ k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict
     // ---- code-length code and header ----
     if (lane == 0) {
         for (int i = 0; i < 19; i++) t->blfreq[i] = 0;
-        walk_lengths(t, t->llen, lmax, nullptr);
-        walk_lengths(t, t->dlen, dmax, nullptr);
+        t->nitems = 0;
+        walk_lengths(t, t->llen, lmax);
+        walk_lengths(t, t->dlen, dmax);
         for (int i = 0; i < 19; i++) t->freq[i] = t->blfreq[i];
     }
     __syncwarp();
@@ -753,8 +763,7 @@ k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict
             BitSink sink{blk_hdr + b * kHdrWords, 0, 0, 0, 0};
             sink.put((uint32_t)lmax + 1 - 257, 5); sink.put((uint32_t)dmax + 1 - 1, 5); sink.put((uint32_t)max_bl + 1 - 4, 4);
             for (int r = 0; r <= max_bl; r++) sink.put(t->bllen[c_bl_order[r]], 3);
-            walk_lengths(t, t->llen, lmax, &sink);
-            walk_lengths(t, t->dlen, dmax, &sink);
+            send_items(t, &sink);
             sink.finish();
             hdr_bits = sink.total;
         }
