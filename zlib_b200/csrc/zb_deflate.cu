@@ -241,12 +241,12 @@ struct Found { uint32_t len, dist; };
 
 // longest_match (deflate.c:1027-1168) at window offset `o` (= absolute position gp): candidates from the dist16 chain,
 // quick reject on the word that ends at the byte a better match must reach, strictly longer wins, stop at nice.
-__device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, const uint16_t* dp, uint32_t maxlen,
+__device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, const uint16_t* dp, uint32_t head, uint32_t maxlen,
                                              int chain, uint32_t nice_eff, uint32_t prev_len)
 {
     Found f{kMinMatch - 1, 0};
     if (prev_len > f.len) f.len = prev_len;                     // deflate_slow: only a longer match is of interest
-    uint32_t acc = dp[0];
+    uint32_t acc = head;                                        // = dp[0]: the caller may have it cached
     if (acc == 0 || f.len >= maxlen) return f;
     uint32_t qoff = f.len >= 4 ? f.len - 3 : 0u, qmask = f.len >= 3 ? 0xffffffffu : 0xffffffu;
     uint32_t hq = lds32u(s_mem, o + qoff);
@@ -362,12 +362,25 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     uint32_t ntok = 0, pos = s0;
     if (s0 < blk_end) {
         if (kind == 1) {                                        // deflate_fast, deflate.c:1448-1546
+            // Chain heads of neighbouring positions share a 32-byte sector that L1 (3 % hits: the window image leaves it
+            // ~30 KB) has lost by the time the next token starts.  Four of them are kept per thread in the shared arrays of
+            // the later phases, which are idle during the walk: one 8-byte load serves up to four token starts.
+            s_first[tid] = 0xffffffffu;
+            auto head_of = [&](uint32_t q) -> uint32_t {            // dist16[q]
+                const uint32_t g = q >> 2;
+                if (s_first[tid] != g) {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2*>(dist16) + g);
+                    s_end[tid] = v.x; s_cnt[tid] = v.y; s_first[tid] = g;
+                }
+                const uint32_t w = (q & 2u) ? s_cnt[tid] : s_end[tid];
+                return (q & 1u) ? w >> 16 : w & 0xffffu;
+            };
             while (pos < s1) {
                 const uint32_t maxlen = min(kMaxMatch, blk_end - pos);
                 Found f{0, 0};
                 if (maxlen >= kMinMatch && max_chain > 0) {
                     if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, 0);
-                    else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), maxlen, max_chain, min(nice, maxlen), 0);
+                    else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), kSmemLinks ? links[pos - win_beg] : head_of(pos), maxlen, max_chain, min(nice, maxlen), 0);
                 }
                 if (f.len >= kMinMatch) { mine[ntok++] = (f.dist << 16) | (f.len - kMinMatch); pos += f.len; }
                 else { mine[ntok++] = byte_at(pos); pos++; }
@@ -384,7 +397,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                     if (maxlen >= kMinMatch && prev_len < max_lazy) {
                         const int chain = prev_len >= good ? max(max_chain >> 2, 1) : max_chain;
                         if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, prev_len);
-                        else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), maxlen, chain, min(nice, maxlen), prev_len);
+                        else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), links[pos - win_beg], maxlen, chain, min(nice, maxlen), prev_len);
                         if (f.dist == 0) f.len = kMinMatch - 1;                  // nothing longer than the pending match
                         if (f.len <= 5 && (strategy == 1 || (f.len == kMinMatch && f.dist > kTooFar))) f.len = kMinMatch - 1;   // Z_FILTERED, TOO_FAR
                     }
