@@ -252,7 +252,7 @@ __device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, c
     uint32_t hq = lds32u(s_mem, o + qoff);
     do {
         if (acc > kWindow) break;
-        const uint32_t d = *(dp - acc);                         // next link: issued before the compare so the L2 trip overlaps it
+        const uint32_t d = chain > 1 ? *(dp - acc) : 0u;        // next link: issued before the compare so the L2 trip overlaps it; not for the last candidate the budget allows
         const uint32_t co = o - acc;
         const uint32_t x = lds32u(s_mem, co + qoff) ^ hq;
         if ((x & qmask) == 0) {
