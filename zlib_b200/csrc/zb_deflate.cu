@@ -375,6 +375,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                 const uint32_t w = (q & 2u) ? s_cnt[tid] : s_end[tid];
                 return (q & 1u) ? w >> 16 : w & 0xffffu;
             };
+            uint32_t held = 0;                                  // the even-numbered token waiting for its partner
             while (pos < s1) {
                 const uint32_t maxlen = min(kMaxMatch, blk_end - pos);
                 Found f{0, 0};
@@ -382,9 +383,15 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                     if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, 0);
                     else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), kSmemLinks ? links[pos - win_beg] : head_of(pos), maxlen, max_chain, min(nice, maxlen), 0);
                 }
-                if (f.len >= kMinMatch) { mine[ntok++] = (f.dist << 16) | (f.len - kMinMatch); pos += f.len; }
-                else { mine[ntok++] = byte_at(pos); pos++; }
+                // tokens leave in pairs (the private region is 8-byte aligned): half as many store requests to L2
+                uint32_t tk;
+                if (f.len >= kMinMatch) { tk = (f.dist << 16) | (f.len - kMinMatch); pos += f.len; }
+                else { tk = byte_at(pos); pos++; }
+                if (ntok & 1u) *reinterpret_cast<uint2*>(mine + ntok - 1) = make_uint2(held, tk);
+                else held = tk;
+                ntok++;
             }
+            if (ntok & 1u) mine[ntok - 1] = held;
         } else {                                                // deflate_slow, deflate.c:1554-1674
             uint32_t prev_len = kMinMatch - 1, prev_dist = 0;
             bool avail = false;                                 // position pos-1 is pending (as a literal or as prev match)
