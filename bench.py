@@ -202,7 +202,7 @@ def run_reference(args):
     for i in range(args.warmup + args.steps):
         r = reference_compress_throughput(1, sample)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libzref.so not built on this box"}))
+            emit_line({"impl": "reference", "unavailable": "oracle/_ref/libzref.so not built on this box"})
             return 0
         if i >= args.warmup:
             vals.append(r[0])
@@ -217,12 +217,35 @@ def run_reference(args):
                              "sample": f"compress2 level 1 over {nbytes >> 20} MiB of the mixed corpus, one {nbytes // cores >> 20} MiB slice per host thread"},
             "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ratio": round(ratio, 4), "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------- our arm
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line.  Libraries write there too (NCCL prints its version banner on the first communicator),
+    so file descriptor 1 is pointed at stderr for the run and the line goes to a duplicate of the original."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -578,7 +601,7 @@ def main():
                 "ratio": round(n / clen1, 4), "compressed_bytes": int(clen1),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "verified_by_reference": verified, "extra": extra}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
