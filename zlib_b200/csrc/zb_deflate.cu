@@ -219,8 +219,8 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
 // they also stage the links of the window (128 KiB more shared memory, one CTA per SM) and run 1024 threads
 // (32-byte sub-units).
 constexpr int kWalkThreadsFast = 512, kWalkThreadsLazy = 1024;
-constexpr uint32_t kSubSlotsMax = 66;                           // token slots per sub-unit incl. two spare in front: max over both shapes
-constexpr uint32_t kTmpPerBlock = 1024 * 34 > 512 * 66 ? 1024 * 34 : 512 * 66;   // private token slots per block
+constexpr uint32_t kSubSlotsMax = 68;                           // token slots per sub-unit incl. four in front (two spare, 16-byte alignment): max over both shapes
+constexpr uint32_t kTmpPerBlock = 1024 * 36 > 512 * 68 ? 1024 * 36 : 512 * 68;   // private token slots per block
 constexpr uint32_t kWalkPad = 272;                              // lookahead behind the block (kMaxMatch + word slack)
 // Shared-memory image of the window: rows of 128 bytes followed by one pad word that repeats the first word of
 // the next row.  The lanes of a warp sit 64 bytes apart (one sub-unit each): without the skew they would share two
@@ -307,7 +307,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
     __shared__ uint32_t s_hist[kHistSize];
-    constexpr uint32_t kSub = kBlockBytes / kT, kSubSlots = kSub + 2;   // input bytes / private token slots per thread
+    constexpr uint32_t kSub = kBlockBytes / kT, kSubSlots = kSub + 4;   // input bytes / private token slots per thread (16-byte aligned regions)
     __shared__ uint32_t s_end[kT];                    // end position of each thread's walk, then its prefix maximum
     __shared__ uint32_t s_cnt[kT];                    // kept tokens per thread, then their exclusive prefix sum
     __shared__ uint32_t s_first[kT];
@@ -358,7 +358,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
 
     // ---- walk this thread's sub-unit ----
     const uint32_t s0 = blk_beg + tid * kSub, s1 = min(s0 + kSub, blk_end);
-    uint32_t* mine = tok_tmp + (size_t)b * kTmpPerBlock + (size_t)tid * kSubSlots + 2;
+    uint32_t* mine = tok_tmp + (size_t)b * kTmpPerBlock + (size_t)tid * kSubSlots + 4;
     uint32_t ntok = 0, pos = s0;
     if (s0 < blk_end) {
         if (kind == 1) {                                        // deflate_fast, deflate.c:1448-1546
@@ -375,7 +375,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                 const uint32_t w = (q & 2u) ? s_cnt[tid] : s_end[tid];
                 return (q & 1u) ? w >> 16 : w & 0xffffu;
             };
-            uint32_t held = 0;                                  // the even-numbered token waiting for its partner
+            uint32_t held0 = 0, held1 = 0, held2 = 0;           // tokens waiting for the fourth of their group
             while (pos < s1) {
                 const uint32_t maxlen = min(kMaxMatch, blk_end - pos);
                 Found f{0, 0};
@@ -383,15 +383,23 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                     if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, 0);
                     else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), kSmemLinks ? links[pos - win_beg] : head_of(pos), maxlen, max_chain, min(nice, maxlen), 0);
                 }
-                // tokens leave in pairs (the private region is 8-byte aligned): half as many store requests to L2
+                // tokens leave four at a time (the private region is 16-byte aligned): a quarter of the store requests to L2
                 uint32_t tk;
                 if (f.len >= kMinMatch) { tk = (f.dist << 16) | (f.len - kMinMatch); pos += f.len; }
                 else { tk = byte_at(pos); pos++; }
-                if (ntok & 1u) *reinterpret_cast<uint2*>(mine + ntok - 1) = make_uint2(held, tk);
-                else held = tk;
+                const uint32_t ph = ntok & 3u;
+                if (ph == 3u) *reinterpret_cast<uint4*>(mine + ntok - 3) = make_uint4(held0, held1, held2, tk);
+                else if (ph == 2u) held2 = tk;
+                else if (ph == 1u) held1 = tk;
+                else held0 = tk;
                 ntok++;
             }
-            if (ntok & 1u) mine[ntok - 1] = held;
+            {
+                const uint32_t ph = ntok & 3u, at = ntok - ph;
+                if (ph > 0) mine[at] = held0;
+                if (ph > 1) mine[at + 1] = held1;
+                if (ph > 2) mine[at + 2] = held2;
+            }
         } else {                                                // deflate_slow, deflate.c:1554-1674
             uint32_t prev_len = kMinMatch - 1, prev_dist = 0;
             bool avail = false;                                 // position pos-1 is pending (as a literal or as prev match)
@@ -473,7 +481,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
 #pragma unroll
     for (int w = 0; w < kT / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; all += v; }
     // region descriptor for the copy: {first kept slot (index into this block's private slots), output offset | count << 16}
-    s_first[tid] = (uint32_t)tid * kSubSlots + (uint32_t)(first + 2);
+    s_first[tid] = (uint32_t)tid * kSubSlots + (uint32_t)(first + 4);
     s_cnt[tid] = (before + x - keep) | (keep << 16);             // a block holds at most 32768 tokens, a sub-unit at most 66
     __syncthreads();
     // ---- each warp moves its 32 regions, coalesced, and tallies ----
