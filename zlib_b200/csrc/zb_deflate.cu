@@ -241,6 +241,7 @@ struct Found { uint32_t len, dist; };
 
 // longest_match (deflate.c:1027-1168) at window offset `o` (= absolute position gp): candidates from the dist16 chain,
 // quick reject on the word that ends at the byte a better match must reach, strictly longer wins, stop at nice.
+template <bool kSkipLast>                                       // links in global memory: no load for the last candidate the budget allows
 __device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, const uint16_t* dp, uint32_t head, uint32_t maxlen,
                                              int chain, uint32_t nice_eff, uint32_t prev_len)
 {
@@ -252,7 +253,7 @@ __device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, c
     uint32_t hq = lds32u(s_mem, o + qoff);
     do {
         if (acc > kWindow) break;
-        const uint32_t d = chain > 1 ? *(dp - acc) : 0u;        // next link: issued before the compare so the L2 trip overlaps it; not for the last candidate the budget allows
+        const uint32_t d = (!kSkipLast || chain > 1) ? *(dp - acc) : 0u;   // next link: issued before the compare so that its trip overlaps it
         const uint32_t co = o - acc;
         const uint32_t x = lds32u(s_mem, co + qoff) ^ hq;
         if ((x & qmask) == 0) {
@@ -307,7 +308,8 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
     __shared__ uint32_t s_hist[kHistSize];
-    constexpr uint32_t kSub = kBlockBytes / kT, kSubSlots = kSub + 4;   // input bytes / private token slots per thread (16-byte aligned regions)
+    constexpr uint32_t kFront = kSmemLinks ? 2 : 4;             // spare slots in front of a region; four keep the greedy shape's regions 16-byte aligned
+    constexpr uint32_t kSub = kBlockBytes / kT, kSubSlots = kSub + kFront;   // input bytes / private token slots per thread
     __shared__ uint32_t s_end[kT];                    // end position of each thread's walk, then its prefix maximum
     __shared__ uint32_t s_cnt[kT];                    // kept tokens per thread, then their exclusive prefix sum
     __shared__ uint32_t s_first[kT];
@@ -358,7 +360,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
 
     // ---- walk this thread's sub-unit ----
     const uint32_t s0 = blk_beg + tid * kSub, s1 = min(s0 + kSub, blk_end);
-    uint32_t* mine = tok_tmp + (size_t)b * kTmpPerBlock + (size_t)tid * kSubSlots + 4;
+    uint32_t* mine = tok_tmp + (size_t)b * kTmpPerBlock + (size_t)tid * kSubSlots + kFront;
     uint32_t ntok = 0, pos = s0;
     if (s0 < blk_end) {
         if (kind == 1) {                                        // deflate_fast, deflate.c:1448-1546
@@ -381,7 +383,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                 Found f{0, 0};
                 if (maxlen >= kMinMatch && max_chain > 0) {
                     if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, 0);
-                    else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), kSmemLinks ? links[pos - win_beg] : head_of(pos), maxlen, max_chain, min(nice, maxlen), 0);
+                    else f = walk_search<!kSmemLinks>(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), kSmemLinks ? links[pos - win_beg] : head_of(pos), maxlen, max_chain, min(nice, maxlen), 0);
                 }
                 // tokens leave four at a time (the private region is 16-byte aligned): a quarter of the store requests to L2
                 uint32_t tk;
@@ -412,7 +414,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                     if (maxlen >= kMinMatch && prev_len < max_lazy) {
                         const int chain = prev_len >= good ? max(max_chain >> 2, 1) : max_chain;
                         if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, prev_len);
-                        else f = walk_search(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), links[pos - win_beg], maxlen, chain, min(nice, maxlen), prev_len);
+                        else f = walk_search<!kSmemLinks>(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), links[pos - win_beg], maxlen, chain, min(nice, maxlen), prev_len);
                         if (f.dist == 0) f.len = kMinMatch - 1;                  // nothing longer than the pending match
                         if (f.len <= 5 && (strategy == 1 || (f.len == kMinMatch && f.dist > kTooFar))) f.len = kMinMatch - 1;   // Z_FILTERED, TOO_FAR
                     }
@@ -481,7 +483,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
 #pragma unroll
     for (int w = 0; w < kT / 32; w++) { const uint32_t v = s_wsum[w]; if (w < warp) before += v; all += v; }
     // region descriptor for the copy: {first kept slot (index into this block's private slots), output offset | count << 16}
-    s_first[tid] = (uint32_t)tid * kSubSlots + (uint32_t)(first + 4);
+    s_first[tid] = (uint32_t)tid * kSubSlots + (uint32_t)(first + (int)kFront);
     s_cnt[tid] = (before + x - keep) | (keep << 16);             // a block holds at most 32768 tokens, a sub-unit at most 66
     __syncthreads();
     // ---- each warp moves its 32 regions, coalesced, and tallies ----
