@@ -1,2 +1,2 @@
-python -m pytest tests/test_deflate_gpu.py tests/test_stream_gpu.py -m gpu -x -q 2>&1 | tail -2
-python tools/probe_codec.py 1024 2>&1 | head -2
+python bench.py > gpurun_out/bench20.json 2> gpurun_out/bench20.log; python -c "
+import json; d=json.load(open('gpurun_out/bench20.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac']); print({k:(v.get('GBps') if isinstance(v,dict) else v) for k,v in d['extra'].items()})"
