@@ -47,7 +47,12 @@ void  zb200_free_pinned(void *p);
 void *zb200_alloc_device(size_t bytes);
 void  zb200_free_device(void *p);
 int   zb200_copy(void *dst, const void *src, size_t bytes, void *stream);   /* any direction, synchronous */
+int   zb200_copy_async(void *dst, const void *src, size_t bytes, void *stream);   /* returns once enqueued */
 int   zb200_sync(void *stream);
+/* Page-locks host memory the caller already owns (e.g. a shared-memory mapping that several one-GPU processes
+ * write their shards into), so that copies to and from it run at pinned speed and asynchronously. */
+int   zb200_host_register(void *host_ptr, size_t bytes);
+int   zb200_host_unregister(void *host_ptr);
 
 /* ---- checksums: crc32() + adler32() in one pass (qcsrc/crc32.c:219, adler32.c:57) ----
  * Computes crc32(0, buf, len) and adler32(1, buf, len); either result pointer may
@@ -144,11 +149,6 @@ uint64_t zb200_kernel_launches(void);
  * stream, zb200_profile_report() synchronises and writes "kernel=total_ms:launches;..." . */
 void zb200_profile(int enable);
 int  zb200_profile_report(char *out, size_t cap);
-
-/* Synthetic corpora of SURVEY.md section 8(d): kind 0 = text (T), 1 = mixed (M),
- * 2 = xorshift64* noise.  Deterministic in (kind, seed, offset); host memory only.
- * Workload generator for benchmarks and tests, not part of the codec. */
-void zb200_synth(void *host_dst, size_t len, int kind, uint64_t seed);
 
 #ifdef __cplusplus
 }

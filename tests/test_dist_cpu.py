@@ -222,3 +222,105 @@ def test_sharded_zip_archive(world, tmp_path):
         r = subprocess.run([miniunz, "-o", str(tmp_path / "sharded.zip")], cwd=out, capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
         assert sum(len(fs) for _, _, fs in os.walk(out)) == 45
+
+
+# ---------------------------------------------------------------------------------------------
+# deflate_rounds: pieces dealt round robin, transfers of round j while round j + 1 is compressed (bench.py --gpus N)
+# ---------------------------------------------------------------------------------------------
+class _StandInLib:
+    """What deflate_rounds needs from the library, on host pointers: system zlib as the per-piece compressor (raw
+    deflate, preset dictionary, Z_SYNC_FLUSH unless last); the combine is the real host-side crc32_combine."""
+
+    def __init__(self, real):
+        import ctypes as C
+        self.real, self.C = real, C
+        outer = self
+
+        class _Dll:
+            @staticmethod
+            def zb200_copy_async(dst, src, n, stream):
+                C.memmove(dst, src, n)
+                return 0
+
+            @staticmethod
+            def zb200_sync(stream):
+                return 0
+        self.dll = _Dll()
+
+    def _check(self, rc, what):
+        assert rc == 0, what
+
+    def crc32_combine(self, a, b, n):
+        return self.real.crc32_combine(a, b, n)
+
+    def deflate_shard(self, src, n, dict_, dict_len, dst, cap, level, wrap, flags, stream=None):
+        C = self.C
+        raw = C.string_at(src, n)
+        zd = C.string_at(dict_, dict_len) if dict_len else None
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY, zd) if zd else zlib.compressobj(6, zlib.DEFLATED, -15)
+        z = co.compress(raw) + (co.flush(zlib.Z_SYNC_FLUSH) if (flags & 1) else co.flush(zlib.Z_FINISH))
+        assert len(z) <= cap
+        C.memmove(dst, z, len(z))
+        return len(z), zlib.crc32(raw), zlib.adler32(raw)
+
+
+def _worker_rounds(rank, world, port, total, P, host_mode, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes as C
+        import numpy as np
+        import zhelpers
+        from zlib_b200 import dist as zd, load, binding as zb
+        lib = _StandInLib(load())
+        data = np.frombuffer(zhelpers.corpus(1, total, 8), dtype=np.uint8).copy()
+        ranges = zd.piece_ranges(total, world, P)
+        assert sorted(x for r in ranges for x in r if x[1] > x[0])[0][0] == 0
+        pieces, outs = [], []
+        for a, b in ranges[rank]:
+            dl = min(a, zd.WINDOW)
+            pieces.append((data.ctypes.data + a, b - a, data.ctypes.data + a - dl, dl))
+            outs.append(torch.empty(b - a + 4096, dtype=torch.uint8))
+        # the last piece of the stream is the last NON-EMPTY one; here sizes are chosen so that every piece is non-empty
+        final = torch.zeros(total + 65536, dtype=torch.uint8) if rank == 0 and not host_mode else None
+        host_final = None
+        if host_mode:                                            # every rank writes into its own buffer; rank 0's is checked piecewise
+            hbuf = np.zeros(total + 65536, dtype=np.uint8)
+            host_final = hbuf.ctypes.data
+        tot, crc, adl, n_in = zd.deflate_rounds(lib, pieces, 6, zb.WRAP_ZLIB, root=0, outs=outs, final=final, host_final=host_final)
+        assert n_in == total and crc == zlib.crc32(data.tobytes()) and adl == zlib.adler32(data.tobytes())
+        if host_mode:
+            # gather the per-rank host buffers: in the real run they are ONE shared mapping; here add them up
+            t = torch.from_numpy(hbuf.astype(np.int32))
+            dist.all_reduce(t)
+            z = bytes(t.to(torch.uint8).numpy()[:tot])
+            if rank == 0:
+                hdr = C.string_at(host_final, 2)
+                assert z[:2] == hdr
+        else:
+            z = bytes(final.numpy()[:tot]) if rank == 0 else None
+        if rank == 0:
+            assert zlib.decompress(z) == data.tobytes()
+            orc = zhelpers.Oracle()
+            rc, dec, used = orc.inflate(z, total, 1)
+            assert rc == 0 and dec == data.tobytes() and used == len(z)
+        q.put((rank, "ok"))
+    except Exception:          # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,total,P,host_mode", [(2, 131072 * 12, 3, False), (3, 131072 * 12 - 77, 2, False), (2, 131072 * 8, 4, True)])
+def test_rounds_assemble_one_stream(world, total, P, host_mode):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_rounds, args=(r, world, port, total, P, host_mode, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert all(m == "ok" for _, m in res), res

@@ -115,6 +115,8 @@ class Lib:
             "zb200_alloc_pinned": (vp, [sz]), "zb200_free_pinned": (None, [vp]),
             "zb200_alloc_device": (vp, [sz]), "zb200_free_device": (None, [vp]),
             "zb200_copy": (C.c_int, [vp, vp, sz, vp]), "zb200_sync": (C.c_int, [vp]),
+            "zb200_copy_async": (C.c_int, [vp, vp, sz, vp]),
+            "zb200_host_register": (C.c_int, [vp, sz]), "zb200_host_unregister": (C.c_int, [vp]),
             "zb200_checksum": (C.c_int, [vp, sz, u32p, u32p, vp]),
             "zb200_checksum_dev": (C.c_int, [vp, sz, vp, vp]),
             "zb200_checksum_batch": (C.c_int, [vp, vp, sz, vp, vp, vp]),
@@ -129,7 +131,6 @@ class Lib:
             "zb200_inflate_batch_dev": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, C.c_int, vp]),
             "zb200_kernel_launches": (C.c_uint64, []),
             "zb200_profile": (None, [C.c_int]), "zb200_profile_report": (C.c_int, [C.c_char_p, sz]),
-            "zb200_synth": (None, [vp, sz, C.c_int, C.c_uint64]),
         }
         self.missing = []
         for name, (res, args) in sig.items():
@@ -405,12 +406,10 @@ class Lib:
         self.dll.inflateEnd(C.byref(strm))
         return rc, bytes(out), (msg.decode() if msg else None), tin
 
-    def synth(self, n: int, kind: int = 1, seed: int = 1):
-        """numpy uint8 array of synthetic corpus bytes."""
-        import numpy as np
-        a = np.empty(n, dtype=np.uint8)
-        self.dll.zb200_synth(C.c_void_p(a.ctypes.data), n, kind, seed)
-        return a
+    def synth(self, n: int, kind: int = 1, seed: int = 1, offset: int = 0):
+        """numpy uint8 array of synthetic corpus bytes; generated by libzbsynth.so, not by this library."""
+        from . import synth as _synth
+        return _synth.synth(n, kind, seed, offset)
 
     def profile(self, enable: bool) -> None:
         self.dll.zb200_profile(1 if enable else 0)

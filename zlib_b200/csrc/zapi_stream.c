@@ -122,6 +122,7 @@ ZAPI int deflateInit2_(z_streamp strm, int level, int method, int windowBits, in
     if (memLevel < 1 || memLevel > MAX_MEM_LEVEL || method != Z_DEFLATED || windowBits < 8 || windowBits > 15 ||
         level < 0 || level > 9 || strategy < 0 || strategy > Z_FIXED)
         return Z_STREAM_ERROR;                                  /* deflate.c:265-269 */
+    if (windowBits == 8) windowBits = 9;                        /* deflate.c:270: the reference never runs a 256-byte window */
     if (zb200_init(-1) != Z_OK) return Z_STREAM_ERROR;          /* no device, no stream: there is no CPU path */
     s = (zs *)strm->zalloc(strm->opaque, 1, (uInt)sizeof(zs));
     if (s == Z_NULL) return Z_MEM_ERROR;
@@ -229,6 +230,7 @@ static int zs_compress(z_streamp strm, int level, int final, int force_mark)
     if (!final) flags |= ZB200_DEFLATE_NOT_LAST;
     if (force_mark) flags |= ZB200I_DEFLATE_FORCE_MARK;
     if (s->strategy != Z_DEFAULT_STRATEGY) flags |= (s->strategy << 8);       /* Z_FILTERED, Z_HUFFMAN_ONLY, Z_RLE, Z_FIXED */
+    if (s->wbits != 15) flags |= ZB200I_DEFLATE_WBITS(s->wbits);              /* match distances stay inside the declared window */
     cap = (size_t)compressBound((uLong)s->in_len) + 64;
     if (s->out_pos == s->out_len) s->out_pos = s->out_len = 0;
     if (zs_reserve(&s->out, &s->out_cap, s->out_len + cap)) return Z_MEM_ERROR;
@@ -443,7 +445,7 @@ ZAPI int inflateInit2_(z_streamp strm, int windowBits, const char *version, int 
     if (s == Z_NULL) return Z_MEM_ERROR;
     memset(s, 0, sizeof(zs));
     s->kind = KIND_INFLATE; s->strm = strm; s->inf_wrap = wrap; s->wbits = windowBits;
-    rc = zb200i_inflate_open(&s->inf, wrap);
+    rc = zb200i_inflate_open(&s->inf, wrap | (windowBits << 8));   /* the window size rides along (inflate.c:622) */
     if (rc != Z_OK) { strm->zfree(strm->opaque, s); return rc == Z_MEM_ERROR ? Z_MEM_ERROR : Z_STREAM_ERROR; }
     strm->state = s;
     strm->total_in = strm->total_out = 0;
@@ -466,7 +468,7 @@ ZAPI int inflateReset(z_streamp strm)                           /* inflate.c:103
     strm->adler = 1;
     s->inf_done = s->inf_bad = s->inf_started = 0;
     s->gz_head = Z_NULL; s->gz_st = GZ_FIXED; s->gz_have = 0;
-    return zb200i_inflate_reset(s->inf, s->inf_wrap) == 0 ? Z_OK : Z_STREAM_ERROR;
+    return zb200i_inflate_reset(s->inf, s->inf_wrap | (s->wbits << 8)) == 0 ? Z_OK : Z_STREAM_ERROR;
 }
 
 ZAPI int inflateEnd(z_streamp strm)                             /* inflate.c:1155-1167 */
@@ -565,7 +567,7 @@ ZAPI int inflate(z_streamp strm, int flush)                     /* inflate.c:554
     in0 = strm->avail_in; out0 = strm->avail_out;
     if (zb200i_inflate_mode(s->inf) == 8 /* awaiting dictionary */) { strm->adler = s->inf_dict_id; return Z_NEED_DICT; }
     if (out0 == 0 && in0 == 0) return Z_BUF_ERROR;
-    if (!s->inf_started && flush == Z_FINISH && s->gz_head == Z_NULL && in0 >= 65536u) {
+    if (!s->inf_started && flush == Z_FINISH && s->gz_head == Z_NULL && in0 >= 65536u && s->wbits == 15) {
         /* uncompress() spelled out: the whole stream and the whole buffer in the first call */
         if (zb200i_inflate_try_parallel(strm->next_in, in0, strm->next_out, out0, s->inf_wrap, &in_used, &out_len, &check) == 0) {
             strm->next_in += in_used; strm->avail_in -= (uInt)in_used; strm->total_in += in_used;

@@ -11,6 +11,9 @@ extern "C" {
 /* Forces the empty stored block at the end of a non-final shard even when the shard
  * already ends on a byte boundary (Z_SYNC_FLUSH / Z_FULL_FLUSH marker, deflate.c:808-819). */
 #define ZB200I_DEFLATE_FORCE_MARK 8
+/* deflateInit2's windowBits below 15 (bits 12..15 of flags, 0 = 15): no match reaches further back than the reference's
+ * MAX_DIST = (1 << windowBits) - 262 (h/deflate.h:276), so a decoder that sizes its window from CINFO can follow. */
+#define ZB200I_DEFLATE_WBITS(w) (((w) & 15) << 12)
 
 /* ---- one resumable inflate stream (inflate.c state machine on the device) ---- */
 typedef struct zb200i_inflater zb200i_inflater;

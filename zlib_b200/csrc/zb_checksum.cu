@@ -440,19 +440,20 @@ int checksum_jobs_launch(Ctx* c, const uint8_t* d_base, const ChunkDesc* d_cd, u
     return 0;
 }
 
+int checksum_attr_setup()                                      // once per device, from ensure_init
+{
+    ZB_CUDA(cudaFuncSetAttribute(k_checksum_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMainSmem));
+    return 0;
+}
+
 int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        ZB_CUDA(cudaFuncSetAttribute(k_checksum_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMainSmem));
-        attr_set = true;
-    }
     if (len < kMainThreshold) {
         // one stripe kernel over everything
         uint32_t threads_wanted = (uint32_t)((len + 63) / 64);
         uint32_t blocks = (threads_wanted + kStripeThreads - 1) / kStripeThreads;
         if (blocks < 1) blocks = 1;
-        if (blocks > (uint32_t)kSMs) blocks = kSMs;
+        if (blocks > (uint32_t)device_sms()) blocks = (uint32_t)device_sms();
         uint64_t nthreads = (uint64_t)blocks * kStripeThreads;
         uint32_t stripe = (uint32_t)((len + nthreads - 1) / nthreads);
         if (stripe < 16) stripe = 16;
@@ -468,7 +469,7 @@ int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, 
     const uint64_t n_units = (len - head) / kStride;
     const uint64_t tail_begin = head + n_units * kStride;
     // every resident warp gets the same number of iterations; several rounds only for huge inputs
-    uint64_t warps = (uint64_t)kSMs * kMainWarps;
+    uint64_t warps = (uint64_t)device_sms() * kMainWarps;
     uint64_t rounds = (n_units + warps * kMaxIters - 1) / (warps * kMaxIters);
     uint64_t total_warps = warps * rounds;
     uint32_t iters = (uint32_t)((n_units + total_warps - 1) / total_warps);

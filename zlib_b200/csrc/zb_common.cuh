@@ -18,7 +18,7 @@ enum { ZB_OK = 0, ZB_STREAM_END = 1, ZB_NEED_DICT = 2, ZB_STREAM_ERROR = -2, ZB_
 
 namespace zb {
 
-constexpr int kSMs = 148;                 // B200: 2 dies x 74 SMs
+int device_sms();                          // SM count of the calling thread's device (148 on B200: 2 dies x 74)
 constexpr uint32_t kCrcPoly = 0xEDB88320u;
 constexpr uint32_t kAdlerBase = 65521u;
 
@@ -46,6 +46,7 @@ struct Ctx {
     cudaStream_t aux[2] = {nullptr, nullptr};   // copy-in / copy-out streams of the slab pipeline
     cudaEvent_t* evs = nullptr; int nev = 0;
     int ensure_aux(int nevents);               // both streams and at least `nevents` events
+    int device = 0;                        // the device this context's streams and buffers live on
     Ctx* next = nullptr;
 };
 

@@ -243,7 +243,7 @@ struct Found { uint32_t len, dist; };
 // quick reject on the word that ends at the byte a better match must reach, strictly longer wins, stop at nice.
 template <bool kSkipLast>                                       // links in global memory: no load for the last candidate the budget allows
 __device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, const uint16_t* dp, uint32_t head, uint32_t maxlen,
-                                             int chain, uint32_t nice_eff, uint32_t prev_len)
+                                             int chain, uint32_t nice_eff, uint32_t prev_len, uint32_t max_dist)
 {
     Found f{kMinMatch - 1, 0};
     if (prev_len > f.len) f.len = prev_len;                     // deflate_slow: only a longer match is of interest
@@ -252,7 +252,7 @@ __device__ __forceinline__ Found walk_search(const uint8_t* s_mem, uint32_t o, c
     uint32_t qoff = f.len >= 4 ? f.len - 3 : 0u, qmask = f.len >= 3 ? 0xffffffffu : 0xffffffu;
     uint32_t hq = lds32u(s_mem, o + qoff);
     do {
-        if (acc > kWindow) break;
+        if (acc > max_dist) break;
         const uint32_t d = (!kSkipLast || chain > 1) ? *(dp - acc) : 0u;   // next link: issued before the compare so that its trip overlaps it
         const uint32_t co = o - acc;
         const uint32_t x = lds32u(s_mem, co + qoff) ^ hq;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kT, kSmemLinks ? 1 : 3)
 k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
           uint32_t* __restrict__ tok_tmp, uint32_t* __restrict__ tok, uint32_t* __restrict__ blk_ntok,
           uint32_t* __restrict__ blk_hist, int kind, int max_chain, uint32_t nice, uint32_t max_lazy, uint32_t good,
-          int strategy, const ChunkDesc* __restrict__ cd)
+          int strategy, uint32_t max_dist, const ChunkDesc* __restrict__ cd, uint32_t nblocks, uint32_t* __restrict__ next_block)
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
     __shared__ uint32_t s_hist[kHistSize];
@@ -315,12 +315,28 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     __shared__ uint32_t s_first[kT];
     __shared__ uint32_t s_wsum[kT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t b = blockIdx.x;
+    // Persistent CTAs (next_block != nullptr): the grid is one CTA per resident slot and every CTA takes the next
+    // unclaimed block from a device counter.  The private token regions are then indexed by SLOT, not by block: a few
+    // tens of MB that are rewritten every ~100 us and stay in L2, instead of one region per block of the slab (half a
+    // GB per slab that went out to HBM and came back).
+    __shared__ uint32_t s_claim;
+    const uint32_t slot = blockIdx.x;
+  for (;;) {
+    uint32_t b;
+    if (next_block) {
+        __syncthreads();                                        // the previous block's shared memory is no longer read
+        if (tid == 0) s_claim = atomicAdd(next_block, 1u);
+        __syncthreads();
+        b = s_claim;
+        if (b >= nblocks) return;
+    } else {
+        b = blockIdx.x;
+    }
     uint32_t blk_beg, blk_end, win_beg;                         // absolute positions in buf
     if (cd) {                                                   // job mode: block b is the (b % 4)-th block of a chunk of some job
         const ChunkDesc d = cd[b / kBlocksPerChunk];
         const uint32_t rel = (b % kBlocksPerChunk) * kBlockBytes;
-        if (rel >= d.len) return;                               // short chunk: this block slot is unused (nobody reads it)
+        if (rel >= d.len) { if (next_block) continue; return; } // short chunk: this block slot is unused (nobody reads it)
         blk_beg = d.beg + rel;
         blk_end = d.beg + min(d.len, rel + kBlockBytes);
         win_beg = blk_beg - d.job_beg > kWindow ? blk_beg - kWindow : d.job_beg;
@@ -360,7 +376,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
 
     // ---- walk this thread's sub-unit ----
     const uint32_t s0 = blk_beg + tid * kSub, s1 = min(s0 + kSub, blk_end);
-    uint32_t* mine = tok_tmp + (size_t)b * kTmpPerBlock + (size_t)tid * kSubSlots + kFront;
+    uint32_t* mine = tok_tmp + (size_t)(next_block ? slot : b) * kTmpPerBlock + (size_t)tid * kSubSlots + kFront;
     uint32_t ntok = 0, pos = s0;
     if (s0 < blk_end) {
         if (kind == 1) {                                        // deflate_fast, deflate.c:1448-1546
@@ -383,7 +399,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                 Found f{0, 0};
                 if (maxlen >= kMinMatch && max_chain > 0) {
                     if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, 0);
-                    else f = walk_search<!kSmemLinks>(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), kSmemLinks ? links[pos - win_beg] : head_of(pos), maxlen, max_chain, min(nice, maxlen), 0);
+                    else f = walk_search<!kSmemLinks>(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), kSmemLinks ? links[pos - win_beg] : head_of(pos), maxlen, max_chain, min(nice, maxlen), 0, max_dist);
                 }
                 // tokens leave four at a time (the private region is 16-byte aligned): a quarter of the store requests to L2
                 uint32_t tk;
@@ -414,7 +430,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                     if (maxlen >= kMinMatch && prev_len < max_lazy) {
                         const int chain = prev_len >= good ? max(max_chain >> 2, 1) : max_chain;
                         if (strategy == 3) f = walk_search_rle(s_mem, sm_off + pos - win_beg, pos > win_beg, maxlen, prev_len);
-                        else f = walk_search<!kSmemLinks>(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), links[pos - win_beg], maxlen, chain, min(nice, maxlen), prev_len);
+                        else f = walk_search<!kSmemLinks>(s_mem, sm_off + pos - win_beg, links + (pos - win_beg), links[pos - win_beg], maxlen, chain, min(nice, maxlen), prev_len, max_dist);
                         if (f.dist == 0) f.len = kMinMatch - 1;                  // nothing longer than the pending match
                         if (f.len <= 5 && (strategy == 1 || (f.len == kMinMatch && f.dist > kTooFar))) f.len = kMinMatch - 1;   // Z_FILTERED, TOO_FAR
                     }
@@ -488,7 +504,7 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     __syncthreads();
     // ---- each warp moves its 32 regions, coalesced, and tallies ----
     uint32_t* out = tok + (size_t)b * kBlockBytes;
-    const uint32_t* tmp_blk = tok_tmp + (size_t)b * kTmpPerBlock;
+    const uint32_t* tmp_blk = tok_tmp + (size_t)(next_block ? slot : b) * kTmpPerBlock;
     auto tally = [&](uint32_t v) {
         const bool is_match = (v >> 16) != 0;
         atomicAdd(&s_hist[is_match ? 257 + len_code(v & 0xffffu) : v], 1u);
@@ -516,6 +532,8 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
     __syncthreads();
     for (int i = tid; i < (int)kHistSize; i += kT) blk_hist[(size_t)b * kHistSize + i] = s_hist[i];
     if (tid == 0) blk_ntok[b] = all;
+    if (!next_block) return;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1235,7 +1253,24 @@ __global__ void k_empty_payload(uint8_t* out, uint64_t cap, uint64_t at, int not
 // ------------------------------------------------------------------------------------------
 struct DeflateParams {
     LevelCfg cfg; int level, strategy, wrap, flags;
+    uint32_t max_dist;                                          // kWindow, or the reference's MAX_DIST of a smaller windowBits
 };
+
+// Development knobs (read once): ZB200_WALK_PERSIST=0 restores one CTA per block; ZB200_L1_CHAIN / ZB200_L1_NICE override
+// the level-1 search budget for sweeps.  None of them is part of the interface.
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+static bool walk_persistent() { static const bool on = env_int("ZB200_WALK_PERSIST", 1) != 0; return on; }
+static unsigned walk_grid(uint64_t nblocks, bool lazy_shape)
+{
+    if (!walk_persistent()) return (unsigned)nblocks;
+    const uint64_t slots = (uint64_t)device_sms() * (lazy_shape ? 1 : 3);
+    return (unsigned)std::min<uint64_t>(nblocks, slots);
+}
+static uint64_t walk_slots(uint64_t nblocks) { return walk_persistent() ? std::min<uint64_t>(nblocks, (uint64_t)device_sms() * 3) : nblocks; }
 
 // One slab: d_buf = [dict bytes][n source bytes], contiguous in device memory.  The slab's payload starts at
 // out[(*d_start or 0) + start_add]; *d_end receives where the next slab starts.  Everything is asynchronous on s.
@@ -1256,33 +1291,37 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
     uint32_t *d_hist = nullptr, *d_codes = nullptr, *d_hdr = nullptr, *d_tok = nullptr, *d_ntok = nullptr;
     if (cfg.kind != 0) {
         if ((rc = c->ws[3].ensure(total * 2 + 64)) != 0) return rc;          // dist16
-        if ((rc = c->ws[4].ensure(nblocks * kTmpPerBlock * 4 + 64)) != 0) return rc;               // private token regions
+        if ((rc = c->ws[4].ensure((uint64_t)walk_slots(nblocks) * kTmpPerBlock * 4 + 64)) != 0) return rc;               // private token regions
         if ((rc = c->ws[5].ensure(nblocks * kBlockBytes * 4 + 64)) != 0) return rc;               // tokens, contiguous per block
         if ((rc = c->ws[6].ensure(nblocks * sizeof(BlockMeta))) != 0) return rc;
         if ((rc = c->ws[7].ensure(nblocks * kHistSize * 4)) != 0) return rc;
         if ((rc = c->ws[8].ensure(nblocks * kHistSize * 4)) != 0) return rc;
         if ((rc = c->ws[9].ensure(nblocks * kHdrWords * 4)) != 0) return rc;
-        if ((rc = c->ws[10].ensure(nblocks * 4)) != 0) return rc;
+        if ((rc = c->ws[10].ensure(nblocks * 4 + 16)) != 0) return rc;
         uint16_t* d_dist = c->ws[3].as<uint16_t>();
         uint32_t* d_tmp = c->ws[4].as<uint32_t>();
         d_tok = c->ws[5].as<uint32_t>();
         d_blk = c->ws[6].as<BlockMeta>();
         d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
         d_ntok = c->ws[10].as<uint32_t>();
+        uint32_t* d_next = walk_persistent() ? d_ntok + nblocks : nullptr;   // the walk kernel's block counter
         const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
         if (cfg.chain != 0 && P.strategy != 3) {                // Z_RLE needs no chains
             // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
             if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
             else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
         }
-        if (cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3)
-            ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), (unsigned)nblocks, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_buf, (uint32_t)total,
+        const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
+        const unsigned wgrid = walk_grid(nblocks, lazy_shape);
+        if (d_next) ZB_CUDA(cudaMemsetAsync(d_next, 0, 4, s));
+        if (lazy_shape)
+            ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), wgrid, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_buf, (uint32_t)total,
                       (uint32_t)dict, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy, (const ChunkDesc*)nullptr);
+                      (uint32_t)cfg.good, P.strategy, P.max_dist, (const ChunkDesc*)nullptr, (uint32_t)nblocks, d_next);
         else
-            ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), (unsigned)nblocks, kWalkThreadsFast, kWalkSmem, s, d_buf, (uint32_t)total,
+            ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), wgrid, kWalkThreadsFast, kWalkSmem, s, d_buf, (uint32_t)total,
                       (uint32_t)dict, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy, (const ChunkDesc*)nullptr);
+                      (uint32_t)cfg.good, P.strategy, P.max_dist, (const ChunkDesc*)nullptr, (uint32_t)nblocks, d_next);
         ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, n, d_blk, d_hist,
                   d_codes, d_hdr, P.strategy == 4 ? 1 : 0, (const ChunkDesc*)nullptr, (uint64_t)0);
     }
@@ -1315,31 +1354,35 @@ static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uin
     uint32_t *d_hist = nullptr, *d_codes = nullptr, *d_hdr = nullptr, *d_tok = nullptr, *d_ntok = nullptr;
     if (nchunks && cfg.kind != 0) {
         if ((rc = c->ws[3].ensure(span * 2 + 64)) != 0) return rc;
-        if ((rc = c->ws[4].ensure(nblocks * kTmpPerBlock * 4 + 64)) != 0) return rc;
+        if ((rc = c->ws[4].ensure((uint64_t)walk_slots(nblocks) * kTmpPerBlock * 4 + 64)) != 0) return rc;
         if ((rc = c->ws[5].ensure(nblocks * kBlockBytes * 4 + 64)) != 0) return rc;
         if ((rc = c->ws[6].ensure(nblocks * sizeof(BlockMeta))) != 0) return rc;
         if ((rc = c->ws[7].ensure(nblocks * kHistSize * 4)) != 0) return rc;
         if ((rc = c->ws[8].ensure(nblocks * kHistSize * 4)) != 0) return rc;
         if ((rc = c->ws[9].ensure(nblocks * kHdrWords * 4)) != 0) return rc;
-        if ((rc = c->ws[10].ensure(nblocks * 4)) != 0) return rc;
+        if ((rc = c->ws[10].ensure(nblocks * 4 + 16)) != 0) return rc;
         uint16_t* d_dist = c->ws[3].as<uint16_t>();
         uint32_t* d_tmp = c->ws[4].as<uint32_t>();
         d_tok = c->ws[5].as<uint32_t>();
         d_blk = c->ws[6].as<BlockMeta>();
         d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
         d_ntok = c->ws[10].as<uint32_t>();
+        uint32_t* d_next = walk_persistent() ? d_ntok + nblocks : nullptr;   // the walk kernel's block counter
         if (cfg.chain != 0 && P.strategy != 3) {
             if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
             else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
         }
-        if (cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3)
-            ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), (unsigned)nblocks, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_base, (uint32_t)span,
+        const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
+        const unsigned wgrid = walk_grid(nblocks, lazy_shape);
+        if (d_next) ZB_CUDA(cudaMemsetAsync(d_next, 0, 4, s));
+        if (lazy_shape)
+            ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), wgrid, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_base, (uint32_t)span,
                       0u, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy, d_cd);
+                      (uint32_t)cfg.good, P.strategy, P.max_dist, d_cd, (uint32_t)nblocks, d_next);
         else
-            ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), (unsigned)nblocks, kWalkThreadsFast, kWalkSmem, s, d_base, (uint32_t)span,
+            ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), wgrid, kWalkThreadsFast, kWalkSmem, s, d_base, (uint32_t)span,
                       0u, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy, d_cd);
+                      (uint32_t)cfg.good, P.strategy, P.max_dist, d_cd, (uint32_t)nblocks, d_next);
         ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, span, d_blk, d_hist,
                   d_codes, d_hdr, P.strategy == 4 ? 1 : 0, d_cd, nblocks);
     }
@@ -1409,19 +1452,27 @@ static int deflate_enqueue_dev(Ctx* c, cudaStream_t s, const uint8_t* d_buf, uin
     return 0;
 }
 
+int deflate_setup()                                             // once per device, from ensure_init (under its lock)
+{
+    ZB_CUDA(cudaFuncSetAttribute(k_lz_link<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
+    ZB_CUDA(cudaFuncSetAttribute(k_lz_link<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
+    ZB_CUDA(cudaFuncSetAttribute(k_lz_walk<kWalkThreadsFast, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem));
+    ZB_CUDA(cudaFuncSetAttribute(k_lz_walk<kWalkThreadsLazy, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem + kWalkLinkSmem));
+    return 0;
+}
+
 static int deflate_params(DeflateParams& P, int level, int wrap, int flags)
 {
-    static bool attr = false;
-    if (!attr) {
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_link<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_link<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << kHashBits) * 2));
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_walk<kWalkThreadsFast, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem));
-        ZB_CUDA(cudaFuncSetAttribute(k_lz_walk<kWalkThreadsLazy, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmem + kWalkLinkSmem));
-        attr = true;
-    }
     if (level < 0) level = 6;
     P.cfg = h_levels[level]; P.level = level; P.wrap = wrap; P.flags = flags;
+    if (level == 1) {
+        static const int chain1 = env_int("ZB200_L1_CHAIN", 0), nice1 = env_int("ZB200_L1_NICE", 0);
+        if (chain1 > 0) P.cfg.chain = (uint16_t)chain1;
+        if (nice1 > 0) P.cfg.nice = (uint16_t)nice1;
+    }
     P.strategy = (flags >> 8) & 7;                              // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
+    const int wbits = (flags >> 12) & 15;                       // 0 = 15; deflate.c:270-279, h/deflate.h:276
+    P.max_dist = (wbits >= 9 && wbits < 15) ? (1u << wbits) - 262u : kWindow;
     if (P.strategy == 2 && P.cfg.kind != 0) { P.cfg.chain = 0; P.cfg.kind = 1; }   // literals only (deflate.c:1490)
     return 0;
 }

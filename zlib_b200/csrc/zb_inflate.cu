@@ -351,7 +351,13 @@ __device__ Stop decode_fast(Bits& b, Out& o, const WarpTables* t, const uint8_t*
         const uint32_t tot = (e >> 5) & 31u;
         const uint32_t mlen = (e >> 16) + __funnelshift_r(win & ((1u << tot) - 1u), 0u, e);   // bit 31 is clear: not a literal
         off += tot;
-        if (off >= 32) { off -= 32; lo = hi; hi = nxt; wi++; nxt = __ldg(words + wi + 2); }
+        if (off >= 32) {
+            // the word index moves here too: without this test a stream whose every word crossing falls between a length
+            // and its distance (one-bit codes at an odd phase) would never meet the limit at the top of the loop
+            off -= 32; lo = hi; hi = nxt; wi++;
+            if (wi > w_lim) break;                              // back to the start of this symbol (end_wi / end_off)
+            nxt = __ldg(words + wi + 2);
+        }
         const uint32_t dwin = __funnelshift_r(lo, hi, off);
         const uint32_t de = dtab[dwin & (kDistSize - 1)];
         const uint32_t dtot = (de >> 5) & 31u;
@@ -457,7 +463,10 @@ __device__ void inflate_warp(const uint8_t* in, uint64_t in_len, uint8_t* out, u
                 const uint32_t flg = peek(b, 8); drop(b, 8);
                 if (((cmf << 8) + flg) % 31u) { st->msg = kMsgHeader; stop = kError; continue; }
                 if ((cmf & 15u) != 8u) { st->msg = kMsgMethod; stop = kError; continue; }
-                if ((cmf >> 4) + 8u > 15u) { st->msg = kMsgWindow; stop = kError; continue; }
+                {   // inflate.c:622: a stream that declares a larger window than the caller opened is refused
+                    const uint32_t wb = (st->flags >> 8) & 15u;
+                    if ((cmf >> 4) + 8u > (wb ? wb : 15u)) { st->msg = kMsgWindow; stop = kError; continue; }
+                }
                 s1 = 1; s2 = 0;
                 if (flg & 0x20u) {                    // preset dictionary, inflate.c:630, 761-770
                     if (!streaming) { st->msg = kMsgNeedDict; stop = kError; continue; }
@@ -912,7 +921,11 @@ __device__ bool seg_fast(Bits& b, const WarpTables* t, const uint8_t* in, uint16
         const uint32_t tot = (e >> 5) & 31u;
         const uint32_t mlen = (e >> 16) + __funnelshift_r(win & ((1u << tot) - 1u), 0u, e);
         off += tot;
-        if (off >= 32) { off -= 32; lo = hi; hi = nxt; wi++; nxt = __ldg(words + wi + 2); }
+        if (off >= 32) {
+            off -= 32; lo = hi; hi = nxt; wi++;
+            if (wi > w_lim) break;                              // same bound as in decode_fast: the symbol is redone by the careful loop
+            nxt = __ldg(words + wi + 2);
+        }
         const uint32_t dwin = __funnelshift_r(lo, hi, off);
         const uint32_t de = dtab[dwin & (kDistSize - 1)];
         const uint32_t dtot = (de >> 5) & 31u;
@@ -1322,10 +1335,10 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
         uint32_t ncand = 0;
         ZB_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
         if (source == 0) {
-            ZB_LAUNCH(k_find_markers, kSMs * 8, 256, 0, s, d_src, hdr, len, d_count, d_pos, cand_cap);
+            ZB_LAUNCH(k_find_markers, device_sms() * 8, 256, 0, s, d_src, hdr, len, d_count, d_pos, cand_cap);
         } else {
             uint32_t nprobe = 0;
-            ZB_LAUNCH(k_find_blocks_probe, kSMs * 16, 256, 0, s, d_src, len, hdr * 8 + 1, len * 8, d_count, d_probe, cand_cap);
+            ZB_LAUNCH(k_find_blocks_probe, device_sms() * 16, 256, 0, s, d_src, len, hdr * 8 + 1, len * 8, d_count, d_probe, cand_cap);
             ZB_CUDA(cudaMemcpyAsync(&nprobe, d_count, 4, cudaMemcpyDeviceToHost, s));
             ZB_CUDA(cudaStreamSynchronize(s));
             if (nprobe == 0 || nprobe > cand_cap) return 1;
@@ -1471,7 +1484,7 @@ extern "C" int zb200i_inflate_try_parallel(const uint8_t* in, size_t in_len, uin
 
 // ---- one resumable stream behind zlib.h's inflate() ----
 struct zb200i_inflater {
-    int wrap = 1;
+    int wrap = 1, wbits = 0;
     InfState* d_state = nullptr;
     InfCallResult* d_res = nullptr;
     uint8_t* d_arena = nullptr;                  // [32 KiB history][output window]
@@ -1505,10 +1518,13 @@ static int inflater_write_state(zb200i_inflater* h, int wrap)
 {
     InfState st;
     memset(&st, 0, sizeof(st));
+    const int wbits = (wrap >> 8) & 15;                          // 0 = 15 (inflateInit2's windowBits, inflate.c:622)
+    wrap &= 0xff;
     st.wrap = wrap; st.mode = kModeHead; st.s1 = 1;
+    st.flags = (uint32_t)wbits << 8;
     ZB_CUDA(cudaMemcpyAsync(h->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, h->s));
     ZB_CUDA(cudaStreamSynchronize(h->s));
-    h->wrap = wrap; h->hist = 0; h->mode = kModeHead; h->check = wrap >= ZB200_WRAP_GZIP ? 0u : 1u; h->carry.clear();
+    h->wrap = wrap; h->wbits = wbits; h->hist = 0; h->mode = kModeHead; h->check = wrap >= ZB200_WRAP_GZIP ? 0u : 1u; h->carry.clear();
     h->crc = 0; h->produced = 0;
     return 0;
 }
@@ -1546,7 +1562,7 @@ extern "C" void zb200i_inflate_close(zb200i_inflater* h)
 extern "C" int zb200i_inflate_clone(zb200i_inflater** out, const zb200i_inflater* src)
 {
     zb200i_inflater* h = nullptr;
-    int rc = zb200i_inflate_open(&h, src->wrap);
+    int rc = zb200i_inflate_open(&h, src->wrap | (src->wbits << 8));
     if (rc) return rc;
     cudaError_t e = cudaMemcpy(h->d_state, src->d_state, sizeof(InfState), cudaMemcpyDeviceToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_arena, src->d_arena, kWindow32, cudaMemcpyDeviceToDevice);
@@ -1659,6 +1675,10 @@ extern "C" int zb200i_inflate_run(zb200i_inflater* h, const uint8_t* in, size_t 
         }
         produced += res.out_len;
         st = res.status; m = res.msg;
+        if (res.in_used > total_in) {                                  // the decoder may never run past what it was given
+            set_error("internal error: inflate consumed %llu of %zu input bytes", (unsigned long long)res.in_used, total_in);
+            return ZB_STREAM_ERROR;
+        }
         // account for the input: the decoder consumed res.in_used bytes of [carry | feed]
         const size_t carry_n = h->carry.size();
         size_t from_new = res.in_used > carry_n ? res.in_used - carry_n : 0;

@@ -45,10 +45,23 @@ void set_error(const char* fmt, ...)
     if (getenv("ZB200_TRACE")) fprintf(stderr, "[zb200] %s\n", t_err);
 }
 
-static std::mutex g_mu;
-static int g_state = 0;                    // 0 = untouched, 1 = ready, -1 = failed
-static int g_device = -1;
-static Ctx* g_free = nullptr;
+// Per-device state.  A thread's calls run on its *bound* device (zb200_init(d) binds the calling thread; threads that
+// never called it use the process default = the first device bound, else CUDA's current device).  Every device has its
+// own context pool, table uploads and kernel attributes, so one process can drive all eight GPUs of a box (one host
+// thread per device, see zb_multi.cu) as well as the one-process-per-GPU layout.
+constexpr int kMaxDevices = 32;
+struct DevState {
+    std::mutex mu;
+    std::atomic<int> state{0};             // 0 = untouched, 1 = ready, -1 = failed
+    Ctx* free_list = nullptr;
+    int sms = 148;
+};
+static DevState g_dev[kMaxDevices];
+static std::atomic<int> g_default_device{-1};
+static thread_local int t_device = -1;
+
+int deflate_setup();                       // zb_deflate.cu: kernel attributes (per device)
+int checksum_attr_setup();                 // zb_checksum.cu
 
 int DevBuf::ensure(size_t bytes)
 {
@@ -113,46 +126,63 @@ int Ctx::ensure_aux(int nevents)
     return 0;
 }
 
+static int current_device_index()
+{
+    int dev = t_device;
+    if (dev < 0) dev = g_default_device.load(std::memory_order_acquire);
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev;
+}
+
+int device_sms() { const int d = current_device_index(); return (d >= 0 && d < kMaxDevices) ? g_dev[d].sms : 148; }
+
 int ensure_init()
 {
-    if (g_state == 1) {
-        if (g_device >= 0) cudaSetDevice(g_device);   // calling thread may be new
+    const int dev = current_device_index();
+    if (dev < 0 || dev >= kMaxDevices) { set_error("zb200: device index %d out of range", dev); return ZB_STREAM_ERROR; }
+    DevState& D = g_dev[dev];
+    if (D.state.load(std::memory_order_acquire) == 1) {
+        cudaSetDevice(dev);                                     // the calling thread may be new, or last used another device
         return 0;
     }
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_state == 1) return 0;
+    std::lock_guard<std::mutex> lk(D.mu);
+    if (D.state.load(std::memory_order_relaxed) == 1) { cudaSetDevice(dev); return 0; }
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
         cudaGetLastError();
         set_error("zb200: no CUDA device available -- this library has no CPU path");
-        g_state = -1;
+        D.state.store(-1, std::memory_order_release);
         return ZB_STREAM_ERROR;
     }
-    int dev = 0;
-    if (g_device >= 0) dev = g_device; else cudaGetDevice(&dev);
-    if (cudaSetDevice(dev) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", dev); g_state = -1; return ZB_STREAM_ERROR; }
+    if (dev >= n) { set_error("zb200: device %d does not exist (%d devices)", dev, n); D.state.store(-1, std::memory_order_release); return ZB_STREAM_ERROR; }
+    if (cudaSetDevice(dev) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", dev); D.state.store(-1, std::memory_order_release); return ZB_STREAM_ERROR; }
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); g_state = -1; return ZB_STREAM_ERROR; }
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); D.state.store(-1, std::memory_order_release); return ZB_STREAM_ERROR; }
     if (prop.major != 10) {
         set_error("zb200: device %d is sm_%d%d; this build contains sm_100a code only", dev, prop.major, prop.minor);
-        g_state = -1;
+        D.state.store(-1, std::memory_order_release);
         return ZB_STREAM_ERROR;
     }
-    g_device = dev;
-    if (checksum_setup() != 0) { g_state = -1; return ZB_STREAM_ERROR; }
-    g_state = 1;
+    D.sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    if (checksum_setup() != 0 || checksum_attr_setup() != 0 || deflate_setup() != 0) { D.state.store(-1, std::memory_order_release); return ZB_STREAM_ERROR; }
+    int expected = -1;
+    g_default_device.compare_exchange_strong(expected, dev, std::memory_order_acq_rel);
+    D.state.store(1, std::memory_order_release);
     return 0;
 }
 
 Ctx* ctx_acquire(cudaStream_t use)
 {
+    const int dev = current_device_index();
+    DevState& D = g_dev[dev];
     Ctx* c = nullptr;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (g_free) { c = g_free; g_free = c->next; c->next = nullptr; }
+        std::lock_guard<std::mutex> lk(D.mu);
+        if (D.free_list) { c = D.free_list; D.free_list = c->next; c->next = nullptr; }
     }
     if (!c) {
         c = new Ctx();
+        c->device = dev;
         if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->idle, cudaEventDisableTiming) != cudaSuccess) {
             set_error("stream/event creation failed");
@@ -175,9 +205,10 @@ Ctx* ctx_acquire_own()
 void ctx_release(Ctx* c, cudaStream_t used)
 {
     cudaEventRecord(c->idle, used);
-    std::lock_guard<std::mutex> lk(g_mu);
-    c->next = g_free;
-    g_free = c;
+    DevState& D = g_dev[c->device];
+    std::lock_guard<std::mutex> lk(D.mu);
+    c->next = D.free_list;
+    D.free_list = c;
 }
 
 MemKind classify(const void* p)
@@ -355,11 +386,15 @@ using namespace zb;
 
 ZB_API int zb200_init(int device)
 {
+    if (device >= kMaxDevices) { set_error("zb200_init: device %d out of range", device); return ZB_STREAM_ERROR; }
     if (device >= 0) {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (g_state == 1 && g_device != device) { set_error("zb200 already initialised on device %d", g_device); return ZB_STREAM_ERROR; }
-        g_device = device;
-        if (g_state == -1) g_state = 0;
+        t_device = device;                                      // binds the calling thread
+        DevState& D = g_dev[device];
+        int failed = -1;
+        D.state.compare_exchange_strong(failed, 0);             // a failed attempt may be retried
+    } else {
+        const int d = current_device_index();
+        if (d >= 0 && d < kMaxDevices) { int failed = -1; g_dev[d].state.compare_exchange_strong(failed, 0); }
     }
     return ensure_init();
 }
@@ -402,6 +437,30 @@ ZB_API int zb200_copy(void* dst, const void* src, size_t bytes, void* stream)
     if (rc) return rc;
     ZB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     ZB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+ZB_API int zb200_copy_async(void* dst, const void* src, size_t bytes, void* stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    ZB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+
+ZB_API int zb200_host_register(void* host_ptr, size_t bytes)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    ZB_CUDA(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+ZB_API int zb200_host_unregister(void* host_ptr)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    ZB_CUDA(cudaHostUnregister(host_ptr));
     return 0;
 }
 

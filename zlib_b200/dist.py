@@ -51,6 +51,7 @@ class StreamPlan:
 
 
 def zlib_header(level: int) -> bytes:
+    level = 6 if level < 0 else level                                       # Z_DEFAULT_COMPRESSION, deflate.c:251
     fl = 0 if level < 2 else 1 if level < 6 else 2 if level == 6 else 3     # deflate.c:625-649
     h = (0x78 << 8) | (fl << 6)
     h += 31 - h % 31
@@ -59,6 +60,7 @@ def zlib_header(level: int) -> bytes:
 
 def plan_stream(metas: Sequence[Sequence[int]], level: int, wrap: int, crc_combine: Callable[[int, int, int], int]) -> StreamPlan:
     """metas[r] = (compressed bytes, input bytes, crc32, adler32) in rank order."""
+    level = 6 if level < 0 else level
     header = zlib_header(level) if wrap == zb.WRAP_ZLIB else (
         bytes([31, 139, 8, 0, 0, 0, 0, 0, 2 if level == 9 else 4 if level < 2 else 0, 3]) if wrap == zb.WRAP_GZIP else b"")
     offsets, pos, crc, adl, n_in = [], len(header), 0, 1, 0
@@ -88,6 +90,12 @@ def exchange_meta(local: Sequence[int], device, group=None) -> List[List[int]]:
     return out.view(world, 4).cpu().tolist()
 
 
+def _global(group, r: int) -> int:
+    """send/recv take GLOBAL ranks; `root` and the loop indices here are ranks within `group`."""
+    import torch.distributed as dist
+    return r if group is None else dist.get_global_rank(group, r)
+
+
 def gather_stream(local_bytes, local_len: int, plan: StreamPlan, root: int = 0, group=None):
     """Variable-length gather of the shards into one buffer on `root` (uint8 tensor) incl. header/trailer."""
     import torch
@@ -95,7 +103,7 @@ def gather_stream(local_bytes, local_len: int, plan: StreamPlan, root: int = 0, 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if rank != root:
         if local_len:
-            dist.send(local_bytes[:local_len], dst=root, group=group)
+            dist.send(local_bytes[:local_len], dst=_global(group, root), group=group)
         return None
     out = torch.empty(plan.total, dtype=torch.uint8, device=local_bytes.device)
     if plan.header:
@@ -108,7 +116,7 @@ def gather_stream(local_bytes, local_len: int, plan: StreamPlan, root: int = 0, 
         if r == root:
             out[a:b] = local_bytes[:b - a]
         elif b > a:
-            dist.recv(out[a:b], src=r, group=group)
+            dist.recv(out[a:b], src=_global(group, r), group=group)
     return out
 
 
@@ -143,6 +151,100 @@ def deflate_sharded(lib, data, halo, level: int = 6, wrap: int = zb.WRAP_ZLIB, g
     plan = plan_stream(metas, level, wrap, lib.crc32_combine)
     assembled = gather_stream(out, clen, plan, root, group) if assemble else None
     return plan, out, clen, assembled
+
+
+# ---------------------------------------------------------------------------------------------
+# One stream from all ranks with the gather hidden behind the compression (bench.py --gpus N)
+# ---------------------------------------------------------------------------------------------
+def piece_ranges(total: int, world: int, pieces_per_rank: int, chunk: int = CHUNK) -> List[List[Tuple[int, int]]]:
+    """The input cut into world * pieces_per_rank pieces dealt round robin: global piece g = j * world + r is round j of
+    rank r.  Returns, per rank, its [begin, end) list in round order.  Pieces are chunk aligned (the last may be short)."""
+    npieces = world * pieces_per_rank
+    nchunks = (total + chunk - 1) // chunk
+    per = (nchunks + npieces - 1) // npieces * chunk
+    out: List[List[Tuple[int, int]]] = [[] for _ in range(world)]
+    for g in range(npieces):
+        out[g % world].append((min(total, g * per), min(total, (g + 1) * per)))
+    return out
+
+
+def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=None, root: int = 0, outs=None,
+                   final=None, host_final: Optional[int] = None, stream=None, copy_stream=None, last_round_is_last: bool = True):
+    """ONE stream from all ranks, assembled on `root` while the compression is still running.
+
+    pieces[j] = (src_ptr, n, dict_ptr, dict_len) for round j: this rank's j-th piece (device or pinned host memory) and
+    the <= 32 KiB in front of it.  The stream is the pieces in GLOBAL order g = j * world + r, so after round j
+    every rank knows (one all-gather of {len, n, crc32, adler32}) where its round-j output lands in the final stream,
+    and the transfer of round j -- NCCL send/recv into `final` on the root (device mode), or a D2H copy straight into
+    the shared, page-locked host buffer at `host_final` (host mode) -- runs while round j + 1 is compressed.  Only the
+    last round's transfer is exposed.  The root adds the header and the trailer with the combined checksum.
+    outs[j]: this rank's device output buffer of round j.  Returns (total stream length, crc32, adler32, n_in).
+    """
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lvl = 6 if level < 0 else level
+    header = zlib_header(lvl) if wrap == zb.WRAP_ZLIB else (
+        bytes([31, 139, 8, 0, 0, 0, 0, 0, 2 if lvl == 9 else 4 if lvl < 2 else 0, 3]) if wrap == zb.WRAP_GZIP else b"")
+    rounds = len(pieces)
+    pos, crc_all, adl_all, n_all = len(header), 0, 1, 0
+    works = []
+    dev = outs[0].device
+    for j, (src_ptr, n, dict_ptr, dict_len) in enumerate(pieces):
+        last = last_round_is_last and j == rounds - 1 and rank == world - 1
+        flags = zb.ZB200_DEFLATE_NO_HEADER | zb.ZB200_DEFLATE_NO_TRAILER | (0 if last else zb.ZB200_DEFLATE_NOT_LAST)
+        clen, crc, adl = lib.deflate_shard(src_ptr, n, dict_ptr if dict_len else None, dict_len, outs[j].data_ptr(),
+                                           outs[j].numel(), level, zb.WRAP_RAW, flags, stream)
+        metas = exchange_meta((clen, n, crc, adl), dev, group)
+        offs = []
+        for cl, m, c, a in metas:                                  # global order within a round = rank order
+            offs.append(pos)
+            pos += cl
+            if m:
+                crc_all = lib.crc32_combine(crc_all, c, m)
+                adl_all = adler_join(adl_all, a, m)
+            n_all += m
+        if host_final is not None:                                 # every rank writes its own part of the shared host buffer
+            if clen:
+                lib._check(lib.dll.zb200_copy_async(host_final + offs[rank], outs[j].data_ptr(), clen, zb._stream(copy_stream)),
+                           "zb200_copy_async")
+        elif final is not None or rank != root:
+            ops = []
+            if rank == root:
+                for r in range(world):
+                    cl = metas[r][0]
+                    if not cl:
+                        continue
+                    if r == root:
+                        final[offs[r]:offs[r] + cl].copy_(outs[j][:cl], non_blocking=True)
+                    else:
+                        ops.append(dist.P2POp(dist.irecv, final[offs[r]:offs[r] + cl], _global(group, r), group))
+            elif clen:
+                ops.append(dist.P2POp(dist.isend, outs[j][:clen], _global(group, root), group))
+            if ops:
+                works += dist.batch_isend_irecv(ops)
+    if wrap == zb.WRAP_ZLIB:
+        trailer = adl_all.to_bytes(4, "big")
+    elif wrap == zb.WRAP_GZIP:
+        trailer = crc_all.to_bytes(4, "little") + (n_all & 0xFFFFFFFF).to_bytes(4, "little")
+    else:
+        trailer = b""
+    total = pos + len(trailer)
+    for w in works:
+        w.wait()
+    if rank == root:
+        if host_final is not None:
+            import ctypes as C
+            C.memmove(host_final, header, len(header))
+            C.memmove(host_final + pos, trailer, len(trailer))
+        elif final is not None:
+            if header:
+                final[:len(header)] = torch.tensor(list(header), dtype=torch.uint8, device=dev)
+            if trailer:
+                final[pos:total] = torch.tensor(list(trailer), dtype=torch.uint8, device=dev)
+    if host_final is not None:
+        lib._check(lib.dll.zb200_sync(zb._stream(copy_stream)), "zb200_sync")
+    return total, crc_all, adl_all, n_all
 
 
 # ---------------------------------------------------------------------------------------------
@@ -218,6 +320,34 @@ def inflate_sharded(lib, streams: Sequence[bytes], caps: Sequence[int], wrap: in
     return mine, outs, [int(r[0]) for r in res], [int(r[1]) for r in res]
 
 
+def inflate_sharded_dev(lib, d_src, src_off, d_dst, dst_off, wrap: int = zb.WRAP_ZLIB, group=None, stream=None):
+    """Device-resident form of inflate_sharded for the timed runs: every rank holds the stream set (d_src with host
+    offsets src_off[n + 1]) and the output arena; rank r decodes its contiguous, size-balanced range into its own part of
+    d_dst.  Exchange: one all-reduce(MAX) that fills in {status, length} of every stream on every rank.
+    Returns (first, last) stream index of this rank and the [n, 2] tensor of {status, length}."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n = len(src_off) - 1
+    sizes = [int(src_off[i + 1] - src_off[i]) for i in range(n)]
+    parts = balance_streams(sizes, world)
+    mine = parts[rank]
+    dev = d_src.device
+    res = torch.full((n, 2), -100, dtype=torch.int64, device=dev)
+    a, b = (mine[0], mine[-1] + 1) if mine else (0, 0)
+    if b > a:
+        d_so = torch.as_tensor(src_off[a:b + 1], dtype=torch.int64).to(dev)
+        d_do = torch.as_tensor(dst_off[a:b + 1], dtype=torch.int64).to(dev)
+        d_len = torch.zeros(b - a, dtype=torch.int64, device=dev)
+        d_st = torch.zeros(b - a, dtype=torch.int32, device=dev)
+        lib.inflate_batch_dev(d_src.data_ptr(), d_so.data_ptr(), b - a, d_dst.data_ptr(), d_do.data_ptr(), d_len.data_ptr(),
+                              d_st.data_ptr(), wrap, stream)
+        res[a:b, 0] = d_st.to(torch.int64)
+        res[a:b, 1] = d_len
+    dist.all_reduce(res, op=dist.ReduceOp.MAX, group=group)
+    return (a, b), res
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE config 5: one ZIP archive whose members are compressed on all ranks (SURVEY.md 8(e), 8(f) rank 1)
 # ---------------------------------------------------------------------------------------------
@@ -266,7 +396,7 @@ def zip_sharded(lib, names: Sequence[str], datas: Sequence[bytes], level: int = 
     seg_t = torch.frombuffer(bytearray(seg), dtype=torch.uint8).to(dev) if seg else torch.empty(0, dtype=torch.uint8, device=dev)
     if rank != root:
         if len(seg):
-            dist.send(seg_t, dst=root, group=group)
+            dist.send(seg_t, dst=_global(group, root), group=group)
         return None
     parts, base, order, glob = [], 0, [], []
     for r in range(world):
@@ -274,7 +404,7 @@ def zip_sharded(lib, names: Sequence[str], datas: Sequence[bytes], level: int = 
             parts.append(seg)
         elif seg_len[r]:
             buf = torch.empty(seg_len[r], dtype=torch.uint8, device=dev)
-            dist.recv(buf, src=r, group=group)
+            dist.recv(buf, src=_global(group, r), group=group)
             parts.append(bytes(buf.cpu().numpy()))
         else:
             parts.append(b"")

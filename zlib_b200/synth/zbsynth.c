@@ -1,5 +1,7 @@
-/* zb_synth.c -- synthetic corpora for benchmarks and tests.
+/* zbsynth.c -- synthetic corpora for benchmarks and tests.
  *
+ * Built into its own tiny library (zlib_b200/libzbsynth.so), NOT into libzb200.so: the reference arm of bench.py
+ * generates its input with it and must not map the product library.
  * Workload generator only; no codec arithmetic.  Every 64 KiB page is generated from
  * its own xorshift64* state derived from (seed, page index), so the output is
  * deterministic, position-addressable and can be produced by several host threads.
@@ -10,7 +12,8 @@
  *              {u32 counter, u32 small(0..255), u32 0, u32 random}
  *   kind 2     raw generator output (incompressible)
  */
-#include "../../include/zb200.h"
+#include <stddef.h>
+#include <stdint.h>
 #include <pthread.h>
 #include <string.h>
 #include <unistd.h>
@@ -78,14 +81,15 @@ static void noise_page(uint8_t *dst, size_t n, uint64_t s)
     }
 }
 
-typedef struct { uint8_t *dst; size_t len; int kind; uint64_t seed; const vocab_t *v; int tid, nthreads; } job_t;
+typedef struct { uint8_t *dst; size_t len; int kind; uint64_t seed; const vocab_t *v; int tid, nthreads; uint64_t page0; } job_t;
 
 static void *worker(void *arg)
 {
     job_t *j = (job_t *)arg;
     size_t pages = (j->len + PAGE - 1) / PAGE;
-    for (size_t p = (size_t)j->tid; p < pages; p += (size_t)j->nthreads) {
-        size_t off = p * PAGE, n = j->len - off < PAGE ? j->len - off : PAGE;
+    for (size_t q = (size_t)j->tid; q < pages; q += (size_t)j->nthreads) {
+        size_t off = q * PAGE, n = j->len - off < PAGE ? j->len - off : PAGE;
+        uint64_t p = j->page0 + q;                               /* page index within the whole corpus */
         uint64_t s = 0x9E3779B97F4A7C15ULL ^ (j->seed * 0xBF58476D1CE4E5B9ULL) ^ ((p + 1) * 0x94D049BB133111EBULL);
         if (s == 0) s = 1;
         xs64(&s); xs64(&s);
@@ -96,8 +100,10 @@ static void *worker(void *arg)
     return NULL;
 }
 
-ZAPI void zb200_synth(void *host_dst, size_t len, int kind, uint64_t seed)
+/* Bytes [offset, offset + len) of the corpus (kind, seed); offset must be a multiple of 64 KiB (the page size). */
+ZAPI int zbsynth_fill(void *host_dst, size_t len, int kind, uint64_t seed, uint64_t offset)
 {
+    if (offset % PAGE) return -1;
     vocab_t local;
     make_vocab(&local, seed);
     long nc = sysconf(_SC_NPROCESSORS_ONLN);
@@ -106,9 +112,10 @@ ZAPI void zb200_synth(void *host_dst, size_t len, int kind, uint64_t seed)
     pthread_t th[32];
     job_t jobs[32];
     for (int t = 0; t < nt; t++) {
-        jobs[t] = (job_t){(uint8_t *)host_dst, len, kind, seed, &local, t, nt};
+        jobs[t] = (job_t){(uint8_t *)host_dst, len, kind, seed, &local, t, nt, offset / PAGE};
         if (t > 0) pthread_create(&th[t], NULL, worker, &jobs[t]);
     }
     worker(&jobs[0]);
     for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
+    return 0;
 }
