@@ -141,6 +141,24 @@ int zb200_inflate_batch_dev(const void *d_src, const uint64_t *d_src_off, size_t
                             void *d_dst, const uint64_t *d_dst_off, uint64_t *d_dst_len,
                             int32_t *d_status, int wrap, void *stream);
 
+/* ---- all GPUs of the box behind one call: one host thread per device inside the library ----
+ * Host buffers, like zlib.h's own calls (pinned memory moves fastest).  ndev <= 0 means every visible device.
+ * zb200_multi_deflate: the input is cut into chunk-aligned pieces dealt round robin over the devices; every piece is
+ *   compressed with the 32 KiB in front of it as dictionary and ends on a byte boundary; one NCCL all-gather per round of
+ *   {compressed bytes, input bytes, crc32, adler32} places every piece in the stream, the bytes go D2H straight there.
+ *   Result: ONE valid raw / zlib / gzip stream in dst (what compress2 returns for the whole buffer, qcsrc/compress.c:22).
+ * zb200_multi_checksum: a slice per device, all-gather of {crc32, adler32, len}, crc32_combine / adler32_combine fold
+ *   (qcsrc/crc32.c:370, qcsrc/adler32.c:128) in slice order.
+ * zb200_multi_inflate_batch: zb200_inflate_batch with the streams dealt to the devices in contiguous ranges of nearly
+ *   equal compressed size; no exchange.
+ * NCCL (libnccl.so.2) is loaded at run time by the first of these calls. */
+int zb200_multi_devices(void);
+int zb200_multi_deflate(const void *src, size_t src_len, void *dst, size_t *dst_len, int level, int wrap, int ndev,
+                        uint32_t *crc, uint32_t *adler);
+int zb200_multi_checksum(const void *buf, size_t len, int ndev, uint32_t *crc, uint32_t *adler);
+int zb200_multi_inflate_batch(const void *src, const uint64_t *src_off, size_t n, void *dst, const uint64_t *dst_off,
+                              uint64_t *dst_len, int32_t *status, int wrap, int ndev);
+
 /* ---- instrumentation -------------------------------------------------- */
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t zb200_kernel_launches(void);
