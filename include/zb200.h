@@ -89,6 +89,13 @@ int zb200_deflate_shard(const void *src, size_t src_len, const void *dict, size_
                         void *dst, size_t *dst_len, int level, int wrap, int flags,
                         uint32_t *crc, uint32_t *adler, void *stream);
 
+/* The same call in two halves: _begin enqueues everything and returns (for pinned host or device buffers without
+ * blocking), _end waits and reports.  A caller with several pieces begins piece j + 1 before it ends piece j, so the
+ * GPU is never idle while the host reads a length (the multi-GPU rounds do this).  Every _begin needs its _end. */
+int zb200_deflate_shard_begin(void **job, const void *src, size_t src_len, const void *dict, size_t dict_len,
+                              void *dst, size_t dst_cap, int level, int wrap, int flags, void *stream);
+int zb200_deflate_shard_end(void *job, size_t *dst_len, uint32_t *crc, uint32_t *adler);
+
 /* n independent inputs -> n independent streams (minizip-style per-file streams).
  * src/dst are single arenas; src_off and dst_off have n+1 entries (dst_off gives
  * each stream's slot, which must hold compressBound of its input). */

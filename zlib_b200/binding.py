@@ -122,6 +122,8 @@ class Lib:
             "zb200_checksum_batch": (C.c_int, [vp, vp, sz, vp, vp, vp]),
             "zb200_deflate": (C.c_int, [vp, sz, vp, C.POINTER(sz), C.c_int, C.c_int, vp]),
             "zb200_deflate_shard": (C.c_int, [vp, sz, vp, sz, vp, C.POINTER(sz), C.c_int, C.c_int, C.c_int, u32p, u32p, vp]),
+            "zb200_deflate_shard_begin": (C.c_int, [C.POINTER(vp), vp, sz, vp, sz, vp, sz, C.c_int, C.c_int, C.c_int, vp]),
+            "zb200_deflate_shard_end": (C.c_int, [vp, C.POINTER(sz), u32p, u32p]),
             "zb200_deflate_batch": (C.c_int, [vp, vp, sz, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
             "zb200_zip_bound": (sz, [vp, vp, sz]),
             "zb200_zip_build": (C.c_int, [vp, vp, vp, sz, C.c_int, C.c_uint32, vp, C.POINTER(sz)]),
@@ -221,6 +223,23 @@ class Lib:
         crc, adl = C.c_uint32(0), C.c_uint32(0)
         self._check(self.dll.zb200_deflate_shard(ps, src_len, pk, dict_len, pd, C.byref(ol), level, wrap, flags,
                                                  C.byref(crc), C.byref(adl), _stream(stream)), "zb200_deflate_shard")
+        return ol.value, crc.value, adl.value
+
+    def deflate_shard_begin(self, src: Buf, src_len: int, dict_: Buf, dict_len: int, dst: Buf, dst_cap: int, level: int,
+                            wrap: int, flags: int, stream=None):
+        """First half of deflate_shard: everything enqueued; returns the job handle for deflate_shard_end."""
+        ps, k1 = _ptr(src)
+        pk, k3 = _ptr(dict_)
+        pd, k2 = _ptr(dst)
+        job = C.c_void_p(0)
+        self._check(self.dll.zb200_deflate_shard_begin(C.byref(job), ps, src_len, pk, dict_len, pd, dst_cap, level, wrap, flags,
+                                                       _stream(stream)), "zb200_deflate_shard_begin")
+        return job
+
+    def deflate_shard_end(self, job) -> Tuple[int, int, int]:
+        ol = C.c_size_t(0)
+        crc, adl = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.dll.zb200_deflate_shard_end(job, C.byref(ol), C.byref(crc), C.byref(adl)), "zb200_deflate_shard_end")
         return ol.value, crc.value, adl.value
 
     def checksum_batch(self, bufs, stream=None):

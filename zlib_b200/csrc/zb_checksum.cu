@@ -28,6 +28,7 @@
 //
 // Roofline: HBM.  Algorithmic bytes = len (read once), 8 bytes written.
 #include "zb_deflate.cuh"
+#include <stdlib.h>
 
 namespace zb {
 
@@ -47,6 +48,7 @@ struct Partial {
 };
 
 __device__ uint32_t g_tab_stride[4][256];  // v<<(8t) times x^(8*512)
+__device__ __align__(128) uint32_t g_tab_image[32768];   // the same four tables in the bank-replicated shared-memory layout of k_checksum_main (128 KiB)
 __device__ uint32_t g_tab_byte[256];       // the classic byte table (crc32.h table 0)
 __device__ uint32_t g_lane_mul[128];       // x^(8*(512 - 16*lane - 4*k))
 __constant__ uint32_t c_pow8[64];          // x^(8*2^k) mod P
@@ -105,6 +107,11 @@ int checksum_setup()
     uint32_t p = 0x00800000u;
     for (int k = 0; k < 64; k++) { pw[k] = p; p = gf2_mul(p, p); }
     ZB_CUDA(cudaMemcpyToSymbol(g_tab_stride, tabs, sizeof(tabs)));
+    {   // word i of the image: table t = 2 * (i >> 14) + ((i >> 5) & 1), entry v = (i >> 6) & 255, replicated over the 32 banks
+        static uint32_t image[32768];
+        for (uint32_t i = 0; i < 32768; i++) image[i] = tabs[((i >> 14) << 1) | ((i >> 5) & 1u)][(i >> 6) & 255u];
+        ZB_CUDA(cudaMemcpyToSymbol(g_tab_image, image, sizeof(image)));
+    }
     ZB_CUDA(cudaMemcpyToSymbol(g_tab_byte, tab0, sizeof(tab0)));
     ZB_CUDA(cudaMemcpyToSymbol(g_lane_mul, lane_mul, sizeof(lane_mul)));
     ZB_CUDA(cudaMemcpyToSymbol(c_pow8, pw, sizeof(pw)));
@@ -117,14 +124,38 @@ int checksum_setup()
 // from a 64 KiB-aligned shared address, so bank = l (a warp's 32 lookups never conflict) and the address of a lookup
 // is ONE byte permute: byte 1 of the address is the index byte of the register, bytes 0, 2, 3 come from a per-lane
 // constant (PRMT), instead of extract + scale + add.  The kernel is instruction bound, so this is what moves it.
+// The image itself arrives by TMA: one thread issues two 64 KiB bulk copies (cp.async.bulk, SASS UBLKCP) from the
+// ready-made image in global memory and everybody waits on the mbarrier -- 32 scattered stores per thread before.
+// kTma: the DATA also comes through shared memory -- every warp keeps a private ring of kTmaSlots x 512 bytes that its
+// lane 0 refills with bulk copies (one mbarrier per slot), so the loads leave the instruction stream and registers no
+// longer cap the bytes in flight.  The ring lives in the shared memory the 64 KiB alignment of the image leaves unused.
+// The combine tree runs in the same launch: the last CTA to publish its record folds all of them (see fold_records).
 constexpr uint32_t kPrefetchAhead = 16;                          // iterations (512 B each) between an L2 prefetch and its use
 constexpr uint32_t kTabImage = 2 * 65536;                       // bytes of the table image
-constexpr size_t kMainSmem = kTabImage + 65536;                 // + slack to align the image to 64 KiB
+constexpr int kTmaSlots = 5;                                    // 512-byte pieces in flight per warp (kTma)
+constexpr uint32_t kRingLow = 3, kRingHigh = kTmaSlots - kRingLow;   // slots below / above the image (16 KiB per slot and CTA)
+constexpr size_t kMainSmem = 65536 + kTabImage + kRingHigh * 16384;   // 64 KiB of alignment room (hosting the low slots) + image + high slots
+
+struct FoldArgs {                                               // per-launch constants of the combine, computed on the host
+    uint32_t pw_stride[10];                                     // x^(8 * S * 2^k), S = bytes one CTA covers
+    uint32_t pw_last;                                           // x^(8 * D): from the end of the last full CTA to the end of the last CTA
+    uint32_t pw_tail;                                           // x^(8 * (len - aligned end)): over the ragged tail
+    uint32_t pw_head;                                           // x^(8 * (len - head)): from the end of the head bytes to the end
+    uint32_t pw_len;                                            // x^(8 * len): for the 0xffffffff pre-conditioning
+    uint64_t cta_bytes;                                         // S
+};
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t saddr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
     return v;
 }
 
@@ -142,57 +173,200 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p)
     return v;
 }
 
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// One 512-byte iteration of a warp: four Horner steps per lane and the three Adler accumulators.
+#define ZB_CK_STEP(W, J)                                                                                              \
+    do {                                                                                                              \
+        c0 = stride_step(c0, k0, k1, k2, k3) ^ (W).x; c1 = stride_step(c1, k0, k1, k2, k3) ^ (W).y;                    \
+        c2 = stride_step(c2, k0, k1, k2, k3) ^ (W).z; c3 = stride_step(c3, k0, k1, k2, k3) ^ (W).w;                    \
+        const uint32_t sum_ = __dp4a((W).x, 0x01010101u, __dp4a((W).y, 0x01010101u, __dp4a((W).z, 0x01010101u, __dp4a((W).w, 0x01010101u, 0u)))); \
+        s_b = __dp4a((W).x, 0x0d0e0f10u, __dp4a((W).y, 0x090a0b0cu, __dp4a((W).z, 0x05060708u, __dp4a((W).w, 0x01020304u, s_b)))); \
+        s_a += sum_; s_j += (J) * sum_;                                                                               \
+    } while (0)
+
+// The combine tree, run by the last CTA (1024 threads): record i of the grid covers bytes up to
+//   end_i = base + (i + 1) * S   (i < n - 1),      end_{n-1} = base + aligned length,
+// so with q counted from the back over the first n - 1 records the register at the aligned end is
+//   ( sum_q u_q X^q ) * x^(8 D)  xor  u_last,      X = x^(8 S),
+// a polynomial in X evaluated by pairing neighbours: ten levels of ONE modular multiply per thread with the host's
+// X^(2^k), instead of one modular power per record.  Head and tail bytes, the pre-conditioning and the Adler sums
+// (closed form per record) are folded in the same pass.
+__device__ void fold_records(const Partial* __restrict__ parts, uint32_t n_parts, const uint8_t* __restrict__ buf, uint64_t len,
+                             uint64_t head, uint64_t tail_begin, const FoldArgs& fa, uint32_t* __restrict__ out2, uint32_t* s_x)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t m = n_parts - 1;                             // records with the uniform spacing
+    // ---- CRC: u_q = record m - 1 - q ----
+    uint32_t u = 0, a = 0, b = 0;
+    // (the records were published with a fence before the counter moved; volatile loads keep them out of registers cached earlier)
+    for (uint32_t i = tid; i < n_parts; i += blockDim.x) {
+        const volatile Partial* vp = parts + i;
+        const uint32_t pa = vp->a, pb = vp->b;
+        const uint64_t end = vp->end;
+        if (end == 0) continue;
+        const uint64_t suffix = len - end;
+        a += pa;
+        b = (b + pb + (uint32_t)((suffix % kAdlerBase) * pa % kAdlerBase)) % kAdlerBase;
+        a %= kAdlerBase;
+    }
+    if ((uint32_t)tid < m) u = ((const volatile Partial*)(parts + (m - 1 - tid)))->reg;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {                               // levels inside a warp: lane q takes lane q + 2^k
+        const uint32_t hi = __shfl_down_sync(0xffffffffu, u, 1u << k);
+        if ((lane & ((2 << k) - 1)) == 0) u ^= gf2_mul(hi, fa.pw_stride[k]);
+    }
+    if (lane == 0) s_x[warp] = u;
+    __syncthreads();
+    uint32_t reg = 0;
+    if (warp == 0) {
+        uint32_t v = s_x[lane];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const uint32_t hi = __shfl_down_sync(0xffffffffu, v, 1u << k);
+            if ((lane & ((2 << k) - 1)) == 0) v ^= gf2_mul(hi, fa.pw_stride[5 + k]);
+        }
+        if (lane == 0) {
+            const volatile Partial* last = parts + m;
+            uint32_t r = (m ? gf2_mul(v, fa.pw_last) : 0u) ^ last->reg;      // at the aligned end
+            r = gf2_mul(r, fa.pw_tail);                                       // at the end of the buffer
+            // head bytes (< 16): byte-wise, then moved to the end; tail bytes (< 512): byte-wise from the register so far
+            uint32_t hreg = 0;
+            for (uint64_t o = 0; o < head; o++) hreg = g_tab_byte[(hreg ^ buf[o]) & 0xffu] ^ (hreg >> 8);
+            if (head) r ^= gf2_mul(hreg, fa.pw_head);
+            uint32_t treg = 0;
+            for (uint64_t o = tail_begin; o < len; o++) treg = g_tab_byte[(treg ^ buf[o]) & 0xffu] ^ (treg >> 8);
+            r ^= treg;
+            r ^= gf2_mul(0xffffffffu, fa.pw_len);                              // 0xffffffff pre-conditioning
+            reg = r;
+        }
+    }
+    // ---- Adler: ragged edges, then the sums ----
+    const uint64_t n_edge = head + (len - tail_begin);
+    for (uint64_t e = tid; e < n_edge; e += blockDim.x) {
+        const uint64_t o = e < head ? e : tail_begin + (e - head);
+        const uint32_t v = buf[o];
+        a = (a + v) % kAdlerBase;
+        b = (b + (uint32_t)(((len - o) % kAdlerBase) * v % kAdlerBase)) % kAdlerBase;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    __syncthreads();                                            // s_x is reused
+    if (lane == 0) { s_x[warp] = a % kAdlerBase; s_x[32 + warp] = b % kAdlerBase; }
+    __syncthreads();
+    if (warp == 0) {
+        a = s_x[lane]; b = s_x[32 + lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if (lane == 0) {
+            const uint32_t s1 = (1u + a) % kAdlerBase;
+            const uint32_t s2 = (uint32_t)((len % kAdlerBase + b) % kAdlerBase);
+            out2[0] = ~reg;
+            out2[1] = (s2 << 16) | s1;
+        }
+    }
+}
+
+template <bool kTma>
 __global__ void __launch_bounds__(kMainThreads, 1)
 k_checksum_main(const uint8_t* __restrict__ base, uint64_t n_units, uint32_t iters_per_warp,
-                uint64_t base_off, Partial* __restrict__ parts)
+                uint64_t base_off, Partial* __restrict__ parts, const uint8_t* __restrict__ buf, uint64_t len,
+                uint64_t tail_begin, const FoldArgs fa, uint32_t* __restrict__ out2, unsigned int* __restrict__ done_ctas)
 {
-    extern __shared__ __align__(16) uint8_t s_raw[];
+    extern __shared__ __align__(128) uint8_t s_raw[];
     __shared__ Partial s_part[kMainWarps];
-    const uint32_t img = ((uint32_t)__cvta_generic_to_shared(s_raw) + 65535u) & ~65535u;   // shared address of the image
-    for (uint32_t i = threadIdx.x; i < kTabImage / 4; i += kMainThreads) {
-        const uint32_t t = ((i >> 14) << 1) | ((i >> 5) & 1u), v = (i >> 6) & 255u;
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(img + i * 4), "r"(g_tab_stride[t][v]) : "memory");
+    __shared__ __align__(8) uint64_t s_bar[1 + kMainWarps * kTmaSlots];   // [0] table image, then one per warp and slot
+    __shared__ uint32_t s_x[64];
+    __shared__ uint32_t s_last;
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t img = (raw + 65535u) & ~65535u;              // shared address of the image
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (kTma && img - raw < kRingLow * 16384u) __trap();       // the low ring slots live in the alignment room in front of the image
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        if (kTma) for (int i = 0; i < kMainWarps * kTmaSlots; i++) mbar_init(bar0 + 8 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar0, kTabImage);
+        bulk_g2s(img, g_tab_image, 65536, bar0);
+        bulk_g2s(img + 65536, reinterpret_cast<const uint8_t*>(g_tab_image) + 65536, 65536, bar0);
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint64_t warp = (uint64_t)blockIdx.x * kMainWarps + wid;
     const uint64_t u0 = warp * iters_per_warp;
     Partial mine{0, 0, 0, 0, 0};
-    if (u0 < n_units) {
-        const uint32_t iters = (uint32_t)min((uint64_t)iters_per_warp, n_units - u0);
-        const uint4* p = reinterpret_cast<const uint4*>(base + u0 * kStride) + lane;
-        const uint32_t k0 = img + lane * 4, k1 = k0 + 128, k2 = k0 + 65536, k3 = k2 + 128;
+    const uint32_t iters = u0 < n_units ? (uint32_t)min((uint64_t)iters_per_warp, n_units - u0) : 0u;
+    const uint8_t* seg = base + u0 * kStride;
+    // ring slot s of this warp: 512 bytes at (slot base) + wid * 512; slots 0..kRingLow-1 below the image, the rest above
+    auto slot_addr = [&](uint32_t sl) -> uint32_t {
+        return (sl < kRingLow ? img - (kRingLow - sl) * 16384u : img + kTabImage + (sl - kRingLow) * 16384u) + (uint32_t)wid * 512u;
+    };
+    const uint32_t wbar = bar0 + 8 + 8 * (uint32_t)(wid * kTmaSlots);
+    if (kTma && lane == 0) {
+        for (uint32_t j = 0; j < (uint32_t)kTmaSlots && j < iters; j++) {
+            mbar_expect_tx(wbar + 8 * j, kStride);
+            bulk_g2s(slot_addr(j), seg + (size_t)j * kStride, kStride, wbar + 8 * j);
+        }
+    }
+    mbar_wait(bar0, 0);                                         // the table image has landed
 
+    if (iters) {
+        const uint4* p = reinterpret_cast<const uint4*>(seg) + lane;
+        const uint32_t k0 = img + lane * 4, k1 = k0 + 128, k2 = k0 + 65536, k3 = k2 + 128;
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
         uint32_t s_a = 0, s_j = 0, s_b = 0;    // sum, iteration-weighted sum, in-piece weighted sum
-
-        uint32_t j = 0;
-        // two loads in flight per lane
-        for (; j + 2 <= iters; j += 2) {
-            // two iterations use 1 KiB per warp; ask L2 for the 1 KiB that is kPrefetchAhead iterations away (registers cap
-            // the loads in flight at two per lane, which alone does not cover the HBM latency-bandwidth product)
-            if (lane < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p - lane) + (size_t)min(j + kPrefetchAhead, iters - 2) * kStride + (lane * 128) % 1024));
-            uint4 w0 = ld_stream(p + (size_t)j * 32);
-            uint4 w1 = ld_stream(p + (size_t)(j + 1) * 32);
-            c0 = stride_step(c0, k0, k1, k2, k3) ^ w0.x; c1 = stride_step(c1, k0, k1, k2, k3) ^ w0.y;
-            c2 = stride_step(c2, k0, k1, k2, k3) ^ w0.z; c3 = stride_step(c3, k0, k1, k2, k3) ^ w0.w;
-            uint32_t sum0 = __dp4a(w0.x, 0x01010101u, __dp4a(w0.y, 0x01010101u, __dp4a(w0.z, 0x01010101u, __dp4a(w0.w, 0x01010101u, 0u))));
-            s_b = __dp4a(w0.x, 0x0d0e0f10u, __dp4a(w0.y, 0x090a0b0cu, __dp4a(w0.z, 0x05060708u, __dp4a(w0.w, 0x01020304u, s_b))));
-            s_a += sum0; s_j += j * sum0;
-            c0 = stride_step(c0, k0, k1, k2, k3) ^ w1.x; c1 = stride_step(c1, k0, k1, k2, k3) ^ w1.y;
-            c2 = stride_step(c2, k0, k1, k2, k3) ^ w1.z; c3 = stride_step(c3, k0, k1, k2, k3) ^ w1.w;
-            uint32_t sum1 = __dp4a(w1.x, 0x01010101u, __dp4a(w1.y, 0x01010101u, __dp4a(w1.z, 0x01010101u, __dp4a(w1.w, 0x01010101u, 0u))));
-            s_b = __dp4a(w1.x, 0x0d0e0f10u, __dp4a(w1.y, 0x090a0b0cu, __dp4a(w1.z, 0x05060708u, __dp4a(w1.w, 0x01020304u, s_b))));
-            s_a += sum1; s_j += (j + 1) * sum1;
-        }
-        for (; j < iters; ++j) {
-            uint4 w0 = ld_stream(p + (size_t)j * 32);
-            c0 = stride_step(c0, k0, k1, k2, k3) ^ w0.x; c1 = stride_step(c1, k0, k1, k2, k3) ^ w0.y;
-            c2 = stride_step(c2, k0, k1, k2, k3) ^ w0.z; c3 = stride_step(c3, k0, k1, k2, k3) ^ w0.w;
-            uint32_t sum0 = __dp4a(w0.x, 0x01010101u, __dp4a(w0.y, 0x01010101u, __dp4a(w0.z, 0x01010101u, __dp4a(w0.w, 0x01010101u, 0u))));
-            s_b = __dp4a(w0.x, 0x0d0e0f10u, __dp4a(w0.y, 0x090a0b0cu, __dp4a(w0.z, 0x05060708u, __dp4a(w0.w, 0x01020304u, s_b))));
-            s_a += sum0; s_j += j * sum0;
+        if (kTma) {
+            uint32_t sl = 0, par = 0;
+            for (uint32_t j = 0; j < iters; ++j) {
+                mbar_wait(wbar + 8 * sl, par);
+                const uint4 w0 = lds128(slot_addr(sl) + lane * 16);
+                __syncwarp();                                   // every lane has its 16 bytes: the slot can be refilled
+                if (lane == 0 && j + kTmaSlots < iters) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(wbar + 8 * sl, kStride);
+                    bulk_g2s(slot_addr(sl), seg + (size_t)(j + kTmaSlots) * kStride, kStride, wbar + 8 * sl);
+                }
+                ZB_CK_STEP(w0, j);
+                if (++sl == (uint32_t)kTmaSlots) { sl = 0; par ^= 1u; }
+            }
+        } else {
+            uint32_t j = 0;
+            // two loads in flight per lane
+            for (; j + 2 <= iters; j += 2) {
+                // two iterations use 1 KiB per warp; ask L2 for the 1 KiB that is kPrefetchAhead iterations away (registers cap
+                // the loads in flight at two per lane, which alone does not cover the HBM latency-bandwidth product)
+                if (lane < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p - lane) + (size_t)min(j + kPrefetchAhead, iters - 2) * kStride + (lane * 128) % 1024));
+                const uint4 w0 = ld_stream(p + (size_t)j * 32);
+                const uint4 w1 = ld_stream(p + (size_t)(j + 1) * 32);
+                ZB_CK_STEP(w0, j);
+                ZB_CK_STEP(w1, j + 1);
+            }
+            for (; j < iters; ++j) {
+                const uint4 w0 = ld_stream(p + (size_t)j * 32);
+                ZB_CK_STEP(w0, j);
+            }
         }
 
         // Move the four lane registers to the end of the segment and reduce across the warp.
@@ -211,7 +385,7 @@ k_checksum_main(const uint8_t* __restrict__ base, uint64_t n_units, uint32_t ite
         mine = Partial{reg, a % kAdlerBase, b % kAdlerBase, 0, base_off + (u0 + iters) * kStride};
     }
     // The CTA's warps cover consecutive segments: fold their partials to the end of the last one here (one modular
-    // power per warp, all CTAs at once), so the final kernel sees one record per CTA instead of one per warp.
+    // power per warp, all CTAs at once), so the combine sees one record per CTA instead of one per warp.
     if (lane == 0) s_part[wid] = mine;
     __syncthreads();
     if (wid == 0) {
@@ -232,7 +406,17 @@ k_checksum_main(const uint8_t* __restrict__ base, uint64_t n_units, uint32_t ite
             a += __shfl_xor_sync(0xffffffffu, a, o);
             b += __shfl_xor_sync(0xffffffffu, b, o);
         }
-        if (lane == 0) parts[blockIdx.x] = Partial{reg, a % kAdlerBase, b % kAdlerBase, 0, cta_end};
+        if (lane == 0) {
+            parts[blockIdx.x] = Partial{reg, a % kAdlerBase, b % kAdlerBase, 0, cta_end};
+            __threadfence();                                    // the record is visible before the count moves
+            s_last = atomicAdd(done_ctas, 1u) == gridDim.x - 1 ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    if (s_last) {                                               // every record of the grid is published: fold them
+        __threadfence();
+        fold_records(parts, gridDim.x, buf, len, base_off, tail_begin, fa, out2, s_x);
+        if (threadIdx.x == 0) *done_ctas = 0;                   // ready for the next launch with this context (a context serves one stream at a time)
     }
 }
 
@@ -442,7 +626,8 @@ int checksum_jobs_launch(Ctx* c, const uint8_t* d_base, const ChunkDesc* d_cd, u
 
 int checksum_attr_setup()                                      // once per device, from ensure_init
 {
-    ZB_CUDA(cudaFuncSetAttribute(k_checksum_main, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMainSmem));
+    ZB_CUDA(cudaFuncSetAttribute(k_checksum_main<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMainSmem));
+    ZB_CUDA(cudaFuncSetAttribute(k_checksum_main<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMainSmem));
     return 0;
 }
 
@@ -479,9 +664,29 @@ int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, 
     uint64_t n_parts = blocks;                                  // one record per CTA
     int rc = c->ws[0].ensure(n_parts * sizeof(Partial));
     if (rc) return rc;
-    ZB_LAUNCH(k_checksum_main, blocks, kMainThreads, kMainSmem, s, d_buf + head, n_units, iters, head, c->ws[0].as<Partial>());
-    ZB_LAUNCH(k_checksum_final, 1, 1024, 0, s, c->ws[0].as<Partial>(), (uint32_t)n_parts, d_buf, (uint64_t)len, head,
-              tail_begin, d_out2);
+    if (blocks > 1025) {                                        // beyond the in-kernel combine (2.5 TB): not reachable with 64-bit lengths in 180 GB
+        set_error("checksum: %u CTAs exceed the combine tree", blocks);
+        return ZB_STREAM_ERROR;
+    }
+    if ((rc = c->ensure_flags()) != 0) return rc;
+    unsigned int* done = c->flags.as<unsigned int>();            // zero between launches (the last CTA resets it)
+    // constants of the combine (fold_records): powers of x for the uniform spacing of the CTA records and for the edges
+    FoldArgs fa;
+    const uint64_t S = (uint64_t)kMainWarps * iters * kStride;
+    fa.cta_bytes = S;
+    for (int k = 0; k < 10; k++) fa.pw_stride[k] = host_pow8(S << k);
+    const uint64_t aligned = n_units * kStride;
+    fa.pw_last = host_pow8(aligned - (uint64_t)(blocks - 1) * S);
+    fa.pw_tail = host_pow8(len - tail_begin);
+    fa.pw_head = host_pow8(len - head);
+    fa.pw_len = host_pow8(len);
+    static const bool tma = getenv("ZB200_CKSUM_TMA") ? atoi(getenv("ZB200_CKSUM_TMA")) != 0 : false;
+    if (tma)
+        ZB_LAUNCH(k_checksum_main<true>, blocks, kMainThreads, kMainSmem, s, d_buf + head, n_units, iters, head, c->ws[0].as<Partial>(),
+                  d_buf, (uint64_t)len, tail_begin, fa, d_out2, done);
+    else
+        ZB_LAUNCH(k_checksum_main<false>, blocks, kMainThreads, kMainSmem, s, d_buf + head, n_units, iters, head, c->ws[0].as<Partial>(),
+                  d_buf, (uint64_t)len, tail_begin, fa, d_out2, done);
     ZB_CHECK_LAUNCH();
     return 0;
 }

@@ -41,6 +41,8 @@ struct Ctx {
     cudaEvent_t  idle = nullptr;           // recorded when the context is released
     DevBuf in, out, ws[12];
     DevBuf small;                          // few-KB result words
+    DevBuf flags;                          // 256 bytes, zero whenever no kernel of this context is running (self-resetting counters)
+    int ensure_flags();
     void* pinned = nullptr; size_t pinned_cap = 0;
     int ensure_pinned(size_t bytes);
     cudaStream_t aux[2] = {nullptr, nullptr};   // copy-in / copy-out streams of the slab pipeline

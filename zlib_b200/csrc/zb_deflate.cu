@@ -1491,12 +1491,40 @@ static int deflate_params(DeflateParams& P, int level, int wrap, int flags)
 
 using namespace zb;
 
-ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict, size_t dict_len, void* dst,
-                               size_t* dst_len, int level, int wrap, int flags, uint32_t* crc, uint32_t* adler, void* stream)
+// One shard in two halves.  begin: everything is enqueued (copies in, slab kernels on two streams, checksums, header and
+// trailer, the result words on their way to pinned memory); end: wait, copy out what is still on the device, report.
+// zb200_deflate_shard is begin + end; a caller with several pieces (the multi-GPU rounds) begins piece j + 1 before it
+// ends piece j, so the GPU never waits for the host to read a length.
+struct ShardJob {
+    Ctx* c = nullptr; Ctx* c2 = nullptr;
+    cudaStream_t s = nullptr, s_out = nullptr;
+    HostStager stager;                                          // pageable sources of 64 MiB and more
+    HostDrainer drainer;                                        // and pageable destinations
+    std::vector<uint64_t> cut;
+    uint64_t nslabs = 0, hdr_len = 0, n = 0;
+    size_t cap = 0;
+    void* dst = nullptr; uint8_t* d_out = nullptr;
+    bool dst_on_host = false;
+    cudaEvent_t* ev_done = nullptr;
+    uint64_t* h_res = nullptr; uint64_t* h_pos = nullptr;
+    int rc = 0;
+};
+
+static void shard_release(ShardJob* J)
+{
+    J->stager.finish();
+    J->drainer.finish();
+    if (J->c2) ctx_release(J->c2, J->c2->own_stream);
+    if (J->c) ctx_release(J->c, J->s);
+    J->c = J->c2 = nullptr;
+}
+
+static int shard_begin(ShardJob* J, const void* src, size_t src_len, const void* dict, size_t dict_len, void* dst, size_t cap,
+                       int level, int wrap, int flags, void* stream)
 {
     int rc = ensure_init();
     if (rc) return rc;
-    if (!dst_len || level < -1 || level > 9 || wrap < 0 || wrap > 2 || (src_len && !src) || dict_len > kWindow) {
+    if (level < -1 || level > 9 || wrap < 0 || wrap > 2 || (src_len && !src) || dict_len > kWindow || !dst) {
         set_error("zb200_deflate: bad argument");
         return ZB_STREAM_ERROR;
     }
@@ -1507,7 +1535,7 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
     const int last_is_final = (flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
     const uint64_t hdr_len = (flags & ZB200_DEFLATE_NO_HEADER) ? 0 : wrap == ZB200_WRAP_ZLIB ? 2 : wrap == ZB200_WRAP_GZIP ? 10 : 0;
     const uint64_t n = src_len;
-    std::vector<uint64_t> cut;
+    std::vector<uint64_t>& cut = J->cut;
     plan_slabs(n, (n != 0 && classify(src) != kDevice) || classify(dst) != kDevice, cut);
     const uint64_t nslabs = cut.size() - 1;
 
@@ -1515,24 +1543,27 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
     if (!c) return ZB_MEM_ERROR;
     Ctx* c2 = nullptr;
     cudaStream_t s = pick_stream(c, stream);
-    const size_t cap = *dst_len;
-    HostStager stager;                                          // pageable sources of 64 MiB and more (joined before the contexts go back)
-    HostDrainer drainer;                                        // and pageable destinations
+    J->c = c; J->s = s; J->cap = cap; J->dst = dst; J->n = n; J->nslabs = nslabs; J->hdr_len = hdr_len;
+    HostStager& stager = J->stager;
     do {
         const bool src_on_host = n != 0 && classify(src) != kDevice;
         const bool dst_on_host = classify(dst) != kDevice;
+        J->dst_on_host = dst_on_host;
         if ((rc = c->ensure_aux((int)(3 * nslabs + 4))) != 0) break;
-        cudaStream_t s_in = c->aux[0], s_out = c->aux[1];
+        cudaStream_t s_in = c->aux[0];
+        J->s_out = c->aux[1];
         cudaEvent_t* ev_in = c->evs;
         cudaEvent_t* ev_done = c->evs + nslabs;
         cudaEvent_t* ev_scan = c->evs + 2 * nslabs;
         cudaEvent_t ev_start = c->evs[3 * nslabs + 1], ev_join = c->evs[3 * nslabs + 2];
+        J->ev_done = ev_done;
         cudaError_t e = cudaSuccess;
         // Odd slabs run on a second context and stream: the walk kernel is latency bound and leaves issue slots and
         // some shared memory free, which the pack / code kernels of the neighbouring slab can use.
         if (nslabs > 1 && !c2 && !g_profile) {                  // per-kernel timing (zb200_profile) wants the slabs serialized
             c2 = ctx_acquire_own();
             if (!c2) { rc = ZB_MEM_ERROR; break; }
+            J->c2 = c2;
         }
         // ---- [dict][src] as one contiguous device range ----
         const uint8_t* d_buf;
@@ -1562,6 +1593,7 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
             if ((rc = c->out.ensure(cap + 16)) != 0) break;
             d_out = c->out.as<uint8_t>();
         }
+        J->d_out = d_out;
         if ((rc = c->small.ensure(256)) != 0) break;
         if ((rc = c->ws[1].ensure((nslabs + 2) * 8)) != 0) break;
         if ((rc = c->ensure_pinned((nslabs + 8) * 8)) != 0) break;
@@ -1571,6 +1603,7 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
         uint64_t* d_pos = c->ws[1].as<uint64_t>();              // d_pos[i] = end of slab i in the output
         uint64_t* h_res = (uint64_t*)c->pinned;                 // [0..3] result words, [4..] slab ends
         uint64_t* h_pos = h_res + 4;
+        J->h_res = h_res; J->h_pos = h_pos;
         if ((e = cudaMemsetAsync(d_err, 0, 4, s)) != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         if (c2) {                                               // the second stream starts where the caller's stream is now
             cudaEventRecord(ev_start, s);
@@ -1622,13 +1655,32 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_res, c->small.p, 32, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) { set_error("deflate launch failed: %s", cudaGetErrorString(e)); cudaStreamSynchronize(s); rc = ZB_STREAM_ERROR; break; }
+    } while (0);
+    if (rc) shard_release(J);
+    return rc;
+}
 
+static int shard_end(ShardJob* J, size_t* dst_len, uint32_t* crc, uint32_t* adler)
+{
+    int rc = 0;
+    Ctx* c = J->c;
+    cudaStream_t s = J->s, s_out = J->s_out;
+    const uint64_t nslabs = J->nslabs, hdr_len = J->hdr_len, n = J->n;
+    const size_t cap = J->cap;
+    void* dst = J->dst;
+    uint8_t* d_out = J->d_out;
+    const bool dst_on_host = J->dst_on_host;
+    uint64_t* h_res = J->h_res; uint64_t* h_pos = J->h_pos;
+    HostDrainer& drainer = J->drainer;
+    (void)c;
+    do {
+        cudaError_t e = cudaSuccess;
         // ---- copy out finished slabs while later ones are still running ----
         uint64_t copied = hdr_len;                              // out[0, hdr_len) is written last, by k_frame
         const bool drain_threads = dst_on_host && n >= HostStager::kMinBytes && classify(dst) == kHostPageable;
         if (dst_on_host) {
             for (uint64_t i = 0; i + 1 < nslabs; i++) {
-                if ((e = cudaEventSynchronize(ev_done[i])) != cudaSuccess) break;
+                if ((e = cudaEventSynchronize(J->ev_done[i])) != cudaSuccess) break;
                 const uint64_t end = h_pos[i];
                 if (end > cap) break;                           // does not fit: reported below from the total
                 if (end > copied) {
@@ -1663,10 +1715,38 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
             if (e != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
         }
     } while (0);
-    stager.finish();
-    drainer.finish();
-    if (c2) ctx_release(c2, c2->own_stream);
-    ctx_release(c, s);
+    shard_release(J);
+    return rc;
+}
+
+ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict, size_t dict_len, void* dst,
+                               size_t* dst_len, int level, int wrap, int flags, uint32_t* crc, uint32_t* adler, void* stream)
+{
+    if (!dst_len) { set_error("zb200_deflate: bad argument"); return ZB_STREAM_ERROR; }
+    ShardJob J;
+    int rc = shard_begin(&J, src, src_len, dict, dict_len, dst, *dst_len, level, wrap, flags, stream);
+    if (rc) return rc;
+    return shard_end(&J, dst_len, crc, adler);
+}
+
+// The two halves as calls of their own (see ShardJob): *job receives a handle that zb200_deflate_shard_end consumes.
+ZB_API int zb200_deflate_shard_begin(void** job, const void* src, size_t src_len, const void* dict, size_t dict_len, void* dst,
+                                     size_t dst_cap, int level, int wrap, int flags, void* stream)
+{
+    if (!job) { set_error("zb200_deflate_shard_begin: bad argument"); return ZB_STREAM_ERROR; }
+    ShardJob* J = new ShardJob();
+    const int rc = shard_begin(J, src, src_len, dict, dict_len, dst, dst_cap, level, wrap, flags, stream);
+    if (rc) { delete J; *job = nullptr; return rc; }
+    *job = J;
+    return 0;
+}
+
+ZB_API int zb200_deflate_shard_end(void* job, size_t* dst_len, uint32_t* crc, uint32_t* adler)
+{
+    if (!job || !dst_len) { set_error("zb200_deflate_shard_end: bad argument"); return ZB_STREAM_ERROR; }
+    ShardJob* J = static_cast<ShardJob*>(job);
+    const int rc = shard_end(J, dst_len, crc, adler);
+    delete J;
     return rc;
 }
 

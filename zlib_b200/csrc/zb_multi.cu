@@ -229,32 +229,48 @@ ZB_API int zb200_multi_deflate(const void* src, size_t src_len, void* dst, size_
         cudaStream_t cs = t->copy_stream[r];
         uint64_t pos = hl;                                      // every worker folds the same records, so all agree on `pos`
         uint32_t crc = 0, adler = 1;
-        for (uint64_t j = 0; j < rounds; j++) {
-            const int k = (int)(j & 1);
+        void* job[2] = {nullptr, nullptr};
+        // Piece j + 1 is enqueued (zb200_deflate_shard_begin) before piece j's length is read back, so the GPU never waits
+        // for the host; the D2H of piece j runs on the copy stream behind the kernels of piece j + 1.
+        auto range = [&](uint64_t j, uint64_t& a, uint64_t& b) {
             const uint64_t g = j * ndev + r;
-            const uint64_t a = std::min<uint64_t>(src_len, g * per), b = std::min<uint64_t>(src_len, (g + 1) * per);
+            a = std::min<uint64_t>(src_len, g * per); b = std::min<uint64_t>(src_len, (g + 1) * per);
+        };
+        auto begin = [&](uint64_t j) -> int {
+            const int k = (int)(j & 1);
+            uint64_t a, b;
+            range(j, a, b);
             const bool ends_stream = b == src_len && a < src_len;     // the piece that ends the stream (later ones, if any, are empty)
-            const bool empty_stream_owner = src_len == 0 && g == 0;
+            const bool empty_stream_owner = src_len == 0 && j == 0 && r == 0;
+            if (b <= a && !empty_stream_owner) return 0;
+            if (t->d_out_cap[k][r] < piece_cap) {
+                if (t->d_out[k][r]) cudaFree(t->d_out[k][r]);
+                t->d_out[k][r] = nullptr; t->d_out_cap[k][r] = 0;
+                if (cudaMalloc(&t->d_out[k][r], piece_cap) != cudaSuccess) { cudaGetLastError(); set_error("zb200_multi_deflate: device allocation of %zu bytes failed", piece_cap); return ZB_MEM_ERROR; }
+                t->d_out_cap[k][r] = piece_cap;
+            }
+            if (j >= 2 && cudaEventSynchronize(t->ev[k][r]) != cudaSuccess) { set_error("zb200_multi_deflate: D2H failed"); return ZB_STREAM_ERROR; }   // the buffer's previous contents are out
+            const size_t dl = (size_t)std::min<uint64_t>(a, 32768);
+            const int flags = ZB200_DEFLATE_NO_HEADER | ZB200_DEFLATE_NO_TRAILER | ((ends_stream || empty_stream_owner) ? 0 : ZB200_DEFLATE_NOT_LAST);
+            return zb200_deflate_shard_begin(&job[k], in + a, (size_t)(b - a), dl ? in + a - dl : nullptr, dl, t->d_out[k][r], piece_cap, level,
+                                             ZB200_WRAP_RAW, flags, nullptr);
+        };
+        int rc0 = begin(0);
+        for (uint64_t j = 0; j < rounds && !rc0; j++) {
+            const int k = (int)(j & 1);
+            if (j + 1 < rounds && (rc0 = begin(j + 1)) != 0) break;
+            uint64_t a, b;
+            range(j, a, b);
             uint64_t rec[4] = {0, b - a, 0, 1};
-            if (b > a || empty_stream_owner) {
-                if (t->d_out_cap[k][r] < piece_cap) {
-                    if (t->d_out[k][r]) cudaFree(t->d_out[k][r]);
-                    t->d_out[k][r] = nullptr; t->d_out_cap[k][r] = 0;
-                    if (cudaMalloc(&t->d_out[k][r], piece_cap) != cudaSuccess) { cudaGetLastError(); set_error("zb200_multi_deflate: device allocation of %zu bytes failed", piece_cap); return ZB_MEM_ERROR; }
-                    t->d_out_cap[k][r] = piece_cap;
-                }
-                if (j >= 2 && cudaEventSynchronize(t->ev[k][r]) != cudaSuccess) { set_error("zb200_multi_deflate: D2H failed"); return ZB_STREAM_ERROR; }   // the buffer's previous contents are out
-                const size_t dl = (size_t)std::min<uint64_t>(a, 32768);
-                size_t got = piece_cap;
+            if (job[k]) {
+                size_t got = 0;
                 uint32_t c32 = 0, a32 = 1;
-                const int flags = ZB200_DEFLATE_NO_HEADER | ZB200_DEFLATE_NO_TRAILER | ((ends_stream || empty_stream_owner) ? 0 : ZB200_DEFLATE_NOT_LAST);
-                const int rc1 = zb200_deflate_shard(in + a, (size_t)(b - a), dl ? in + a - dl : nullptr, dl, t->d_out[k][r], &got, level,
-                                                    ZB200_WRAP_RAW, flags, &c32, &a32, nullptr);
-                if (rc1) return rc1;
+                rc0 = zb200_deflate_shard_end(job[k], &got, &c32, &a32);
+                job[k] = nullptr;
+                if (rc0) break;
                 rec[0] = got; rec[2] = c32; rec[3] = a32;
             }
-            int rc2 = gather4(t, r, rec, cs);
-            if (rc2) return rc2;
+            if ((rc0 = gather4(t, r, rec, cs)) != 0) break;
             const uint64_t* all = t->h_recv[r];
             uint64_t mine_at = 0;
             for (int q = 0; q < ndev; q++) {
@@ -265,10 +281,13 @@ ZB_API int zb200_multi_deflate(const void* src, size_t src_len, void* dst, size_
             }
             if (rec[0]) {
                 if (mine_at + rec[0] > cap) sh.overflow.store(1);
-                else if (cudaMemcpyAsync(out + mine_at, t->d_out[k][r], rec[0], cudaMemcpyDeviceToHost, cs) != cudaSuccess) { set_error("zb200_multi_deflate: D2H failed: %s", cudaGetErrorString(cudaGetLastError())); return ZB_STREAM_ERROR; }
+                else if (cudaMemcpyAsync(out + mine_at, t->d_out[k][r], rec[0], cudaMemcpyDeviceToHost, cs) != cudaSuccess) { set_error("zb200_multi_deflate: D2H failed: %s", cudaGetErrorString(cudaGetLastError())); rc0 = ZB_STREAM_ERROR; break; }
             }
             cudaEventRecord(t->ev[k][r], cs);
         }
+        for (int k = 0; k < 2; k++)                              // after a failure: nothing may stay enqueued against the scratch
+            if (job[k]) { size_t g = 0; zb200_deflate_shard_end(job[k], &g, nullptr, nullptr); job[k] = nullptr; }
+        if (rc0) { cudaStreamSynchronize(cs); return rc0; }
         if (cudaStreamSynchronize(cs) != cudaSuccess) { set_error("zb200_multi_deflate: D2H failed: %s", cudaGetErrorString(cudaGetLastError())); return ZB_STREAM_ERROR; }
         if (r == 0) { sh.total = pos; sh.crc = crc; sh.adler = adler; }
         return 0;

@@ -97,6 +97,15 @@ int Ctx::ensure_pinned(size_t bytes)
     return 0;
 }
 
+int Ctx::ensure_flags()
+{
+    if (flags.p) return 0;
+    int rc = flags.ensure(256);
+    if (rc) return rc;
+    if (cudaMemset(flags.p, 0, 256) != cudaSuccess) { cudaGetLastError(); set_error("flag words could not be cleared"); return ZB_MEM_ERROR; }
+    return 0;
+}
+
 int Ctx::ensure_aux(int nevents)
 {
     for (int i = 0; i < 2; i++) {

@@ -168,6 +168,18 @@ def piece_ranges(total: int, world: int, pieces_per_rank: int, chunk: int = CHUN
     return out
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for the exchange and the transfers of deflate_rounds."""
+    import torch
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=None, root: int = 0, outs=None,
                    final=None, host_final: Optional[int] = None, stream=None, copy_stream=None, last_round_is_last: bool = True):
     """ONE stream from all ranks, assembled on `root` while the compression is still running.
@@ -190,39 +202,61 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
     pos, crc_all, adl_all, n_all = len(header), 0, 1, 0
     works = []
     dev = outs[0].device
-    for j, (src_ptr, n, dict_ptr, dict_len) in enumerate(pieces):
+    # Pipelined when the library offers the two halves of the call: piece j + 1 is enqueued before piece j's length is read,
+    # and the exchange and the transfers run on a side stream, so nothing of them queues behind the next piece's kernels.
+    pipelined = hasattr(lib, "deflate_shard_begin") and dev.type == "cuda"
+    side = _side_stream(dev) if pipelined else None
+    import contextlib
+
+    def on_side():
+        return torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+
+    def args_of(j):
+        src_ptr, n, dict_ptr, dict_len = pieces[j]
         last = last_round_is_last and j == rounds - 1 and rank == world - 1
         flags = zb.ZB200_DEFLATE_NO_HEADER | zb.ZB200_DEFLATE_NO_TRAILER | (0 if last else zb.ZB200_DEFLATE_NOT_LAST)
-        clen, crc, adl = lib.deflate_shard(src_ptr, n, dict_ptr if dict_len else None, dict_len, outs[j].data_ptr(),
-                                           outs[j].numel(), level, zb.WRAP_RAW, flags, stream)
-        metas = exchange_meta((clen, n, crc, adl), dev, group)
-        offs = []
-        for cl, m, c, a in metas:                                  # global order within a round = rank order
-            offs.append(pos)
-            pos += cl
-            if m:
-                crc_all = lib.crc32_combine(crc_all, c, m)
-                adl_all = adler_join(adl_all, a, m)
-            n_all += m
-        if host_final is not None:                                 # every rank writes its own part of the shared host buffer
-            if clen:
-                lib._check(lib.dll.zb200_copy_async(host_final + offs[rank], outs[j].data_ptr(), clen, zb._stream(copy_stream)),
-                           "zb200_copy_async")
-        elif final is not None or rank != root:
-            ops = []
-            if rank == root:
-                for r in range(world):
-                    cl = metas[r][0]
-                    if not cl:
-                        continue
-                    if r == root:
-                        final[offs[r]:offs[r] + cl].copy_(outs[j][:cl], non_blocking=True)
-                    else:
-                        ops.append(dist.P2POp(dist.irecv, final[offs[r]:offs[r] + cl], _global(group, r), group))
-            elif clen:
-                ops.append(dist.P2POp(dist.isend, outs[j][:clen], _global(group, root), group))
-            if ops:
-                works += dist.batch_isend_irecv(ops)
+        return (src_ptr, n, dict_ptr if dict_len else None, dict_len, outs[j].data_ptr(), outs[j].numel(), level, zb.WRAP_RAW, flags, stream)
+
+    jobs = {}
+    if pipelined and rounds:
+        jobs[0] = lib.deflate_shard_begin(*args_of(0))
+    for j in range(rounds):
+        n = pieces[j][1]
+        if pipelined:
+            if j + 1 < rounds:
+                jobs[j + 1] = lib.deflate_shard_begin(*args_of(j + 1))
+            clen, crc, adl = lib.deflate_shard_end(jobs.pop(j))
+        else:
+            clen, crc, adl = lib.deflate_shard(*args_of(j))
+        with on_side():
+            metas = exchange_meta((clen, n, crc, adl), dev, group)
+            offs = []
+            for cl, m, c, a in metas:                              # global order within a round = rank order
+                offs.append(pos)
+                pos += cl
+                if m:
+                    crc_all = lib.crc32_combine(crc_all, c, m)
+                    adl_all = adler_join(adl_all, a, m)
+                n_all += m
+            if host_final is not None:                             # every rank writes its own part of the shared host buffer
+                if clen:
+                    lib._check(lib.dll.zb200_copy_async(host_final + offs[rank], outs[j].data_ptr(), clen, zb._stream(copy_stream)),
+                               "zb200_copy_async")
+            elif final is not None or rank != root:
+                ops = []
+                if rank == root:
+                    for r in range(world):
+                        cl = metas[r][0]
+                        if not cl:
+                            continue
+                        if r == root:
+                            final[offs[r]:offs[r] + cl].copy_(outs[j][:cl], non_blocking=True)
+                        else:
+                            ops.append(dist.P2POp(dist.irecv, final[offs[r]:offs[r] + cl], _global(group, r), group))
+                elif clen:
+                    ops.append(dist.P2POp(dist.isend, outs[j][:clen], _global(group, root), group))
+                if ops:
+                    works += dist.batch_isend_irecv(ops)
     if wrap == zb.WRAP_ZLIB:
         trailer = adl_all.to_bytes(4, "big")
     elif wrap == zb.WRAP_GZIP:
@@ -230,18 +264,21 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
     else:
         trailer = b""
     total = pos + len(trailer)
-    for w in works:
-        w.wait()
-    if rank == root:
-        if host_final is not None:
-            import ctypes as C
-            C.memmove(host_final, header, len(header))
-            C.memmove(host_final + pos, trailer, len(trailer))
-        elif final is not None:
-            if header:
-                final[:len(header)] = torch.tensor(list(header), dtype=torch.uint8, device=dev)
-            if trailer:
-                final[pos:total] = torch.tensor(list(trailer), dtype=torch.uint8, device=dev)
+    with on_side():
+        for w in works:
+            w.wait()
+        if rank == root:
+            if host_final is not None:
+                import ctypes as C
+                C.memmove(host_final, header, len(header))
+                C.memmove(host_final + pos, trailer, len(trailer))
+            elif final is not None:
+                if header:
+                    final[:len(header)] = torch.tensor(list(header), dtype=torch.uint8, device=dev)
+                if trailer:
+                    final[pos:total] = torch.tensor(list(trailer), dtype=torch.uint8, device=dev)
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)              # the caller's stream sees the assembled stream
     if host_final is not None:
         lib._check(lib.dll.zb200_sync(zb._stream(copy_stream)), "zb200_sync")
     return total, crc_all, adl_all, n_all
