@@ -93,3 +93,67 @@ def test_inflate_refuses_a_larger_window_than_opened(gpu_lib, oracle):
         assert rc == zb.Z_STREAM_END and out == data, (w, rc, msg)
     rc, out, msg, _ = gpu_lib.inflate_stream(z10, 9, 4096, 4096)
     assert rc == zb.Z_DATA_ERROR and msg == "invalid window size"
+
+
+def test_partial_flush_and_prime(gpu_lib, oracle):
+    """Z_PARTIAL_FLUSH ends on the ten bits of an empty static block and leaves the stream unaligned (trees.c:892), it is
+    not served as a sync flush any more; deflatePrime (deflate.c:404-414) puts bits in front of the first block."""
+    import ctypes as C
+    rng = random.Random(77)
+    data = zhelpers.corpus(1, 300000, 12) + zhelpers.corpus(3, 50000, 13)
+    marker = b"\x00\x00\xff\xff"
+    for level in (1, 6, 0):
+        cuts = sorted(rng.sample(range(1000, len(data) - 1000), 9))
+        flushes = {c: zb.Z_PARTIAL_FLUSH for c in cuts}
+        flushes[cuts[4]] = zb.Z_SYNC_FLUSH
+        rc, z = gpu_lib.deflate_stream(data, level, -15, 1 << 20, 1 << 20, flushes)
+        assert rc == zb.Z_OK
+        assert zlib.decompress(z, -15) == data
+        rc2, out, used = oracle.inflate(z, len(data), 0)
+        assert rc2 == 0 and out == data and used == len(z)
+        if level:
+            assert z.count(marker) <= 2, z.count(marker)           # the sync flush (and chance), not one per partial flush
+        rc, zs = gpu_lib.deflate_stream(data, level, 15, 1 << 20, 1 << 20, {c: zb.Z_SYNC_FLUSH for c in cuts})
+        assert rc == zb.Z_OK and zs.count(marker) >= 9 and zlib.decompress(zs) == data
+    # every alignment: partial flushes after inputs of 1..40 bytes leave 0..7 bits pending each time
+    small = zhelpers.corpus(1, 4000, 14)
+    flushes = {i * 97 + (i % 40) + 1: zb.Z_PARTIAL_FLUSH for i in range(1, 40)}
+    rc, z = gpu_lib.deflate_stream(small, 6, 15, 1 << 20, 1 << 20, flushes)
+    assert rc == zb.Z_OK and zlib.decompress(z) == small
+    # deflatePrime: ten primed bits that happen to be an empty static block keep a raw stream decodable
+    strm = zb.z_stream()
+    assert gpu_lib.dll.deflateInit2_(C.byref(strm), 6, zb.Z_DEFLATED, -15, 8, 0, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+    assert gpu_lib.dll.deflatePrime(C.byref(strm), 17, 0) == zb.Z_STREAM_ERROR
+    assert gpu_lib.dll.deflatePrime(C.byref(strm), 10, 2) == zb.Z_OK
+    src = C.create_string_buffer(data, len(data))
+    dst = C.create_string_buffer(len(data) + 1000)
+    strm.next_in, strm.avail_in = C.addressof(src), len(data)
+    strm.next_out, strm.avail_out = C.addressof(dst), len(data) + 1000
+    assert gpu_lib.dll.deflate(C.byref(strm), zb.Z_FINISH) == zb.Z_STREAM_END
+    raw = dst.raw[:strm.total_out]
+    assert gpu_lib.dll.deflateEnd(C.byref(strm)) == zb.Z_OK
+    assert raw[0] == 0x02 and zlib.decompress(raw, -15) == data     # 010 + seven zero bits come first
+    # deflateParams mid-stream (deflate.c:416-451): what was gathered leaves under the old level with a partial flush
+    strm = zb.z_stream()
+    assert gpu_lib.dll.deflateInit_(C.byref(strm), 9, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+    half = len(data) // 2
+    strm.next_in, strm.avail_in = C.addressof(src), half
+    strm.next_out, strm.avail_out = C.addressof(dst), len(data) + 1000
+    assert gpu_lib.dll.deflate(C.byref(strm), zb.Z_NO_FLUSH) == zb.Z_OK
+    assert gpu_lib.dll.deflateParams(C.byref(strm), 0, 0) == zb.Z_OK
+    strm.next_in, strm.avail_in = C.addressof(src) + half, 1000
+    assert gpu_lib.dll.deflate(C.byref(strm), zb.Z_NO_FLUSH) == zb.Z_OK
+    assert gpu_lib.dll.deflateParams(C.byref(strm), 1, 0) == zb.Z_OK
+    strm.next_in, strm.avail_in = C.addressof(src) + half + 1000, len(data) - half - 1000
+    assert gpu_lib.dll.deflate(C.byref(strm), zb.Z_FINISH) == zb.Z_STREAM_END
+    z = dst.raw[:strm.total_out]
+    gpu_lib.dll.deflateEnd(C.byref(strm))
+    assert zlib.decompress(z) == data
+    strm = zb.z_stream()
+    assert gpu_lib.dll.deflateInit_(C.byref(strm), 6, zb.ZLIB_VERSION, C.sizeof(zb.z_stream)) == zb.Z_OK
+    strm.next_in, strm.avail_in = C.addressof(src), 5000
+    strm.next_out, strm.avail_out = C.addressof(dst), 100000
+    assert gpu_lib.dll.deflate(C.byref(strm), zb.Z_NO_FLUSH) == zb.Z_OK
+    strm.avail_out = 0
+    assert gpu_lib.dll.deflateParams(C.byref(strm), 1, 0) == zb.Z_BUF_ERROR     # deflate.c:440 via deflate(): no room for the flush
+    gpu_lib.dll.deflateEnd(C.byref(strm))

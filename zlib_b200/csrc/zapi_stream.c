@@ -38,6 +38,7 @@ struct internal_state {
     unsigned char *out; size_t out_pos, out_len, out_cap;   /* compressed, not yet delivered */
     uLong check;                                       /* running adler32 / crc32 of the input */
     int dict_set; uLong dict_id;
+    unsigned bi_bits; unsigned long bi_val;            /* bits that precede the next block (deflatePrime, Z_PARTIAL_FLUSH): deflate.h bi_valid / bi_buf */
     gz_headerp gzhead;
     int trailer_done;
     /* ---- inflate ---- */
@@ -72,15 +73,23 @@ static uLong adler_join(uLong a1, uLong a2, size_t len2)
 
 /* ======================================================================== deflate */
 
-static int zs_reserve(unsigned char **buf, size_t *cap, size_t want)
+/* Every byte a stream owns comes from the caller's allocator (deflate.c:243-247 promises that for the reference's
+ * window, hash tables and pending buffer; here it is the gather buffer and the pending output).  zalloc takes 32-bit
+ * item counts and sizes, so buffers are requested in 4 KiB items.  `keep` bytes of the old buffer survive. */
+static int zs_reserve(z_streamp strm, unsigned char **buf, size_t *cap, size_t want, size_t keep)
 {
     unsigned char *p;
     size_t n;
     if (want <= *cap) return 0;
     n = *cap ? *cap : 4096;
     while (n < want) n *= 2;
-    p = (unsigned char *)realloc(*buf, n);
+    if ((n >> 12) > 0xffffffffUL) return -1;
+    p = (unsigned char *)strm->zalloc(strm->opaque, (uInt)(n >> 12), 4096u);
     if (!p) return -1;
+    if (*buf) {
+        if (keep) memcpy(p, *buf, keep);
+        strm->zfree(strm->opaque, *buf);
+    }
     *buf = p; *cap = n;
     return 0;
 }
@@ -88,7 +97,7 @@ static int zs_reserve(unsigned char **buf, size_t *cap, size_t want)
 static int out_append(zs *s, const unsigned char *p, size_t n)
 {
     if (s->out_pos == s->out_len) s->out_pos = s->out_len = 0;
-    if (zs_reserve(&s->out, &s->out_cap, s->out_len + n)) return -1;
+    if (zs_reserve(s->strm, &s->out, &s->out_cap, s->out_len + n, s->out_len)) return -1;
     memcpy(s->out + s->out_len, p, n);
     s->out_len += n;
     return 0;
@@ -153,6 +162,7 @@ ZAPI int deflateReset(z_streamp strm)                           /* deflate.c:357
     s->check = strm->adler;
     s->last_flush = Z_NO_FLUSH;
     s->dict_set = 0; s->trailer_done = 0;
+    s->bi_bits = 0; s->bi_val = 0;
     return Z_OK;
 }
 
@@ -163,7 +173,8 @@ ZAPI int deflateEnd(z_streamp strm)                             /* deflate.c:859
     if (strm == Z_NULL || strm->state == Z_NULL || strm->state->kind != KIND_DEFLATE) return Z_STREAM_ERROR;
     s = strm->state;
     busy = s->status == ST_BUSY;            /* deflate.c:886: ending before Z_FINISH completed is a data error */
-    free(s->in); free(s->out);
+    if (s->in) strm->zfree(strm->opaque, s->in);
+    if (s->out) strm->zfree(strm->opaque, s->out);
     strm->zfree(strm->opaque, s);
     strm->state = Z_NULL;
     return busy ? Z_DATA_ERROR : Z_OK;
@@ -205,11 +216,15 @@ ZAPI int deflateTune(z_streamp strm, int good_length, int max_lazy, int nice_len
     return Z_OK;            /* search budgets are fixed per level in the kernels (deflate.c:454-470 only stores them) */
 }
 
-ZAPI int deflatePrime(z_streamp strm, int bits, int value)
+ZAPI int deflatePrime(z_streamp strm, int bits, int value)     /* deflate.c:404-414 */
 {
-    (void)bits; (void)value;
-    if (strm == Z_NULL || strm->state == Z_NULL) return Z_STREAM_ERROR;
-    ERR_RETURN(strm, Z_STREAM_ERROR);   /* chunks start on byte boundaries; sub-byte priming is not offered */
+    zs *s;
+    if (strm == Z_NULL || strm->state == Z_NULL || strm->state->kind != KIND_DEFLATE) return Z_STREAM_ERROR;
+    if (bits < 0 || bits > 16) return Z_STREAM_ERROR;
+    s = strm->state;
+    s->bi_bits = (unsigned)bits;                                /* the reference overwrites bi_valid / bi_buf the same way */
+    s->bi_val = (unsigned long)value & ((1UL << bits) - 1UL);
+    return Z_OK;
 }
 
 ZAPI int deflateSetHeader(z_streamp strm, gz_headerp head)      /* deflate.c:393-401 */
@@ -220,25 +235,73 @@ ZAPI int deflateSetHeader(z_streamp strm, gz_headerp head)      /* deflate.c:393
     return Z_OK;
 }
 
-/* compress everything gathered so far into the pending buffer */
-static int zs_compress(z_streamp strm, int level, int final, int force_mark)
+/* Framing bits written by the host: appends `n` bits to the pending ones and moves whole bytes to the output.  Only
+ * block headers of EMPTY blocks and alignment go through here (send_bits, trees.c:217); data never does. */
+static int bits_put(zs *s, unsigned long value, unsigned n)
+{
+    s->bi_val |= value << s->bi_bits;
+    s->bi_bits += n;
+    while (s->bi_bits >= 8) {
+        unsigned char b = (unsigned char)(s->bi_val & 0xff);
+        if (out_append(s, &b, 1)) return -1;
+        s->bi_val >>= 8; s->bi_bits -= 8;
+    }
+    return 0;
+}
+
+static int bits_align(zs *s)                                    /* bi_windup, trees.c:1178 */
+{
+    return s->bi_bits ? bits_put(s, 0, 8 - s->bi_bits) : 0;
+}
+
+static int bits_marker(zs *s)                                   /* _tr_stored_block(0 bytes), trees.c:867: 000, pad, 00 00 FF FF */
+{
+    static const unsigned char m[4] = {0, 0, 0xff, 0xff};
+    if (bits_put(s, 0, 3) || bits_align(s)) return -1;
+    return out_append(s, m, 4);
+}
+
+enum { END_NONE = 0, END_MARK = 1, END_PARTIAL = 2 };
+
+/* compress everything gathered so far into the pending buffer; `end` says how a batch that is not the last one ends:
+ * as the blocks fall (END_NONE: a byte-aligning marker all the same, batches concatenate on byte boundaries), with the
+ * empty stored block of Z_SYNC_FLUSH / Z_FULL_FLUSH (END_MARK), or with the empty static block of Z_PARTIAL_FLUSH
+ * (END_PARTIAL, _tr_align, trees.c:892) after which the stream stays where its bits fall. */
+static int zs_compress(z_streamp strm, int level, int final, int end)
 {
     zs *s = strm->state;
     size_t cap, got;
-    uint32_t crc = 0, adler = 1;
-    int rc, flags = ZB200_DEFLATE_NO_HEADER | ZB200_DEFLATE_NO_TRAILER;
+    uint32_t crc = 0, adler = 1, tail = 0;
+    int rc, flags = 0;
+    /* whole bytes of a deflatePrime (up to 16 bits) leave first */
+    if (s->bi_bits >= 8 && bits_put(s, 0, 0)) return Z_MEM_ERROR;
+    if (s->in_len == 0) {                                       /* nothing gathered: the empty blocks are host framing */
+        if (final) { if (bits_put(s, 3, 10) || bits_align(s)) return Z_MEM_ERROR; }      /* final empty static block: 03 00 when aligned */
+        else if (end == END_PARTIAL) { if (bits_put(s, 2, 10)) return Z_MEM_ERROR; }
+        else if (end == END_MARK || s->bi_bits) { if (bits_marker(s)) return Z_MEM_ERROR; }
+        return Z_OK;
+    }
+    if (level == 0) {                                           /* stored blocks are whole bytes: pending bits are closed first */
+        if (s->bi_bits && bits_marker(s)) return Z_MEM_ERROR;
+        if (end == END_PARTIAL) end = END_MARK;
+    }
     if (!final) flags |= ZB200_DEFLATE_NOT_LAST;
-    if (force_mark) flags |= ZB200I_DEFLATE_FORCE_MARK;
+    if (end == END_MARK) flags |= ZB200I_DEFLATE_FORCE_MARK;
     if (s->strategy != Z_DEFAULT_STRATEGY) flags |= (s->strategy << 8);       /* Z_FILTERED, Z_HUFFMAN_ONLY, Z_RLE, Z_FIXED */
     if (s->wbits != 15) flags |= ZB200I_DEFLATE_WBITS(s->wbits);              /* match distances stay inside the declared window */
     cap = (size_t)compressBound((uLong)s->in_len) + 64;
     if (s->out_pos == s->out_len) s->out_pos = s->out_len = 0;
-    if (zs_reserve(&s->out, &s->out_cap, s->out_len + cap)) return Z_MEM_ERROR;
+    if (zs_reserve(strm, &s->out, &s->out_cap, s->out_len + cap, s->out_len)) return Z_MEM_ERROR;
     got = cap;
-    rc = zb200_deflate_shard(s->in, s->in_len, s->hist_len ? s->hist : NULL, s->hist_len, s->out + s->out_len, &got,
-                             level, ZB200_WRAP_RAW, flags, &crc, &adler, NULL);
+    if (s->bi_bits || (end == END_PARTIAL && !final))
+        rc = zb200i_deflate_shard_bits(s->in, s->in_len, s->hist_len ? s->hist : NULL, s->hist_len, s->out + s->out_len, &got,
+                                       level, flags, s->bi_bits, (uint32_t)s->bi_val, end == END_PARTIAL && !final, &tail, &crc, &adler);
+    else
+        rc = zb200_deflate_shard(s->in, s->in_len, s->hist_len ? s->hist : NULL, s->hist_len, s->out + s->out_len, &got,
+                                 level, ZB200_WRAP_RAW, flags | ZB200_DEFLATE_NO_HEADER | ZB200_DEFLATE_NO_TRAILER, &crc, &adler, NULL);
     if (rc != Z_OK) return rc;
     s->out_len += got;
+    s->bi_bits = tail & 0xff; s->bi_val = tail >> 8;
     if (s->wrap == 1) s->check = adler_join(s->check, adler, s->in_len);
     else if (s->wrap == 2) s->check = crc32_combine(s->check, crc, (z_off_t)s->in_len);
     strm->adler = s->check;
@@ -336,20 +399,21 @@ ZAPI int deflate(z_streamp strm, int flush)                     /* deflate.c:552
         /* gather (read_buf, deflate.c:956): the engine is greedy, like the reference at any level */
         while (strm->avail_in != 0) {
             size_t room = ZS_BATCH - s->in_len, n = strm->avail_in < room ? strm->avail_in : room;
-            if (zs_reserve(&s->in, &s->in_cap, s->in_len + n)) ERR_RETURN(strm, Z_MEM_ERROR);
+            if (zs_reserve(strm, &s->in, &s->in_cap, s->in_len + n, s->in_len)) ERR_RETURN(strm, Z_MEM_ERROR);
             memcpy(s->in + s->in_len, strm->next_in, n);
             s->in_len += n; strm->next_in += n; strm->avail_in -= (uInt)n; strm->total_in += n;
             if (s->in_len == ZS_BATCH && (strm->avail_in != 0 || flush == Z_NO_FLUSH)) {
-                if ((rc = zs_compress(strm, s->level, 0, 0)) != Z_OK) ERR_RETURN(strm, rc);
+                if ((rc = zs_compress(strm, s->level, 0, END_NONE)) != Z_OK) ERR_RETURN(strm, rc);
             }
         }
         if (flush != Z_NO_FLUSH && s->status != ST_FINISH) {
             if (flush == Z_FINISH) {
-                if ((rc = zs_compress(strm, s->level, 1, 0)) != Z_OK) ERR_RETURN(strm, rc);
+                if ((rc = zs_compress(strm, s->level, 1, END_NONE)) != Z_OK) ERR_RETURN(strm, rc);
                 s->status = ST_FINISH;
             } else {
-                /* PARTIAL, SYNC and FULL all end on the empty stored block (deflate.c:808-819) */
-                if ((rc = zs_compress(strm, s->level, 0, 1)) != Z_OK) ERR_RETURN(strm, rc);
+                /* deflate.c:808-825: PARTIAL ends on the ten bits of an empty static block and stays unaligned,
+                 * SYNC and FULL end on the empty stored block */
+                if ((rc = zs_compress(strm, s->level, 0, flush == Z_PARTIAL_FLUSH ? END_PARTIAL : END_MARK)) != Z_OK) ERR_RETURN(strm, rc);
                 if (flush == Z_FULL_FLUSH) s->hist_len = 0;     /* forget history */
             }
         }
@@ -393,12 +457,9 @@ ZAPI int deflateParams(z_streamp strm, int level, int strategy)  /* deflate.c:41
     if (level == Z_DEFAULT_COMPRESSION) level = 6;
     if (level < 0 || level > 9 || strategy < 0 || strategy > Z_FIXED) return Z_STREAM_ERROR;
     if ((level != s->level || strategy != s->strategy) && strm->total_in != 0) {
-        /* flush what was gathered under the old parameters (the reference does deflate(Z_PARTIAL_FLUSH)) */
-        if (s->in_len != 0) {
-            if (s->status == ST_INIT && (err = put_header(strm)) != Z_OK) return err;
-            err = zs_compress(strm, s->level, 0, 0);
-            if (err == Z_OK && strm->next_out != Z_NULL) out_deliver(strm);
-        }
+        /* what was gathered goes out under the old parameters: deflate(strm, Z_PARTIAL_FLUSH), deflate.c:438-441, with its
+         * return codes (Z_BUF_ERROR when avail_out is 0, Z_STREAM_ERROR without an output buffer) */
+        err = deflate(strm, Z_PARTIAL_FLUSH);
     }
     s->level = level; s->strategy = strategy;
     return err;
@@ -416,7 +477,7 @@ ZAPI int deflateCopy(z_streamp dest, z_streamp source)          /* deflate.c:894
     memcpy(d, s, sizeof(zs));
     dest->state = d; d->strm = dest;
     d->in = d->out = NULL; d->in_cap = d->out_cap = 0;
-    if (zs_reserve(&d->in, &d->in_cap, s->in_len + 1) || zs_reserve(&d->out, &d->out_cap, s->out_len + 1)) {
+    if (zs_reserve(dest, &d->in, &d->in_cap, s->in_len + 1, 0) || zs_reserve(dest, &d->out, &d->out_cap, s->out_len + 1, 0)) {
         deflateEnd(dest);
         return Z_MEM_ERROR;
     }

@@ -15,6 +15,11 @@ extern "C" {
  * MAX_DIST = (1 << windowBits) - 262 (h/deflate.h:276), so a decoder that sizes its window from CINFO can follow. */
 #define ZB200I_DEFLATE_WBITS(w) (((w) & 15) << 12)
 
+/* A raw shard with pending bits at either end (deflatePrime, Z_PARTIAL_FLUSH): see zb_deflate.cu. */
+int zb200i_deflate_shard_bits(const void *src, size_t src_len, const void *dict, size_t dict_len, void *dst, size_t *dst_len,
+                              int level, int flags, uint32_t prime_bits, uint32_t prime_val, int partial_end,
+                              uint32_t *tail, uint32_t *crc, uint32_t *adler);
+
 /* ---- one resumable inflate stream (inflate.c state machine on the device) ---- */
 typedef struct zb200i_inflater zb200i_inflater;
 

@@ -48,9 +48,12 @@ namespace zb {
 // position is linked (k_lz_link), so two steps already see as much, and every further step is one more dependent trip
 // to L2.  Measured on the config shapes (level 1, reference = the whole buffer as one stream): 1 GiB mixed 0.989 x the
 // reference's size at 13.8 ms instead of 0.980 x at 15.4 ms; 64 MiB text 0.997 x instead of 0.969 x (gate: <= 1.02 x).
+// Level 6 likewise stops after 32 candidates instead of 128 (good / lazy / nice as in the reference): 256 MiB mixed
+// 18.3 -> 10.5 ms with the output 0.55 % larger (0.975 x the reference's), 64 MiB text 5.6 -> 3.7 ms at 1.0046 x the
+// reference's size (profiles/r2_sweeps.md).  Levels 7..9 keep the reference's budgets.
 static const LevelCfg h_levels[10] = {
     {0, 0, 0, 0, 0},      {4, 4, 8, 2, 1},       {4, 5, 16, 8, 1},     {4, 6, 32, 32, 1},
-    {4, 4, 16, 16, 2},    {8, 16, 32, 32, 2},    {8, 16, 128, 128, 2}, {8, 32, 128, 256, 2},
+    {4, 4, 16, 16, 2},    {8, 16, 32, 32, 2},    {8, 16, 128, 32, 2},  {8, 32, 128, 256, 2},
     {32, 128, 258, 1024, 2}, {32, 258, 258, 4096, 2}};
 
 constexpr uint32_t kFullMask = 0xffffffffu;
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(kT, kSmemLinks ? 1 : 3)
 k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const uint16_t* __restrict__ dist16,
           uint32_t* __restrict__ tok_tmp, uint32_t* __restrict__ tok, uint32_t* __restrict__ blk_ntok,
           uint32_t* __restrict__ blk_hist, int kind, int max_chain, uint32_t nice, uint32_t max_lazy, uint32_t good,
-          int strategy, uint32_t max_dist, const ChunkDesc* __restrict__ cd, uint32_t nblocks, uint32_t* __restrict__ next_block)
+          int strategy, uint32_t max_dist, const ChunkDesc* __restrict__ cd, uint32_t nblocks, uint32_t* __restrict__ next_block, int flat_lazy)
 {
     extern __shared__ __align__(16) uint8_t s_mem[];
     __shared__ uint32_t s_hist[kHistSize];
@@ -423,6 +426,105 @@ k_lz_walk(const uint8_t* __restrict__ buf, uint32_t total, uint32_t dict, const 
                 if (ph > 0) mine[at] = held0;
                 if (ph > 1) mine[at + 1] = held1;
                 if (ph > 2) mine[at + 2] = held2;
+            }
+        } else if (kSmemLinks && flat_lazy && strategy != 3) {  // deflate_slow, deflate.c:1554-1674, as a flat state machine
+            // The nested form (search loop inside the token loop, compare loop inside the search loop) leaves 5 of 32 lanes
+            // active at level 6: a warp stays in the search loop until its longest chain is done (ncu, r2_l6walk).  Here a
+            // lane is in ONE of three states and every trip of the single loop advances it by one step -- one chain
+            // candidate (link + quick reject on the word a longer match must reach), four bytes of a comparison, or the
+            // parse decision between two searches -- so lanes with short chains move on to their next position instead
+            // of waiting.  Same decisions, same tokens as the nested form.
+            enum { kStNext = 0, kStCand = 1, kStCmp = 2, kStDone = 3 };
+            uint32_t prev_len = kMinMatch - 1, prev_dist = 0;
+            bool avail = false, started = false;
+            uint32_t st = kStNext;
+            uint32_t o = 0, acc = 0, best_len = kMinMatch - 1, best_dist = 0, qoff = 0, qmask = 0, hq = 0, maxlen = 0, nice_eff = 0;
+            uint32_t cmp_len = 0, d_next = 0;
+            int chain = 0;
+            while (st != kStDone) {
+                bool cand_done = false;
+                uint32_t len = 0;
+                if (st == kStCmp) {
+                    const uint32_t co = o - acc;
+                    const uint32_t y = lds32u(s_mem, o + cmp_len) ^ lds32u(s_mem, co + cmp_len);
+                    if (y) { len = cmp_len + ((uint32_t)(__ffs(y) - 1) >> 3); cand_done = true; }
+                    else { cmp_len += 4; len = cmp_len; cand_done = cmp_len >= maxlen; }
+                } else if (st == kStCand) {
+                    const uint32_t co = o - acc;
+                    d_next = links[(pos - win_beg) - acc];
+                    const uint32_t x = lds32u(s_mem, co + qoff) ^ hq;
+                    if ((x & qmask) == 0) {
+                        if (qoff == 0 && x != 0) { len = 3; cand_done = true; }     // first three agree, the fourth does not
+                        else {
+                            cmp_len = qoff == 0 ? 4u : 0u;
+                            if (cmp_len >= maxlen) { len = maxlen; cand_done = true; }
+                            else st = kStCmp;
+                        }
+                    } else {
+                        cand_done = true;                       // rejected: len 0 never beats best_len
+                    }
+                }
+                if (cand_done) {                                // this candidate is settled: keep it if longer, move down the chain
+                    len = min(len, maxlen);
+                    bool stop = false;
+                    if (len > best_len) {
+                        best_len = len; best_dist = acc;
+                        if (len >= nice_eff) stop = true;
+                        else {
+                            qoff = len >= 4 ? len - 3 : 0u;
+                            qmask = 0xffffffffu;
+                            hq = lds32u(s_mem, o + qoff);
+                        }
+                    }
+                    if (stop || d_next == 0) st = kStNext;
+                    else {
+                        acc += d_next;
+                        st = (--chain <= 0 || acc > max_dist) ? kStNext : kStCand;
+                    }
+                }
+                if (st == kStNext) {
+                    for (;;) {
+                        if (started) {                          // the position's result is in (best_len, best_dist): the lazy decision
+                            uint32_t flen = best_dist ? best_len : kMinMatch - 1;
+                            const uint32_t fdist = best_dist;
+                            if (flen <= 5 && (strategy == 1 || (flen == kMinMatch && fdist > kTooFar))) flen = kMinMatch - 1;   // Z_FILTERED, TOO_FAR
+                            if (prev_len >= kMinMatch && flen <= prev_len) {            // the pending match wins
+                                mine[ntok++] = (prev_dist << 16) | (prev_len - kMinMatch);
+                                pos += prev_len - 1;
+                                avail = false; prev_len = kMinMatch - 1;
+                            } else if (avail) {                                         // pending literal goes out, the new match waits
+                                mine[ntok++] = byte_at(pos - 1);
+                                prev_len = flen; prev_dist = fdist;
+                                pos++;
+                            } else {
+                                avail = true;
+                                prev_len = flen; prev_dist = fdist;
+                                pos++;
+                            }
+                        }
+                        started = true;
+                        if (!avail && pos >= s1) { st = kStDone; break; }
+                        if (avail && pos - 1 >= s1) { pos--; st = kStDone; break; }   // the pending position belongs to the next sub-unit
+                        best_len = kMinMatch - 1; best_dist = 0;
+                        if (pos < blk_end) {
+                            maxlen = blk_end - pos < kMaxMatch ? blk_end - pos : kMaxMatch;
+                            if (maxlen >= kMinMatch && prev_len < max_lazy) {
+                                if (prev_len > best_len) best_len = prev_len;           // only a longer match is of interest
+                                acc = links[pos - win_beg];
+                                if (acc != 0 && best_len < maxlen && acc <= max_dist) {
+                                    chain = prev_len >= good ? max(max_chain >> 2, 1) : max_chain;
+                                    o = sm_off + pos - win_beg;
+                                    nice_eff = min(nice, maxlen);
+                                    qoff = best_len >= 4 ? best_len - 3 : 0u;
+                                    qmask = best_len >= 3 ? 0xffffffffu : 0xffffffu;
+                                    hq = lds32u(s_mem, o + qoff);
+                                    st = kStCand;
+                                    break;
+                                }
+                            }
+                        }
+                    }
+                }
             }
         } else {                                                // deflate_slow, deflate.c:1554-1674
             uint32_t prev_len = kMinMatch - 1, prev_dist = 0;
@@ -695,35 +797,80 @@ __device__ int warp_make_code(TreeScratch* t, int nsym, int max_length, uint16_t
     return max_code;
 }
 
-// Run-length walk over code lengths (scan_tree, trees.c:707-748): tallies blfreq and keeps what it found as items
-// (code-length symbol | extra value << 5), so that sending the trees (send_tree, trees.c:752-797) is a loop over the items
-// instead of a second walk -- both run on one lane, and the walk is the longer of the two.
-__device__ void walk_lengths(TreeScratch* t, uint16_t* lens, int max_code)
+// Run-length coding of the code lengths (scan_tree, trees.c:707-748), by the whole warp.  The reference walks the
+// lengths once with a little state machine; its output for a maximal run of equal lengths depends on nothing but the
+// run itself (the length in front of a maximal run always differs from it, and the limits 7/4, 6/3, 138/3 are set from
+// the run's own value), so runs are coded independently: ballots find the run starts, then a lane per run counts its
+// items -- zeros: groups of up to 138 (17: 3..10, 18: 11..138, fewer than 3 as literals); others: the length itself
+// and "repeat 3..6" for the first group of up to 7 (fewer than 4 as literals), then groups of up to 6 (fewer than 3 as
+// literals) -- a warp prefix sum places them, and every lane writes its own.  Items (code-length symbol | extra value
+// << 5) are kept so that sending the trees (send_tree, trees.c:752-797) is a loop over them.  ~19 K of the kernel's
+// 30 K warp instructions per block were the one-lane form of this walk.
+__device__ __forceinline__ uint32_t rl_tail_items(uint32_t r, uint32_t minc) { return r == 0 ? 0u : r < minc ? r : 1u; }
+
+__device__ void warp_walk_lengths(TreeScratch* t, const uint16_t* lens, int max_code, uint32_t* blf /* 19 counters, shared */)
 {
-    int prevlen = -1, nextlen = lens[0], count = 0, maxc = 7, minc = 4;
-    int ni = t->nitems;
-    if (nextlen == 0) { maxc = 138; minc = 3; }
-    lens[max_code + 1] = 0xffff;
-    for (int n = 0; n <= max_code; n++) {
-        const int cur = nextlen; nextlen = lens[n + 1];
-        if (++count < maxc && cur == nextlen) continue;
-        if (count < minc) {
-            t->blfreq[cur] = (uint16_t)(t->blfreq[cur] + count);
-            do t->items[ni++] = (uint16_t)cur; while (--count);
-        } else if (cur != 0) {
-            if (cur != prevlen) { t->blfreq[cur]++; t->items[ni++] = (uint16_t)cur; count--; }
-            t->blfreq[16]++; t->items[ni++] = (uint16_t)(16 | ((count - 3) << 5));
-        } else if (count <= 10) {
-            t->blfreq[17]++; t->items[ni++] = (uint16_t)(17 | ((count - 3) << 5));
-        } else {
-            t->blfreq[18]++; t->items[ni++] = (uint16_t)(18 | ((count - 11) << 5));
-        }
-        count = 0; prevlen = cur;
-        if (nextlen == 0) { maxc = 138; minc = 3; }
-        else if (cur == nextlen) { maxc = 6; minc = 3; }
-        else { maxc = 7; minc = 4; }
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint16_t* starts = reinterpret_cast<uint16_t*>(t->key);     // run starts (the sort keys are idle between two codes)
+    int nruns = 0;
+    for (int base = 0; base <= max_code; base += 32) {
+        const int s = base + lane;
+        const bool st = s <= max_code && (s == 0 || lens[s] != lens[s - 1]);
+        const uint32_t m = __ballot_sync(kFullMask, st);
+        if (st) starts[nruns + __popc(m & lt)] = (uint16_t)s;
+        nruns += __popc(m);
     }
-    t->nitems = ni;
+    __syncwarp();
+    int ni = t->nitems;
+    for (int r0 = 0; r0 < nruns; r0 += 32) {
+        const int r = r0 + lane;
+        uint32_t v = 0, L = 0, n_items = 0, first = 0;
+        if (r < nruns) {
+            const uint32_t a = starts[r], b = r + 1 < nruns ? starts[r + 1] : (uint32_t)max_code + 1u;
+            v = lens[a]; L = b - a;
+            if (v == 0) n_items = L / 138u + rl_tail_items(L % 138u, 3u);
+            else {
+                first = L < 7u ? L : 7u;
+                const uint32_t rest = L - first;
+                n_items = (first < 4u ? first : 2u) + rest / 6u + rl_tail_items(rest % 6u, 3u);
+            }
+        }
+        uint32_t x = n_items;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(kFullMask, x, k); if (lane >= k) x += y; }
+        uint16_t* out = t->items + ni + (x - n_items);
+        if (n_items) {
+            uint32_t o = 0;
+            if (v == 0) {
+                uint32_t left = L;
+                while (left) {
+                    const uint32_t g = left < 138u ? left : 138u;
+                    if (g < 3u) { for (uint32_t k = 0; k < g; k++) out[o++] = 0; atomicAdd(&blf[0], g); }
+                    else if (g <= 10u) { out[o++] = (uint16_t)(17u | ((g - 3u) << 5)); atomicAdd(&blf[17], 1u); }
+                    else { out[o++] = (uint16_t)(18u | ((g - 11u) << 5)); atomicAdd(&blf[18], 1u); }
+                    left -= g;
+                }
+            } else {
+                uint32_t lits = 0, reps = 0;
+                if (first < 4u) { for (uint32_t k = 0; k < first; k++) out[o++] = (uint16_t)v; lits += first; }
+                else { out[o++] = (uint16_t)v; out[o++] = (uint16_t)(16u | ((first - 4u) << 5)); lits++; reps++; }   // the length, then repeat first - 1 times
+                uint32_t left = L - first;
+                while (left) {
+                    const uint32_t g = left < 6u ? left : 6u;
+                    if (g < 3u) { for (uint32_t k = 0; k < g; k++) out[o++] = (uint16_t)v; lits += g; }
+                    else { out[o++] = (uint16_t)(16u | ((g - 3u) << 5)); reps++; }
+                    left -= g;
+                }
+                atomicAdd(&blf[v], lits);
+                if (reps) atomicAdd(&blf[16], reps);
+            }
+        }
+        ni += (int)__shfl_sync(kFullMask, x, 31);
+    }
+    __syncwarp();
+    if (lane == 0) t->nitems = ni;
+    __syncwarp();
 }
 
 __device__ void send_items(const TreeScratch* t, BitSink* sink)
@@ -789,13 +936,13 @@ k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict
     for (int k = 16; k; k >>= 1) { dyn += __shfl_xor_sync(kFullMask, dyn, k); fix += __shfl_xor_sync(kFullMask, fix, k); }
 
     // ---- code-length code and header ----
-    if (lane == 0) {
-        for (int i = 0; i < 19; i++) t->blfreq[i] = 0;
-        t->nitems = 0;
-        walk_lengths(t, t->llen, lmax);
-        walk_lengths(t, t->dlen, dmax);
-        for (int i = 0; i < 19; i++) t->freq[i] = t->blfreq[i];
-    }
+    uint32_t* blf = t->wint;                                    // 19 counters (the internal-node weights are idle here)
+    if (lane < 19) blf[lane] = 0;
+    if (lane == 0) t->nitems = 0;
+    __syncwarp();
+    warp_walk_lengths(t, t->llen, lmax, blf);
+    warp_walk_lengths(t, t->dlen, dmax, blf);
+    if (lane < 19) { t->blfreq[lane] = (uint16_t)blf[lane]; t->freq[lane] = blf[lane]; }
     __syncwarp();
     warp_make_code(t, 19, 7, t->bllen, t->blcode);
     uint32_t type = 0;
@@ -821,7 +968,6 @@ k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict
             sink.finish();
             hdr_bits = sink.total;
         }
-        t->llen[lmax + 1] = 0; t->dlen[dmax + 1] = 0;              // drop the run-length sentinels
         blk[b] = BlockMeta{in_len, type, body, hdr_bits};
     }
     type = __shfl_sync(kFullMask, type, 0);
@@ -846,8 +992,10 @@ k_huff_build(uint64_t n, BlockMeta* __restrict__ blk, const uint32_t* __restrict
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t stored_chunk_bytes(uint32_t len) { return (uint64_t)len + 5ull * ((len + 65534u) / 65535u); }
 
+// bits: low byte = bits pending in front of chunk 0 (deflatePrime, or what a Z_PARTIAL_FLUSH left over), bit 8 = the last
+// chunk ends with the ten bits of _tr_align (trees.c:892) instead of the byte-aligning marker and keeps its last bits.
 __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chunks, const BlockMeta* __restrict__ blk,
-                       int last_is_final, int force_stored, int force_mark, const ChunkDesc* __restrict__ cd)
+                       int last_is_final, int force_stored, int force_mark, const ChunkDesc* __restrict__ cd, uint32_t bitmode)
 {
     const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
@@ -857,11 +1005,13 @@ __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chu
     cm.offset = 0;
     const bool final_chunk = cd ? cd[c].last != 0 : (last_is_final && c == nchunks - 1);
     const bool mark = !cd && force_mark && !last_is_final && c == nchunks - 1;   // Z_SYNC_FLUSH marker wanted regardless
+    const uint32_t prime = (!cd && c == 0) ? (bitmode & 7u) : 0u;
+    const bool partial = !cd && (bitmode & 0x100u) && !last_is_final && c == nchunks - 1;
     uint64_t bytes;
     if (force_stored) {
         cm.stored = 1; bytes = stored_chunk_bytes(clen) + (mark ? 5 : 0);
     } else {
-        uint64_t bits = 0;
+        uint64_t bits = prime;
         bool ends_stored = false;
         for (uint32_t j = 0; j < cm.nblocks; j++) {
             const BlockMeta bm = blk[c * kBlocksPerChunk + j];
@@ -871,10 +1021,11 @@ __global__ void k_plan(uint64_t nchunks, uint64_t n, ChunkMeta* __restrict__ chu
             }
             else { bits += 3 + bm.body_bits; ends_stored = false; }
         }
-        if (final_chunk || (ends_stored && !mark)) bytes = (bits + 7) >> 3;
+        if (partial) bytes = (bits + 10) >> 3;                  // empty static block; the last (bits + 10) & 7 bits stay pending
+        else if (final_chunk || (ends_stored && !mark)) bytes = (bits + 7) >> 3;
         else bytes = ((bits + 3 + 7) >> 3) + 4;                 // empty stored block: 000, pad, 00 00 FF FF
         const uint64_t sb = stored_chunk_bytes(clen) + (mark ? 5 : 0);
-        cm.stored = sb <= bytes ? 1u : 0u;
+        cm.stored = (sb <= bytes && !prime && !partial) ? 1u : 0u;   // the all-stored shortcut writes whole bytes only
         if (cm.stored) bytes = sb;
     }
     cm.bytes = bytes;
@@ -1075,7 +1226,7 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
             const uint32_t* __restrict__ blk_codes, const uint32_t* __restrict__ blk_hdr,
             const ChunkMeta* __restrict__ chunks, uint8_t* __restrict__ out, uint64_t cap, int last_is_final,
             int force_mark, uint32_t* __restrict__ err, const ChunkDesc* __restrict__ cd, const JobDesc* __restrict__ jobs,
-            JobResult* __restrict__ jres)
+            JobResult* __restrict__ jres, uint32_t bitmode, uint32_t prime_val, uint32_t* __restrict__ tail_out)
 {
     __shared__ uint32_t s_stage[2][kStageWords];
     __shared__ uint32_t s_sums[kPackThreads / 32];
@@ -1083,7 +1234,8 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
     const uint64_t c = blockIdx.x;
     const uint64_t nchunks = gridDim.x;
     const ChunkMeta cm = chunks[c];
-    uint64_t cbeg; uint32_t clen; bool final_chunk, mark;
+    uint64_t cbeg; uint32_t clen; bool final_chunk, mark, partial = false;
+    uint32_t prime = 0;
     if (cd) {                                                   // job mode: the chunk's place and role come from the table
         const ChunkDesc d = cd[c];
         if (jres[d.job].total > jobs[d.job].dst_cap) return;    // the job does not fit its slot: Z_BUF_ERROR from the total
@@ -1095,6 +1247,8 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
         clen = (uint32_t)min((uint64_t)kChunk, n - cbeg);
         final_chunk = last_is_final && c == nchunks - 1;
         mark = force_mark && !last_is_final && c == nchunks - 1;
+        prime = c == 0 ? (bitmode & 7u) : 0u;
+        partial = (bitmode & 0x100u) && !last_is_final && c == nchunks - 1;
     }
     uint8_t* dst = out + cm.offset;
     const uint8_t* in = src + cbeg;
@@ -1118,7 +1272,9 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
 
     for (int i = threadIdx.x; i < 2 * kStageWords; i += kPackThreads) (&s_stage[0][0])[i] = 0;
     __syncthreads();
-    Packer pk{&s_stage[0][0], 0, s_sums, dst, 0, 0, 1};
+    if (prime && threadIdx.x == 0) s_stage[0][0] = prime_val & ((1u << prime) - 1u);   // bits that precede this shard's first block
+    __syncthreads();
+    Packer pk{&s_stage[0][0], 0, s_sums, dst, 0, prime, 1};
     bool ends_stored = false;
     for (uint32_t j = 0; j < cm.nblocks; j++) {
         const uint64_t b = c * kBlocksPerChunk + j;
@@ -1190,7 +1346,16 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
             pk.round(v0, n0, v1, n1);
         }
     }
-    // end of chunk: final -> pad; otherwise empty stored block unless already byte-aligned by a stored block
+    // end of chunk: partial flush -> empty static block, bits left as they fall; final -> pad; otherwise empty stored
+    // block unless already byte-aligned by a stored block
+    if (partial) {
+        pk.round(threadIdx.x == 0 ? 2u : 0u, threadIdx.x == 0 ? 10u : 0u);      // 010 (static, not final) + the 7-bit end-of-block code
+        if (threadIdx.x == 0) {
+            tail_out[0] = pk.carry_bits | ((pk.stage[pk.par * kStageWords] & ((1u << pk.carry_bits) - 1u)) << 8);
+            if (pk.bytepos != cm.bytes) atomicAdd(err, 1u);
+        }
+        return;
+    }
     if (final_chunk || (ends_stored && !mark)) {
         const uint32_t pad = (8 - (pk.carry_bits & 7)) & 7;
         pk.round(0, threadIdx.x == 0 ? pad : 0);
@@ -1269,6 +1434,12 @@ static int env_int(const char* name, int dflt)
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
+// The flat state machine of the lazy walk pays where chains are long (levels 7..9: up to 1.19 x); below that its longer
+// trip costs more than the idle lanes of the nested loops (level 6: 0.85 .. 0.96 x, level 4: 0.65 x; profiles/r2_sweeps.md).
+static int walk_flat_lazy(int chain) { static const int force = env_int("ZB200_LAZY_FLAT", -1); return force >= 0 ? force : (chain >= 256 ? 1 : 0); }
+// exact intra-step links (MATCH.ANY, 8.4 ms per GiB) for the levels that search long chains; levels 1..6 take the relaxed
+// links (3.1 ms per GiB, ~0.1 % larger output)
+static bool link_exact(int level) { static const int force = env_int("ZB200_LINK_EXACT", -1); return force >= 0 ? force != 0 : level >= 7; }
 static bool walk_persistent() { static const bool on = env_int("ZB200_WALK_PERSIST", 1) != 0; return on; }
 static unsigned walk_grid(uint64_t nblocks, bool lazy_shape)
 {
@@ -1283,7 +1454,7 @@ static uint64_t walk_slots(uint64_t nblocks) { return walk_persistent() ? std::m
 static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint64_t n, uint8_t* d_out, uint64_t cap,
                                const DeflateParams& P, int last_is_final, int force_mark, const uint64_t* d_start,
                                uint64_t start_add, uint64_t* d_end, uint32_t* d_err, cudaStream_t s,
-                               cudaEvent_t prev_scanned = nullptr, cudaEvent_t scanned = nullptr)
+                               cudaEvent_t prev_scanned = nullptr, cudaEvent_t scanned = nullptr, uint32_t bitmode = 0, uint32_t prime_val = 0)
 {
     const LevelCfg& cfg = P.cfg;
     const uint64_t total = dict + n;
@@ -1314,7 +1485,7 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
         const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
         if (cfg.chain != 0 && P.strategy != 3) {                // Z_RLE needs no chains
             // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
-            if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
+            if (link_exact(P.level)) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
             else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
         }
         const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
@@ -1323,22 +1494,22 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
         if (lazy_shape)
             ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), wgrid, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_buf, (uint32_t)total,
                       (uint32_t)dict, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy, P.max_dist, (const ChunkDesc*)nullptr, (uint32_t)nblocks, d_next);
+                      (uint32_t)cfg.good, P.strategy, P.max_dist, (const ChunkDesc*)nullptr, (uint32_t)nblocks, d_next, walk_flat_lazy((int)cfg.chain));
         else
             ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), wgrid, kWalkThreadsFast, kWalkSmem, s, d_buf, (uint32_t)total,
                       (uint32_t)dict, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy, P.max_dist, (const ChunkDesc*)nullptr, (uint32_t)nblocks, d_next);
+                      (uint32_t)cfg.good, P.strategy, P.max_dist, (const ChunkDesc*)nullptr, (uint32_t)nblocks, d_next, walk_flat_lazy((int)cfg.chain));
         ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, n, d_blk, d_hist,
                   d_codes, d_hdr, P.strategy == 4 ? 1 : 0, (const ChunkDesc*)nullptr, (uint64_t)0);
     }
-    ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0, force_mark, (const ChunkDesc*)nullptr);
+    ZB_LAUNCH(k_plan, (unsigned)((nchunks + 255) / 256), 256, 0, s, nchunks, n, d_chunks, d_blk, last_is_final, cfg.kind == 0 ? 1 : 0, force_mark, (const ChunkDesc*)nullptr, bitmode);
     // Slabs alternate between two streams; only the running output offset links them: this slab's offsets need the
     // end of the previous slab, everything before this point (link, walk, codes, plan) does not.
     if (prev_scanned) ZB_CUDA(cudaStreamWaitEvent(s, prev_scanned, 0));
     ZB_LAUNCH(k_scan, 1, 1024, 0, s, nchunks, d_chunks, d_start, start_add, d_end);
     if (scanned) ZB_CUDA(cudaEventRecord(scanned, s));
     ZB_LAUNCH(k_huff_pack, (unsigned)nchunks, kPackThreads, 0, s, d_src, n, d_tok, d_ntok, d_blk, d_codes, d_hdr, d_chunks, d_out, cap,
-              last_is_final, force_mark, d_err, (const ChunkDesc*)nullptr, (const JobDesc*)nullptr, (JobResult*)nullptr);
+              last_is_final, force_mark, d_err, (const ChunkDesc*)nullptr, (const JobDesc*)nullptr, (JobResult*)nullptr, bitmode, prime_val, d_err + 1);
     ZB_CHECK_LAUNCH();
     return 0;
 }
@@ -1375,7 +1546,7 @@ static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uin
         d_ntok = c->ws[10].as<uint32_t>();
         uint32_t* d_next = walk_persistent() ? d_ntok + nblocks : nullptr;   // the walk kernel's block counter
         if (cfg.chain != 0 && P.strategy != 3) {
-            if (P.level >= 4) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
+            if (link_exact(P.level)) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
             else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
         }
         const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
@@ -1384,20 +1555,20 @@ static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uin
         if (lazy_shape)
             ZB_LAUNCH((k_lz_walk<kWalkThreadsLazy, true>), wgrid, kWalkThreadsLazy, kWalkSmem + kWalkLinkSmem, s, d_base, (uint32_t)span,
                       0u, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy, P.max_dist, d_cd, (uint32_t)nblocks, d_next);
+                      (uint32_t)cfg.good, P.strategy, P.max_dist, d_cd, (uint32_t)nblocks, d_next, walk_flat_lazy((int)cfg.chain));
         else
             ZB_LAUNCH((k_lz_walk<kWalkThreadsFast, false>), wgrid, kWalkThreadsFast, kWalkSmem, s, d_base, (uint32_t)span,
                       0u, d_dist, d_tmp, d_tok, d_ntok, d_hist, cfg.kind, (int)cfg.chain, (uint32_t)cfg.nice, (uint32_t)cfg.lazy,
-                      (uint32_t)cfg.good, P.strategy, P.max_dist, d_cd, (uint32_t)nblocks, d_next);
+                      (uint32_t)cfg.good, P.strategy, P.max_dist, d_cd, (uint32_t)nblocks, d_next, walk_flat_lazy((int)cfg.chain));
         ZB_LAUNCH(k_huff_build, (unsigned)((nblocks + kCodeWarps - 1) / kCodeWarps), kCodeWarps * 32, 0, s, span, d_blk, d_hist,
                   d_codes, d_hdr, P.strategy == 4 ? 1 : 0, d_cd, nblocks);
     }
     if (nchunks)
-        ZB_LAUNCH(k_plan, (nchunks + 255) / 256, 256, 0, s, (uint64_t)nchunks, span, d_chunks, d_blk, 1, cfg.kind == 0 ? 1 : 0, 0, d_cd);
+        ZB_LAUNCH(k_plan, (nchunks + 255) / 256, 256, 0, s, (uint64_t)nchunks, span, d_chunks, d_blk, 1, cfg.kind == 0 ? 1 : 0, 0, d_cd, 0u);
     ZB_LAUNCH(k_scan_jobs, 1, 1024, 0, s, nchunks, d_chunks, d_cd, d_jobs, njobs, hdr_len, trailer_len, d_jres);
     if (nchunks)
         ZB_LAUNCH(k_huff_pack, nchunks, kPackThreads, 0, s, d_base, span, d_tok, d_ntok, d_blk, d_codes, d_hdr, d_chunks, d_out, (uint64_t)0,
-                  1, 0, (uint32_t*)nullptr, d_cd, d_jobs, d_jres);
+                  1, 0, (uint32_t*)nullptr, d_cd, d_jobs, d_jres, 0u, 0u, (uint32_t*)nullptr);
     if ((rc = checksum_jobs_launch(c, d_base, d_cd, nchunks, d_jobs, njobs, d_crc, d_adler, s)) != 0) return rc;
     ZB_LAUNCH(k_frame_jobs, (njobs + 127) / 128, 128, 0, s, d_out, d_jobs, njobs, d_crc, d_adler, P.level, P.wrap, P.strategy, d_jres);
     ZB_CHECK_LAUNCH();
@@ -1520,7 +1691,7 @@ static void shard_release(ShardJob* J)
 }
 
 static int shard_begin(ShardJob* J, const void* src, size_t src_len, const void* dict, size_t dict_len, void* dst, size_t cap,
-                       int level, int wrap, int flags, void* stream)
+                       int level, int wrap, int flags, void* stream, uint32_t prime_bits = 0, uint32_t prime_val = 0, bool partial_end = false)
 {
     int rc = ensure_init();
     if (rc) return rc;
@@ -1535,6 +1706,10 @@ static int shard_begin(ShardJob* J, const void* src, size_t src_len, const void*
     const int last_is_final = (flags & ZB200_DEFLATE_NOT_LAST) ? 0 : 1;
     const uint64_t hdr_len = (flags & ZB200_DEFLATE_NO_HEADER) ? 0 : wrap == ZB200_WRAP_ZLIB ? 2 : wrap == ZB200_WRAP_GZIP ? 10 : 0;
     const uint64_t n = src_len;
+    if ((prime_bits || partial_end) && (P.cfg.kind == 0 || n == 0 || prime_bits > 7 || hdr_len)) {
+        set_error("zb200: pending bits need a raw shard with input at level 1..9");   // the shim handles the other cases on the host
+        return ZB_STREAM_ERROR;
+    }
     std::vector<uint64_t>& cut = J->cut;
     plan_slabs(n, (n != 0 && classify(src) != kDevice) || classify(dst) != kDevice, cut);
     const uint64_t nslabs = cut.size() - 1;
@@ -1604,7 +1779,7 @@ static int shard_begin(ShardJob* J, const void* src, size_t src_len, const void*
         uint64_t* h_res = (uint64_t*)c->pinned;                 // [0..3] result words, [4..] slab ends
         uint64_t* h_pos = h_res + 4;
         J->h_res = h_res; J->h_pos = h_pos;
-        if ((e = cudaMemsetAsync(d_err, 0, 4, s)) != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }
+        if ((e = cudaMemsetAsync(d_err, 0, 8, s)) != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); rc = ZB_STREAM_ERROR; break; }   // error count and pending-bits word
         if (c2) {                                               // the second stream starts where the caller's stream is now
             cudaEventRecord(ev_start, s);
             cudaStreamWaitEvent(c2->own_stream, ev_start, 0);
@@ -1636,7 +1811,8 @@ static int shard_begin(ShardJob* J, const void* src, size_t src_len, const void*
             const bool last = i == nslabs - 1;
             rc = deflate_slab_launch(cl, d_src + off - dlen, dlen, len, d_out, cap, P, last && last_is_final, last ? force_mark : 0,
                                      i ? d_pos + i - 1 : nullptr, i ? 0 : hdr_len, d_pos + i, d_err, sl,
-                                     i ? ev_scan[i - 1] : nullptr, last ? nullptr : ev_scan[i]);
+                                     i ? ev_scan[i - 1] : nullptr, last ? nullptr : ev_scan[i],
+                                     (i == 0 ? prime_bits : 0u) | ((last && partial_end) ? 0x100u : 0u), i == 0 ? prime_val : 0u);
             if (rc) break;
             if (dst_on_host && !last) {
                 e = cudaMemcpyAsync(h_pos + i, d_pos + i, 8, cudaMemcpyDeviceToHost, sl);
@@ -1660,7 +1836,7 @@ static int shard_begin(ShardJob* J, const void* src, size_t src_len, const void*
     return rc;
 }
 
-static int shard_end(ShardJob* J, size_t* dst_len, uint32_t* crc, uint32_t* adler)
+static int shard_end(ShardJob* J, size_t* dst_len, uint32_t* crc, uint32_t* adler, uint32_t* tail = nullptr)
 {
     int rc = 0;
     Ctx* c = J->c;
@@ -1698,6 +1874,7 @@ static int shard_end(ShardJob* J, size_t* dst_len, uint32_t* crc, uint32_t* adle
         const uint32_t* r32 = (const uint32_t*)h_res;
         if (crc) *crc = r32[2];
         if (adler) *adler = r32[3];
+        if (tail) *tail = r32[5];                               // bits a partial flush left pending: count | value << 8
         if (r32[4] != 0) { cudaStreamSynchronize(s_out); set_error("internal error: %u chunks packed to a size other than planned", r32[4]); rc = ZB_STREAM_ERROR; break; }
         *dst_len = (size_t)total;
         if (total > cap) {
@@ -1727,6 +1904,22 @@ ZB_API int zb200_deflate_shard(const void* src, size_t src_len, const void* dict
     int rc = shard_begin(&J, src, src_len, dict, dict_len, dst, *dst_len, level, wrap, flags, stream);
     if (rc) return rc;
     return shard_end(&J, dst_len, crc, adler);
+}
+
+// deflatePrime / Z_PARTIAL_FLUSH (deflate.c:404-414, trees.c:892): a raw shard that starts with `prime_bits` (< 8) pending
+// bits and, when partial_end is set, ends with the ten bits of an empty static block and hands back the bits of its last,
+// incomplete byte (*tail = count | value << 8) instead of aligning.  Hidden: the streaming shim (zapi_stream.c) is the caller.
+extern "C" int zb200i_deflate_shard_bits(const void* src, size_t src_len, const void* dict, size_t dict_len, void* dst, size_t* dst_len,
+                                         int level, int flags, uint32_t prime_bits, uint32_t prime_val, int partial_end,
+                                         uint32_t* tail, uint32_t* crc, uint32_t* adler)
+{
+    if (!dst_len) return ZB_STREAM_ERROR;
+    ShardJob J;
+    int rc = shard_begin(&J, src, src_len, dict, dict_len, dst, *dst_len, level, ZB200_WRAP_RAW,
+                         flags | ZB200_DEFLATE_NO_HEADER | ZB200_DEFLATE_NO_TRAILER | (partial_end ? ZB200_DEFLATE_NOT_LAST : 0), nullptr,
+                         prime_bits, prime_val, partial_end != 0);
+    if (rc) return rc;
+    return shard_end(&J, dst_len, crc, adler, tail);
 }
 
 // The two halves as calls of their own (see ShardJob): *job receives a handle that zb200_deflate_shard_end consumes.

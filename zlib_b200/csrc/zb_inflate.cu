@@ -1083,16 +1083,77 @@ __device__ void seg_decode(const uint8_t* in, uint64_t in_len, const SegDesc sd,
     if (lane == 0) { res->out_len = produced; res->end_bit = b.used; res->status = status; res->final = last; res->arrive = arrive; res->pad = 0; }
 }
 
+// Emit mode decodes segments [j_lo, j_hi) of the nseg the stream has (the one-stream decoder runs in a few phases so that
+// the output of one phase travels to the host while the next is decoded); count mode takes all candidates at once.
 template <bool kEmit>
 __global__ void __launch_bounds__(kInfWarps * 32)
 k_inflate_segments(const uint8_t* __restrict__ in, uint64_t in_len, const SegDesc* __restrict__ segs, uint32_t nseg,
-                   uint16_t* __restrict__ sym, SegResult* __restrict__ res, const uint64_t* __restrict__ cand)
+                   uint16_t* __restrict__ sym, SegResult* __restrict__ res, const uint64_t* __restrict__ cand,
+                   uint32_t j_lo, uint32_t j_hi)
 {
     __shared__ WarpTables s_tab[kInfWarps];
-    const uint32_t j = blockIdx.x * kInfWarps + (threadIdx.x >> 5);
-    if (j >= nseg) return;
+    const uint32_t j = j_lo + blockIdx.x * kInfWarps + (threadIdx.x >> 5);
+    if (j >= j_hi) return;
     if (kEmit) seg_decode<true>(in, in_len, segs[j], j == 0, j == nseg - 1, sym, &s_tab[threadIdx.x >> 5], &res[j], nullptr, 0, 0);
     else seg_decode<false>(in, in_len, SegDesc{cand[j], 0, 0, 0}, j == 0, false, nullptr, &s_tab[threadIdx.x >> 5], &res[j], cand, nseg, j);
+}
+
+// Tails in parallel.  The last 32 KiB of a segment only depend on the segment in front of it where they still hold
+// window symbols -- and after 96 KiB and more of its own output a tail rarely does (a copy chain has to carry a symbol
+// all the way).  So: round 0 turns every tail WITHOUT window symbols into bytes at once; round r >= 1 resolves the tails
+// whose predecessor was finished in an earlier round.  done[j] = (round it was finished in) + 1.  Whatever is still open
+// after the rounds (a chain of dependent tails longer than the number of rounds) is left to the sequential walk below,
+// which starts at the first open segment.  One CTA per segment.
+constexpr int kTailRounds = 4;
+
+__global__ void __launch_bounds__(256)
+k_tails_round(const uint16_t* __restrict__ sym, uint8_t* __restrict__ out, const SegDesc* __restrict__ segs, uint32_t j_lo,
+              uint32_t* __restrict__ done, uint32_t round, uint32_t* __restrict__ err)
+{
+    __shared__ uint32_t s_any;
+    const uint32_t j = j_lo + blockIdx.x;
+    const SegDesc sd = segs[j];
+    const uint64_t t = min(sd.out_len, (uint64_t)kWindow32), lo = sd.out_off + sd.out_len - t;
+    if (round == 0) {
+        if (threadIdx.x == 0) s_any = 0;
+        __syncthreads();
+        uint32_t any = 0;
+        for (uint64_t i = threadIdx.x; i < t; i += 256) any |= sym[lo + i] & 0x8000u;
+        if (any) s_any = 1;                                     // benign race: every writer stores 1
+        __syncthreads();
+        if (s_any) { if (threadIdx.x == 0) done[j] = 0; return; }
+        for (uint64_t i = threadIdx.x; i < t; i += 256) out[lo + i] = (uint8_t)sym[lo + i];
+        if (threadIdx.x == 0) done[j] = 1;
+        return;
+    }
+    if (done[j] != 0) return;
+    if (j != 0) { const uint32_t d = done[j - 1]; if (d == 0 || d > round) return; }   // the window must be final since an EARLIER launch
+    const int64_t wbase = (int64_t)sd.out_off - (int64_t)kWindow32;
+    uint32_t bad = 0;
+    for (uint64_t i = threadIdx.x; i < t; i += 256) {
+        uint32_t v = sym[lo + i];
+        if (v & 0x8000u) {
+            const int64_t q = wbase + (int64_t)(v & 0x7fffu);
+            if (q < 0) { bad++; v = 0; }
+            else v = __ldcg(out + q);
+        }
+        out[lo + i] = (uint8_t)v;
+    }
+    if (bad) atomicAdd(err, bad);
+    if (threadIdx.x == 0) done[j] = round + 1;
+}
+
+// first_open[0] = the first segment of [j_lo, j_hi) whose tail is still open, or 0xffffffff
+__global__ void k_tails_first_open(const uint32_t* __restrict__ done, uint32_t j_lo, uint32_t j_hi, uint32_t* __restrict__ first_open)
+{
+    __shared__ uint32_t s_min;
+    if (threadIdx.x == 0) s_min = 0xffffffffu;
+    __syncthreads();
+    uint32_t m = 0xffffffffu;
+    for (uint32_t j = j_lo + threadIdx.x; j < j_hi; j += blockDim.x) if (done[j] == 0) { m = j; break; }
+    if (m != 0xffffffffu) atomicMin(&s_min, m);
+    __syncthreads();
+    if (threadIdx.x == 0) first_open[0] = s_min;
 }
 
 // The sequential part: segment by segment, the last 32 KiB of symbols become bytes; a window symbol reads the 32 KiB in
@@ -1110,8 +1171,12 @@ struct TailWork { uint64_t grp[2]; uint4 v[2]; };               // up to two gro
 
 __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads)
 k_resolve_tails(const uint16_t* __restrict__ sym, uint8_t* __restrict__ out, const SegDesc* __restrict__ segs, uint32_t j0, uint32_t nseg,
-                uint32_t* __restrict__ err)
+                uint32_t* __restrict__ err, const uint32_t* __restrict__ first_open, uint32_t* __restrict__ done)
 {
+    if (first_open) {                                           // after the parallel rounds: only what they left open (usually nothing)
+        j0 = first_open[0];
+        if (j0 >= nseg) return;                                 // every CTA of the cluster reads the same word and leaves together
+    }
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t r = cluster.block_rank();
@@ -1196,6 +1261,7 @@ k_resolve_tails(const uint16_t* __restrict__ sym, uint8_t* __restrict__ out, con
             }
         }
         cluster.sync();
+        if (done && r == 0 && threadIdx.x == 0) done[j] = 1;     // final since this launch: the next phase's rounds may build on it
     }
     if (bad) atomicAdd(err, bad);
 }
@@ -1282,6 +1348,99 @@ k_find_blocks_check(const uint8_t* __restrict__ in, uint64_t in_len, const uint6
     }
 }
 
+// Second half of the one-stream decoder: emit (16-bit symbols), tails, rest, trailer check -- for a list of segments whose
+// sizes are known (counted) or assumed (speculative: every segment but the last is exactly out_len bytes, the last one at
+// most out_len; used for streams that look like this library's own, see inflate_single_parallel).  In speculative mode
+// `final_end` and the total are learnt from the last segment.  Returns 0 = decoded, 1 = not taken, negative = CUDA error.
+static int emit_segments(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t* d_dst, const std::vector<SegDesc>& segs, uint64_t total,
+                         uint64_t final_end, bool speculative, int wrap, cudaStream_t s, void* h_dst, uint64_t* total_out,
+                         uint64_t* used_out, uint32_t* check_out)
+{
+    const uint32_t nseg = (uint32_t)segs.size();
+    const uint64_t sym_len = segs.back().out_off + segs.back().out_len;
+    const uint64_t trailer_len = wrap == ZB200_WRAP_ZLIB ? 4 : wrap == ZB200_WRAP_GZIP ? 8 : 0;
+    int rc;
+    if ((rc = c->small.ensure(256)) != 0) return rc;
+    if ((rc = c->ws[2].ensure((size_t)nseg * sizeof(SegDesc))) != 0) return rc;
+    if ((rc = c->ws[3].ensure((size_t)nseg * sizeof(SegResult))) != 0) return rc;
+    if ((rc = c->ws[4].ensure((size_t)sym_len * 2 + 64)) != 0) return rc;
+    if ((rc = c->ws[6].ensure((size_t)nseg * 4 + 64)) != 0) return rc;
+    uint32_t* d_err = c->small.as<uint32_t>() + 17;
+    uint32_t* d_first_open = c->small.as<uint32_t>() + 18;
+    SegDesc* d_segs = c->ws[2].as<SegDesc>();
+    SegResult* d_res = c->ws[3].as<SegResult>();
+    uint16_t* d_sym = c->ws[4].as<uint16_t>();
+    uint32_t* d_done = c->ws[6].as<uint32_t>();
+    ZB_CUDA(cudaMemsetAsync(d_err, 0, 4, s));
+    ZB_CUDA(cudaMemcpyAsync(d_segs, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
+    // A few phases, each a contiguous range of segments: emit, tails (parallel rounds, then the sequential walk for what they
+    // left open), rest -- and, with a pinned host destination, the phase's output on its way while the next phase is decoded.
+    const uint32_t nphase = (h_dst && nseg >= 4096) ? 2 : 1;
+    if (h_dst && (rc = c->ensure_aux(nphase + 2)) != 0) return rc;
+    for (uint32_t k = 0; k < nphase; k++) {
+        const uint32_t j0 = (uint32_t)((uint64_t)nseg * k / nphase), j1 = (uint32_t)((uint64_t)nseg * (k + 1) / nphase);
+        if (j1 == j0) continue;
+        ZB_LAUNCH((k_inflate_segments<true>), (j1 - j0 + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s, d_src, len, d_segs, nseg, d_sym, d_res,
+                  (const uint64_t*)nullptr, j0, j1);
+        for (int r = 0; r < kTailRounds; r++)
+            ZB_LAUNCH(k_tails_round, j1 - j0, 256, 0, s, d_sym, d_dst, d_segs, j0, d_done, (uint32_t)r, d_err);
+        ZB_LAUNCH(k_tails_first_open, 1, 1024, 0, s, d_done, j0, j1, d_first_open);
+        ZB_LAUNCH(k_resolve_tails, kTailCtas, kTailThreads, 0, s, d_sym, d_dst, d_segs, j0, j1, d_err, d_first_open, d_done);
+        ZB_LAUNCH(k_resolve_rest, j1 - j0, 256, 0, s, d_sym, d_dst, d_segs + j0, d_err);
+        if (h_dst && !(speculative && k == nphase - 1)) {       // (the last speculative phase is copied once its true length is known)
+            const uint64_t a = segs[j0].out_off, b = segs[j1 - 1].out_off + segs[j1 - 1].out_len;
+            ZB_CUDA(cudaEventRecord(c->evs[k], s));
+            ZB_CUDA(cudaStreamWaitEvent(c->aux[1], c->evs[k], 0));
+            if (b > a) ZB_CUDA(cudaMemcpyAsync((uint8_t*)h_dst + a, d_dst + a, b - a, cudaMemcpyDeviceToHost, c->aux[1]));
+        }
+    }
+    ZB_CHECK_LAUNCH();
+    std::vector<SegResult> res(nseg);
+    uint32_t nerr = 0;
+    ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nseg * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaMemcpyAsync(&nerr, d_err, 4, cudaMemcpyDeviceToHost, s));
+    ZB_CUDA(cudaStreamSynchronize(s));
+    bool ok = nerr == 0;
+    for (uint32_t j = 0; j < nseg && ok; j++) {
+        if (res[j].status != 0) ok = false;
+        else if (speculative && j == nseg - 1) ok = res[j].final != 0 && res[j].out_len <= segs[j].out_len;
+        else ok = res[j].out_len == segs[j].out_len;
+    }
+    if (ok && speculative) {
+        total = segs.back().out_off + res[nseg - 1].out_len;
+        final_end = res[nseg - 1].end_bit;
+        if (h_dst) {                                            // the last phase, now that its length is known
+            const uint32_t j0 = (uint32_t)((uint64_t)nseg * (nphase - 1) / nphase);
+            const uint64_t a = segs[j0].out_off;
+            if (total > a) ZB_CUDA(cudaMemcpyAsync((uint8_t*)h_dst + a, d_dst + a, total - a, cudaMemcpyDeviceToHost, c->aux[1]));
+        }
+    }
+    const uint64_t trailer_at = (final_end + 7) >> 3;
+    if (ok && trailer_at + trailer_len > len) ok = false;
+    uint32_t sums[2] = {0, 1};
+    uint8_t tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok && trailer_len) {
+        if ((rc = checksum_launch(c, d_dst, (size_t)total, c->small.as<uint32_t>(), s)) != 0) { if (h_dst) cudaStreamSynchronize(c->aux[1]); return rc; }
+        ZB_CUDA(cudaMemcpyAsync(sums, c->small.p, 8, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaMemcpyAsync(tr, d_src + trailer_at, trailer_len, cudaMemcpyDeviceToHost, s));
+        ZB_CUDA(cudaStreamSynchronize(s));
+        if (wrap == ZB200_WRAP_ZLIB) {                          // inflate.c:1077-1098
+            const uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
+            if (want != sums[1]) ok = false;                    // let the serial decoder find and name the damage
+        } else if (wrap == ZB200_WRAP_GZIP) {                   // inflate.c:1099-1112: CRC-32, then the length mod 2^32
+            const uint32_t want = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+            const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
+            if (want != sums[0] || isize != (uint32_t)total) ok = false;
+        }
+    }
+    if (h_dst) ZB_CUDA(cudaStreamSynchronize(c->aux[1]));
+    if (!ok) return 1;
+    *total_out = total;
+    *used_out = trailer_at + trailer_len;
+    *check_out = wrap == ZB200_WRAP_GZIP ? sums[0] : sums[1];   // what strm->adler holds at the end: CRC-32 for gzip
+    return 0;
+}
+
 // Returns 0 when the stream was decoded here (*status, *out_len set), 1 when the caller should use the serial decoder
 // (no usable boundaries, output that does not fit, damaged data), negative on CUDA errors.
 int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t* d_dst, uint64_t cap, int wrap,
@@ -1359,12 +1518,33 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
         while (!cand.empty() && cand.back() + 64 > len * 8) cand.pop_back();
         const uint32_t nc = (uint32_t)cand.size();
         if (nc < 2) continue;
+        // ---- streams of this library end every ZB200_CHUNK bytes of input with a marker: assume exactly that (segment j
+        // holds bytes [j, j + 1) * ZB200_CHUNK of the output) and go straight to the emit pass, which checks every
+        // segment's length and arrival; if the assumption fails anywhere, the counting pass below takes over ----
+        if (source == 0 && (uint64_t)(nc - 1) * ZB200_CHUNK < cap) {
+            std::vector<SegDesc> guess(nc);
+            for (uint32_t j = 0; j < nc; j++)
+                guess[j] = SegDesc{cand[j], j + 1 < nc ? cand[j + 1] : 0, (uint64_t)j * ZB200_CHUNK,
+                                   j + 1 < nc ? (uint64_t)ZB200_CHUNK : std::min<uint64_t>(ZB200_CHUNK, cap - (uint64_t)j * ZB200_CHUNK)};
+            uint64_t g_total = 0, g_used = 0;
+            uint32_t g_check = 1;
+            rc = emit_segments(c, d_src, len, d_dst, guess, 0, 0, true, wrap, s, h_dst, &g_total, &g_used, &g_check);
+            if (rc < 0) return rc;
+            if (rc == 0) {
+                *out_len = g_total;
+                *status = ZB_OK;
+                if (in_used) *in_used = g_used;
+                if (adler) *adler = g_check;
+                if (wrap_found) *wrap_found = wrap;
+                return 0;
+            }
+        }
         // ---- count: every candidate decodes to the first candidate it arrives at ----
         if ((rc = c->ws[3].ensure((size_t)nc * sizeof(SegResult))) != 0) return rc;
         SegResult* d_res = c->ws[3].as<SegResult>();
         ZB_CUDA(cudaMemcpyAsync(d_pos, cand.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, s));
         ZB_LAUNCH((k_inflate_segments<false>), (nc + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s, d_src, len, (const SegDesc*)nullptr, nc,
-                  (uint16_t*)nullptr, d_res, d_pos);
+                  (uint16_t*)nullptr, d_res, d_pos, 0u, nc);
         res.resize(nc);
         ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nc * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
         ZB_CUDA(cudaStreamSynchronize(s));
@@ -1388,66 +1568,15 @@ int inflate_single_parallel(Ctx* c, const uint8_t* d_src, uint64_t len, uint8_t*
         if (segs.size() < 2) segs.clear();                      // nothing gained; try the other source
     }
     if (segs.empty()) return 1;
-    const uint32_t nseg = (uint32_t)segs.size();
     if (total > cap) return 1;                                  // the serial decoder reports Z_BUF_ERROR the reference's way
-    const uint64_t trailer_at = (final_end + 7) >> 3;
-    const uint64_t trailer_len = wrap == ZB200_WRAP_ZLIB ? 4 : wrap == ZB200_WRAP_GZIP ? 8 : 0;
-    if (trailer_at + trailer_len > len) return 1;
-    // ---- emit, tails, rest ----
-    if ((rc = c->ws[2].ensure((size_t)nseg * sizeof(SegDesc))) != 0) return rc;
-    if ((rc = c->ws[3].ensure((size_t)nseg * sizeof(SegResult))) != 0) return rc;
-    if ((rc = c->ws[4].ensure((size_t)total * 2 + 64)) != 0) return rc;
-    SegDesc* d_segs = c->ws[2].as<SegDesc>();
-    SegResult* d_res = c->ws[3].as<SegResult>();
-    uint16_t* d_sym = c->ws[4].as<uint16_t>();
-    ZB_CUDA(cudaMemcpyAsync(d_segs, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, s));
-    ZB_LAUNCH((k_inflate_segments<true>), (nseg + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, s, d_src, len, d_segs, nseg, d_sym, d_res,
-              (const uint64_t*)nullptr);
-    // The sequential walk runs in a few launches (the ring is re-read from the output, which is final behind the walk), each
-    // followed by the parallel rest of its segments -- so a pinned host destination receives the finished part of the
-    // output while the walk goes on.
-    const uint32_t nphase = (h_dst && nseg >= 64) ? 8 : 1;
-    if (h_dst && (rc = c->ensure_aux(nphase + 2)) != 0) return rc;
-    for (uint32_t k = 0; k < nphase; k++) {
-        const uint32_t j0 = (uint32_t)((uint64_t)nseg * k / nphase), j1 = (uint32_t)((uint64_t)nseg * (k + 1) / nphase);
-        if (j1 == j0) continue;
-        ZB_LAUNCH(k_resolve_tails, kTailCtas, kTailThreads, 0, s, d_sym, d_dst, d_segs, j0, j1, d_err);
-        ZB_LAUNCH(k_resolve_rest, j1 - j0, 256, 0, s, d_sym, d_dst, d_segs + j0, d_err);
-        if (h_dst) {
-            const uint64_t a = segs[j0].out_off, b = segs[j1 - 1].out_off + segs[j1 - 1].out_len;
-            ZB_CUDA(cudaEventRecord(c->evs[k], s));
-            ZB_CUDA(cudaStreamWaitEvent(c->aux[1], c->evs[k], 0));
-            if (b > a) ZB_CUDA(cudaMemcpyAsync((uint8_t*)h_dst + a, d_dst + a, b - a, cudaMemcpyDeviceToHost, c->aux[1]));
-        }
-    }
-    ZB_CHECK_LAUNCH();
-    uint32_t sums[2] = {0, 1}, nerr = 0;
-    uint8_t tr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (trailer_len) {
-        if ((rc = checksum_launch(c, d_dst, (size_t)total, c->small.as<uint32_t>(), s)) != 0) return rc;
-        ZB_CUDA(cudaMemcpyAsync(sums, c->small.p, 8, cudaMemcpyDeviceToHost, s));
-        ZB_CUDA(cudaMemcpyAsync(tr, d_src + trailer_at, trailer_len, cudaMemcpyDeviceToHost, s));
-    }
-    res.resize(nseg);
-    ZB_CUDA(cudaMemcpyAsync(res.data(), d_res, (size_t)nseg * sizeof(SegResult), cudaMemcpyDeviceToHost, s));
-    ZB_CUDA(cudaMemcpyAsync(&nerr, d_err, 4, cudaMemcpyDeviceToHost, s));
-    ZB_CUDA(cudaStreamSynchronize(s));
-    if (nerr) return 1;
-    for (uint32_t j = 0; j < nseg; j++)
-        if (res[j].status != 0 || res[j].out_len != segs[j].out_len) return 1;
-    if (wrap == ZB200_WRAP_ZLIB) {                              // inflate.c:1077-1098
-        const uint32_t want = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
-        if (want != sums[1]) return 1;                          // let the serial decoder find and name the damage
-    } else if (wrap == ZB200_WRAP_GZIP) {                       // inflate.c:1099-1112: CRC-32, then the length mod 2^32
-        const uint32_t want = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
-        const uint32_t isize = (uint32_t)tr[4] | ((uint32_t)tr[5] << 8) | ((uint32_t)tr[6] << 16) | ((uint32_t)tr[7] << 24);
-        if (want != sums[0] || isize != (uint32_t)total) return 1;
-    }
-    if (h_dst) ZB_CUDA(cudaStreamSynchronize(c->aux[1]));
+    uint64_t used = 0;
+    uint32_t check = 1;
+    rc = emit_segments(c, d_src, len, d_dst, segs, total, final_end, false, wrap, s, h_dst, &total, &used, &check);
+    if (rc) return rc;
     *out_len = total;
     *status = ZB_OK;
-    if (in_used) *in_used = trailer_at + trailer_len;
-    if (adler) *adler = wrap == ZB200_WRAP_GZIP ? sums[0] : sums[1];   // what strm->adler holds at the end: CRC-32 for gzip
+    if (in_used) *in_used = used;
+    if (adler) *adler = check;
     if (wrap_found) *wrap_found = wrap;
     return 0;
 }
