@@ -77,3 +77,27 @@ def test_no_cpu_fallback_without_gpu(lib):
     assert b"no CPU path" in lib.dll.zb200_last_error()
     rc, _ = lib.compress2(b"hello, hello!", 6)
     assert rc == -2                                       # Z_STREAM_ERROR, not a host-side result
+
+
+def test_only_the_c_abi_is_exported():
+    """Symbol hygiene (SURVEY.md hard part 9): the dynamic symbol table holds zlib.h, zb200.h and the three zutil
+    names the reference's own callers reach for -- no C++ runtime instantiations, no mangled names."""
+    import subprocess
+    from zlib_b200 import LIB_PATH
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if l.strip()]
+    assert names and not [n for n in names if n.startswith("_Z")], [n for n in names if n.startswith("_Z")][:5]
+    allowed = ("zb200_", "deflate", "inflate", "compress", "uncompress", "crc32", "adler32", "get_crc_table",
+               "zlib", "zError", "z_errmsg", "zcalloc", "zcfree")
+    stray = [n for n in names if not n.startswith(allowed)]
+    assert not stray, stray
+
+
+def test_corpus_generator_is_its_own_library():
+    """bench.py's reference arm generates its input without mapping libzb200.so (zlib_b200/libzbsynth.so)."""
+    import numpy as np
+    from zlib_b200 import synth
+    a = synth.synth(300000, 1, 1)
+    b = synth.synth(100000, 1, 1, offset=65536 + 11)
+    assert np.array_equal(a[65536 + 11:65536 + 11 + 100000], b)
+    assert not hasattr(__import__("zlib_b200").load().dll, "zb200_synth")

@@ -41,7 +41,7 @@ def test_flush_points_and_full_flush(gpu_lib, oracle):
     flushes = {3: zb.Z_FULL_FLUSH, 1000: zb.Z_SYNC_FLUSH, 70000: zb.Z_PARTIAL_FLUSH, 150000: zb.Z_FULL_FLUSH}
     rc, z = gpu_lib.deflate_stream(data, 6, 15, 1 << 20, 1 << 20, flushes)
     assert rc == zb.Z_OK
-    assert z.count(b"\x00\x00\xff\xff") >= 4                  # every flush leaves the empty stored block
+    assert z.count(b"\x00\x00\xff\xff") >= 3                  # SYNC and FULL flushes leave the empty stored block (PARTIAL an empty static one)
     rc2, out, _ = oracle.inflate(z, len(data))
     assert rc2 == 0 and out == data
     # after a full flush the tail is decodable on its own as raw deflate (history forgotten)

@@ -250,34 +250,46 @@ __device__ void fold_records(const Partial* __restrict__ parts, uint32_t n_parts
             const volatile Partial* last = parts + m;
             uint32_t r = (m ? gf2_mul(v, fa.pw_last) : 0u) ^ last->reg;      // at the aligned end
             r = gf2_mul(r, fa.pw_tail);                                       // at the end of the buffer
-            // head bytes (< 16): byte-wise, then moved to the end; tail bytes (< 512): byte-wise from the register so far
+            // head bytes (< 16): byte-wise on this lane, then moved to the end with the host's power
             uint32_t hreg = 0;
             for (uint64_t o = 0; o < head; o++) hreg = g_tab_byte[(hreg ^ buf[o]) & 0xffu] ^ (hreg >> 8);
             if (head) r ^= gf2_mul(hreg, fa.pw_head);
-            uint32_t treg = 0;
-            for (uint64_t o = tail_begin; o < len; o++) treg = g_tab_byte[(treg ^ buf[o]) & 0xffu] ^ (treg >> 8);
-            r ^= treg;
             r ^= gf2_mul(0xffffffffu, fa.pw_len);                              // 0xffffffff pre-conditioning
             reg = r;
         }
     }
-    // ---- Adler: ragged edges, then the sums ----
+    // ---- ragged edges: Adler over head and tail bytes; CRC of the tail bytes (< 512), one per thread: its byte-table
+    // entry moved to the end of the buffer by a short power (the suffix is below 512) ----
+    uint32_t treg = 0;
     const uint64_t n_edge = head + (len - tail_begin);
     for (uint64_t e = tid; e < n_edge; e += blockDim.x) {
         const uint64_t o = e < head ? e : tail_begin + (e - head);
         const uint32_t v = buf[o];
         a = (a + v) % kAdlerBase;
         b = (b + (uint32_t)(((len - o) % kAdlerBase) * v % kAdlerBase)) % kAdlerBase;
+        if (e >= head) {
+            const uint64_t suffix = len - o - 1;
+            const uint32_t r1 = g_tab_byte[v];
+            treg ^= suffix ? gf2_mul(r1, pow8(suffix)) : r1;
+        }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+        treg ^= __shfl_xor_sync(0xffffffffu, treg, o);
+    }
+    __shared__ uint32_t s_t[32];
     __syncthreads();                                            // s_x is reused
-    if (lane == 0) { s_x[warp] = a % kAdlerBase; s_x[32 + warp] = b % kAdlerBase; }
+    if (lane == 0) { s_x[warp] = a % kAdlerBase; s_x[32 + warp] = b % kAdlerBase; s_t[warp] = treg; }
     __syncthreads();
     if (warp == 0) {
-        a = s_x[lane]; b = s_x[32 + lane];
+        a = s_x[lane]; b = s_x[32 + lane]; treg = s_t[lane];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        for (int o = 16; o; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+            treg ^= __shfl_xor_sync(0xffffffffu, treg, o);
+        }
+        reg ^= treg;                                            // (lane 0 holds the register; the others' value is unused)
         if (lane == 0) {
             const uint32_t s1 = (1u + a) % kAdlerBase;
             const uint32_t s2 = (uint32_t)((len % kAdlerBase + b) % kAdlerBase);
