@@ -42,7 +42,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "deflate_level1_GBps_uncompressed"
 UNIT = "GB/s"
-PIECES_PER_RANK = 4                    # rounds of the multi-GPU run (256 MiB pieces at 1 GiB per GPU)
+PIECES_PER_RANK = 2                    # rounds of the multi-GPU run (512 MiB pieces at 1 GiB per GPU; measured 2 / 4 / 8: 15.2 / 15.9 / 16.2 ms at N = 2)
 WINDOW = 32768
 PRE = 65536                            # bytes generated in front of a piece (the corpus generator works in 64 KiB pages)
 

@@ -1439,7 +1439,7 @@ static int env_int(const char* name, int dflt)
 static int walk_flat_lazy(int chain) { static const int force = env_int("ZB200_LAZY_FLAT", -1); return force >= 0 ? force : (chain >= 256 ? 1 : 0); }
 // exact intra-step links (MATCH.ANY, 8.4 ms per GiB) for the levels that search long chains; levels 1..6 take the relaxed
 // links (3.1 ms per GiB, ~0.1 % larger output)
-static bool link_exact(int level) { static const int force = env_int("ZB200_LINK_EXACT", -1); return force >= 0 ? force != 0 : level >= 7; }
+static bool link_exact(int level, int strategy) { static const int force = env_int("ZB200_LINK_EXACT", -1); return force >= 0 ? force != 0 : (level >= 7 || (level >= 4 && strategy == 4)); }
 static bool walk_persistent() { static const bool on = env_int("ZB200_WALK_PERSIST", 1) != 0; return on; }
 static unsigned walk_grid(uint64_t nblocks, bool lazy_shape)
 {
@@ -1485,7 +1485,7 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
         const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
         if (cfg.chain != 0 && P.strategy != 3) {                // Z_RLE needs no chains
             // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
-            if (link_exact(P.level)) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
+            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
             else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
         }
         const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
@@ -1546,7 +1546,7 @@ static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uin
         d_ntok = c->ws[10].as<uint32_t>();
         uint32_t* d_next = walk_persistent() ? d_ntok + nblocks : nullptr;   // the walk kernel's block counter
         if (cfg.chain != 0 && P.strategy != 3) {
-            if (link_exact(P.level)) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
+            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
             else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
         }
         const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
@@ -1585,7 +1585,11 @@ static void plan_slabs(uint64_t n, bool ramp, std::vector<uint64_t>& cut)
     const uint64_t C = (n + kChunk - 1) / kChunk, full = kSlabChunks, h = full / 2, q = full / 4;
     std::vector<uint64_t> sizes;
     if (!ramp || C <= 4 * full) {
-        for (uint64_t c = 0; c < C; c += full) sizes.push_back(std::min<uint64_t>(full, C - c));
+        // equal slabs, an even number of them: slabs alternate between two streams, and a short last slab would run alone
+        uint64_t k = (C + full - 1) / full;
+        if (k > 1 && (k & 1)) k++;
+        const uint64_t per = (C + k - 1) / k;
+        for (uint64_t c = 0; c < C; c += per) sizes.push_back(std::min<uint64_t>(per, C - c));
     } else {
         const uint64_t mid = C - 2 * (q + h);
         sizes.push_back(q); sizes.push_back(h);
@@ -1647,11 +1651,12 @@ static int deflate_params(DeflateParams& P, int level, int wrap, int flags)
         if (chain1 > 0) P.cfg.chain = (uint16_t)chain1;
         if (nice1 > 0) P.cfg.nice = (uint16_t)nice1;
     }
+    P.strategy = (flags >> 8) & 7;                              // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
     if (level == 6) {
         static const int chain6 = env_int("ZB200_L6_CHAIN", 0);
         if (chain6 > 0) P.cfg.chain = (uint16_t)chain6;
+        else if (P.strategy == 4) P.cfg.chain = 128;            // Z_FIXED keeps the reference's budget: a fixed code pays 5+ bits for every extra token
     }
-    P.strategy = (flags >> 8) & 7;                              // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
     const int wbits = (flags >> 12) & 15;                       // 0 = 15; deflate.c:270-279, h/deflate.h:276
     P.max_dist = (wbits >= 9 && wbits < 15) ? (1u << wbits) - 262u : kWindow;
     if (P.strategy == 2 && P.cfg.kind != 0) { P.cfg.chain = 0; P.cfg.kind = 1; }   // literals only (deflate.c:1490)
@@ -1677,6 +1682,7 @@ struct ShardJob {
     void* dst = nullptr; uint8_t* d_out = nullptr;
     bool dst_on_host = false;
     cudaEvent_t* ev_done = nullptr;
+    cudaEvent_t ev_result = nullptr;                            // the result words have reached pinned memory
     uint64_t* h_res = nullptr; uint64_t* h_pos = nullptr;
     int rc = 0;
 };
@@ -1724,9 +1730,10 @@ static int shard_begin(ShardJob* J, const void* src, size_t src_len, const void*
         const bool src_on_host = n != 0 && classify(src) != kDevice;
         const bool dst_on_host = classify(dst) != kDevice;
         J->dst_on_host = dst_on_host;
-        if ((rc = c->ensure_aux((int)(3 * nslabs + 4))) != 0) break;
+        if ((rc = c->ensure_aux((int)(3 * nslabs + 5))) != 0) break;
         cudaStream_t s_in = c->aux[0];
         J->s_out = c->aux[1];
+        J->ev_result = c->evs[3 * nslabs + 3];
         cudaEvent_t* ev_in = c->evs;
         cudaEvent_t* ev_done = c->evs + nslabs;
         cudaEvent_t* ev_scan = c->evs + 2 * nslabs;
@@ -1830,6 +1837,7 @@ static int shard_begin(ShardJob* J, const void* src, size_t src_len, const void*
         ZB_LAUNCH(k_frame, 1, 32, 0, s, d_out, cap, hdr_len, d_pos + (nslabs ? nslabs - 1 : 0), d_sums, n, level, wrap, flags, d_total);
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_res, c->small.p, 32, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaEventRecord(J->ev_result, s);   // shard_end waits for THIS, not for whatever the caller enqueues behind it
         if (e != cudaSuccess) { set_error("deflate launch failed: %s", cudaGetErrorString(e)); cudaStreamSynchronize(s); rc = ZB_STREAM_ERROR; break; }
     } while (0);
     if (rc) shard_release(J);
@@ -1868,7 +1876,7 @@ static int shard_end(ShardJob* J, size_t* dst_len, uint32_t* crc, uint32_t* adle
             }
         }
         if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(s_out); break; }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = cudaEventSynchronize(J->ev_result);
         if (e != cudaSuccess) { set_error("deflate failed: %s", cudaGetErrorString(e)); cudaStreamSynchronize(s_out); rc = ZB_STREAM_ERROR; break; }
         const uint64_t total = h_res[0];
         const uint32_t* r32 = (const uint32_t*)h_res;
