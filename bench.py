@@ -323,13 +323,15 @@ def emit_line(obj):
 
 
 class SharedHost:
-    """ONE page-locked host buffer that every rank (process) maps: POSIX shared memory registered with the CUDA driver.
-    `ptr` is None when /dev/shm cannot hold it (then every rank falls back to a private pinned buffer)."""
+    """ONE host buffer that every rank (process) maps: POSIX shared memory.  Each rank page-locks only the byte ranges IT
+    writes (pin(): cudaHostRegister of the whole buffer in every process ran into the box's locked-memory limit at 4 and 8
+    ranks), so copies into it run at pinned speed and asynchronously.  `ptr` is None when /dev/shm cannot hold the buffer
+    (then every rank falls back to a private pinned buffer)."""
 
     def __init__(self, lib, tag, size, rank, dist):
         from multiprocessing import shared_memory
         self.lib, self.rank, self.dist, self.size = lib, rank, dist, size
-        self.shm, self.ptr, self.private = None, None, None
+        self.shm, self.ptr, self.private, self.pinned = None, None, None, []
         st = os.statvfs("/dev/shm") if os.path.isdir("/dev/shm") else None
         fits = st is not None and st.f_bavail * st.f_frsize > size + (1 << 30)
         import torch
@@ -350,15 +352,34 @@ class SharedHost:
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=name)
         self.ptr = C.addressof(C.c_char.from_buffer(self.shm.buf))
-        assert lib.dll.zb200_host_register(C.c_void_p(self.ptr), size) == 0, lib.last_error()
 
     @property
     def where(self):
         return self.ptr if self.ptr is not None else self.private
 
+    def pin(self, ranges):
+        """Page-locks [off, off + n) for every (off, n) this rank writes.  True when all of them are locked."""
+        if self.ptr is None:
+            return True                                      # the private buffer is pinned memory already
+        page = 4096
+        spans = sorted((o // page * page, min(self.size, (o + n + page - 1) // page * page)) for o, n in ranges if n)
+        merged = []
+        for a, b in spans:
+            if merged and a <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], b)
+            else:
+                merged.append([a, b])
+        for a, b in merged:
+            if self.lib.dll.zb200_host_register(C.c_void_p(self.ptr + a), b - a) != 0:
+                log(f"[rank {self.rank}] cudaHostRegister of {b - a} bytes failed: {self.lib.last_error()}")
+                return False
+            self.pinned.append(self.ptr + a)
+        return True
+
     def close(self):
         if self.ptr is not None:
-            self.lib.dll.zb200_host_unregister(C.c_void_p(self.ptr))
+            for p in self.pinned:
+                self.lib.dll.zb200_host_unregister(C.c_void_p(p))
             self.dist.barrier()
             self.shm.close()
             if self.rank == 0:
@@ -444,7 +465,14 @@ def main():
     outs = [torch.empty(cap_piece, dtype=torch.uint8, device=dev) for _ in ranges] if world > 1 else None
     d_dst = torch.empty(cap, dtype=torch.uint8, device=dev) if world == 1 else None
     total_cap = lib.compress_bound(total) + 64
-    d_final = torch.empty(total_cap, dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    # the assembled stream lives on rank 0: a buffer every rank can name (CUDA IPC) so that the copy engines carry the
+    # pieces there; when IPC is not to be had, a torch tensor on rank 0 filled by NCCL send / recv
+    d_final, final_ptr, final_close = None, None, None
+    copy_dev = torch.cuda.Stream() if world > 1 else None
+    if world > 1:
+        final_ptr, final_close = zdist.share_device_buffer(lib, total_cap)
+        if final_ptr is None and rank == 0:
+            d_final = torch.empty(total_cap, dtype=torch.uint8, device=dev)
     pin_dst = lib.dll.zb200_alloc_pinned(cap) if world == 1 else None
 
     def barrier():
@@ -459,7 +487,8 @@ def main():
             state["clen"] = lib.deflate(d_src.data_ptr() + PRE, n, d_dst.data_ptr(), cap, level, zb.WRAP_ZLIB, s)
         else:
             state["clen"], state["crc"], state["adler"], _ = zdist.deflate_rounds(
-                lib, pieces_dev, level, zb.WRAP_ZLIB, root=0, outs=outs, final=d_final, stream=s)
+                lib, pieces_dev, level, zb.WRAP_ZLIB, root=0, outs=outs, final=d_final, stream=s,
+                peer_final=final_ptr, copy_stream=copy_dev)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -534,13 +563,21 @@ def main():
         shm = SharedHost(lib, "bench", total_cap, rank, dist)
         shm_ptr = shm.where
         copy_stream = torch.cuda.Stream()
+        placed = []
 
-        def step_e2e():
+        def step_e2e(placed=None):
             state["e2e_len"], _, _, _ = zdist.deflate_rounds(lib, pieces_host, 1, zb.WRAP_ZLIB, root=0, outs=outs,
-                                                             host_final=shm_ptr, stream=s, copy_stream=copy_stream)
-        api = ("zb200_deflate_shard per piece from pinned host input, NCCL all-gather of {len,n,crc,adler} per round, "
-               "D2H of every piece straight into ONE shared page-locked host buffer at its final offset"
-               if shm.ptr is not None else "as above, but /dev/shm cannot hold the stream: every rank copies into a private pinned buffer")
+                                                             host_final=shm_ptr, stream=s, copy_stream=copy_stream, placed=placed)
+        step_e2e(placed)                                     # where this rank's pieces land (the same every step: same data)
+        pinned_ok = shm.pin(placed)
+        t_ok = torch.tensor([1 if pinned_ok else 0], device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        pinned_ok = bool(t_ok.item())
+        api = ("zb200_deflate_shard_begin/_end per piece from pinned host input, NCCL all-gather of {len,n,crc,adler} per round, "
+               "D2H of every piece straight into ONE shared host buffer at its final offset "
+               + ("(every rank page-locks the ranges it writes)" if shm.ptr is not None and pinned_ok else
+                  "(NOT page-locked: cudaHostRegister refused)" if shm.ptr is not None else
+                  "-- /dev/shm cannot hold the stream: every rank copies into a private pinned buffer"))
     step_e2e()
     step_e2e()
     barrier()
@@ -568,7 +605,7 @@ def main():
                 verified = reference_inflate_check(pin_dst, int(state["e2e_len"]), total)
             else:
                 h_final = np.empty(int(clen1), dtype=np.uint8)
-                lib.dll.zb200_copy(C.c_void_p(h_final.ctypes.data), C.c_void_p(d_final.data_ptr()), int(clen1), None)
+                lib.dll.zb200_copy(C.c_void_p(h_final.ctypes.data), C.c_void_p(final_ptr if final_ptr is not None else d_final.data_ptr()), int(clen1), None)
                 if shm.ptr is not None:                         # the stream in the shared host buffer is decoded by the reference;
                     ok_host = reference_inflate_check(shm_ptr, int(state["e2e_len"]), total)
                     same = int(clen1) == int(state["e2e_len"]) and bool(np.array_equal(                    # the one on the root GPU must be the same bytes
@@ -608,10 +645,14 @@ def main():
                 "ratio": round(total / clen1, 4), "compressed_bytes": int(clen1),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "verified_by_reference": verified, "assembled": assembled if world > 1 else True,
+                "gather": (None if world == 1 else "copy engines over NVLink into rank 0's buffer (CUDA IPC)" if final_ptr is not None
+                           else "NCCL send / recv into rank 0's buffer"),
                 "extra": extra}
         emit_line(line)
     if shm is not None:
         shm.close()
+    if final_close is not None:
+        final_close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -1005,6 +1046,7 @@ def zip_config5(args, lib, zb, zdist, synth, dev, world, rank, have_ref, barrier
         allrec = allrec.view(world, width + 1, 5).cpu()
         seg_len = [int(allrec[r, 0, 0]) for r in range(world)]
         base = sum(seg_len[:rank])
+        out["mine"] = (base, ol.value)
         lib._check(lib.dll.zb200_copy_async(shm_ptr + base, d_seg.data_ptr(), ol.value, None), "zb200_copy_async")
         lib._check(lib.dll.zb200_sync(None), "zb200_sync")
         out["total"] = sum(seg_len)
@@ -1019,6 +1061,9 @@ def zip_config5(args, lib, zb, zdist, synth, dev, world, rank, have_ref, barrier
             cd = lib.zip_directory(order, glob, b0)
             C.memmove(shm_ptr + b0, cd, len(cd))
             out["arc_len"] = b0 + len(cd)
+    step()
+    barrier()
+    shm.pin([out["mine"]])                                   # this rank's segment lands in the same place every time
     step()
     barrier()
     ts = []

@@ -53,6 +53,12 @@ int   zb200_sync(void *stream);
  * write their shards into), so that copies to and from it run at pinned speed and asynchronously. */
 int   zb200_host_register(void *host_ptr, size_t bytes);
 int   zb200_host_unregister(void *host_ptr);
+/* Device memory of ANOTHER process on the same box (one process per GPU: torchrun, MPI): the owner exports a 64-byte
+ * handle for a buffer it got from zb200_alloc_device, the others open it and may then name it as the destination of
+ * zb200_copy_async -- the copy engines move the bytes over NVLink without occupying an SM on either side. */
+int   zb200_ipc_export(void *dev_ptr, unsigned char handle[64]);
+int   zb200_ipc_open(const unsigned char handle[64], void **peer_ptr);
+int   zb200_ipc_close(void *peer_ptr);
 
 /* ---- checksums: crc32() + adler32() in one pass (qcsrc/crc32.c:219, adler32.c:57) ----
  * Computes crc32(0, buf, len) and adler32(1, buf, len); either result pointer may

@@ -117,6 +117,7 @@ class Lib:
             "zb200_copy": (C.c_int, [vp, vp, sz, vp]), "zb200_sync": (C.c_int, [vp]),
             "zb200_copy_async": (C.c_int, [vp, vp, sz, vp]),
             "zb200_host_register": (C.c_int, [vp, sz]), "zb200_host_unregister": (C.c_int, [vp]),
+            "zb200_ipc_export": (C.c_int, [vp, vp]), "zb200_ipc_open": (C.c_int, [vp, C.POINTER(vp)]), "zb200_ipc_close": (C.c_int, [vp]),
             "zb200_checksum": (C.c_int, [vp, sz, u32p, u32p, vp]),
             "zb200_checksum_dev": (C.c_int, [vp, sz, vp, vp]),
             "zb200_checksum_batch": (C.c_int, [vp, vp, sz, vp, vp, vp]),

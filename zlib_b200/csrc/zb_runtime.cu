@@ -473,6 +473,35 @@ ZB_API int zb200_host_unregister(void* host_ptr)
     return 0;
 }
 
+ZB_API int zb200_ipc_export(void* dev_ptr, unsigned char handle[64])
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    ZB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+ZB_API int zb200_ipc_open(const unsigned char handle[64], void** peer_ptr)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    ZB_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+ZB_API int zb200_ipc_close(void* peer_ptr)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    ZB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+
 ZB_API int zb200_sync(void* stream)
 {
     int rc = ensure_init();

@@ -180,8 +180,51 @@ def _side_stream(dev):
     return _SIDE[key]
 
 
+def share_device_buffer(lib, nbytes: int, root: int = 0, group=None):
+    """A device buffer on `root` that every rank of the box can name: the root allocates it (zb200_alloc_device), exports
+    a CUDA IPC handle, the others open it.  Returns (pointer valid on this rank, closer) or (None, None) when IPC is not
+    available here (then deflate_rounds falls back to NCCL send / recv)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    h = torch.zeros(65, dtype=torch.uint8, device=dev)
+    ptr = None
+    if rank == root:
+        ptr = lib.dll.zb200_alloc_device(nbytes)
+        buf = (C.c_ubyte * 64)()
+        if ptr and lib.dll.zb200_ipc_export(C.c_void_p(ptr), buf) == 0:
+            h[:64] = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+            h[64] = 1
+    dist.broadcast(h, src=_global(group, root), group=group)
+    ok = int(h[64]) == 1
+    if ok and rank != root:
+        buf = (C.c_ubyte * 64)(*h[:64].cpu().tolist())
+        p = C.c_void_p(0)
+        ok = lib.dll.zb200_ipc_open(buf, C.byref(p)) == 0 and bool(p.value)
+        ptr = p.value if ok else None
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if not bool(flag.item()):
+        if ptr and rank == root:
+            lib.dll.zb200_free_device(C.c_void_p(ptr))
+        elif ptr:
+            lib.dll.zb200_ipc_close(C.c_void_p(ptr))
+        return None, None
+
+    def close():
+        dist.barrier(group)
+        if rank == root:
+            lib.dll.zb200_free_device(C.c_void_p(ptr))
+        else:
+            lib.dll.zb200_ipc_close(C.c_void_p(ptr))
+    return ptr, close
+
+
 def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=None, root: int = 0, outs=None,
-                   final=None, host_final: Optional[int] = None, stream=None, copy_stream=None, last_round_is_last: bool = True):
+                   final=None, host_final: Optional[int] = None, stream=None, copy_stream=None, last_round_is_last: bool = True,
+                   peer_final: Optional[int] = None, placed: Optional[list] = None):
     """ONE stream from all ranks, assembled on `root` while the compression is still running.
 
     pieces[j] = (src_ptr, n, dict_ptr, dict_len) for round j: this rank's j-th piece (device or pinned host memory) and
@@ -189,7 +232,10 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
     every rank knows (one all-gather of {len, n, crc32, adler32}) where its round-j output lands in the final stream,
     and the transfer of round j -- NCCL send/recv into `final` on the root (device mode), or a D2H copy straight into
     the shared, page-locked host buffer at `host_final` (host mode) -- runs while round j + 1 is compressed.  Only the
-    last round's transfer is exposed.  The root adds the header and the trailer with the combined checksum.
+    last round's transfer is exposed.  With `peer_final` (the root's buffer opened through CUDA IPC, share_device_buffer)
+    the device-mode transfers are plain copies issued by their OWNER on its copy stream: the copy engines move them over
+    NVLink, no SM on either side is needed (NCCL's send / recv kernels wait for SM slots that the persistent walk CTAs hold).
+    `placed`, if given, receives (offset, length) of this rank's part of every round.  The root adds the header and the trailer with the combined checksum.
     outs[j]: this rank's device output buffer of round j.  Returns (total stream length, crc32, adler32, n_in).
     """
     import torch
@@ -238,9 +284,12 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
                     crc_all = lib.crc32_combine(crc_all, c, m)
                     adl_all = adler_join(adl_all, a, m)
                 n_all += m
-            if host_final is not None:                             # every rank writes its own part of the shared host buffer
+            if placed is not None:
+                placed.append((offs[rank], clen))
+            if host_final is not None or peer_final is not None:   # every rank writes its own part of the shared buffer
                 if clen:
-                    lib._check(lib.dll.zb200_copy_async(host_final + offs[rank], outs[j].data_ptr(), clen, zb._stream(copy_stream)),
+                    base = host_final if host_final is not None else peer_final
+                    lib._check(lib.dll.zb200_copy_async(base + offs[rank], outs[j].data_ptr(), clen, zb._stream(copy_stream)),
                                "zb200_copy_async")
             elif final is not None or rank != root:
                 ops = []
@@ -272,6 +321,12 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
                 import ctypes as C
                 C.memmove(host_final, header, len(header))
                 C.memmove(host_final + pos, trailer, len(trailer))
+            elif peer_final is not None:
+                ht = torch.tensor(list(header + trailer), dtype=torch.uint8, device=dev)
+                if header:
+                    lib._check(lib.dll.zb200_copy_async(peer_final, ht.data_ptr(), len(header), zb._stream(copy_stream)), "zb200_copy_async")
+                if trailer:
+                    lib._check(lib.dll.zb200_copy_async(peer_final + pos, ht.data_ptr() + len(header), len(trailer), zb._stream(copy_stream)), "zb200_copy_async")
             elif final is not None:
                 if header:
                     final[:len(header)] = torch.tensor(list(header), dtype=torch.uint8, device=dev)
@@ -279,8 +334,10 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
                     final[pos:total] = torch.tensor(list(trailer), dtype=torch.uint8, device=dev)
     if side is not None:
         torch.cuda.current_stream().wait_stream(side)              # the caller's stream sees the assembled stream
-    if host_final is not None:
+    if host_final is not None or peer_final is not None:
         lib._check(lib.dll.zb200_sync(zb._stream(copy_stream)), "zb200_sync")
+    if peer_final is not None:
+        dist.barrier(group)                                        # every rank's copies have landed: the stream is complete on the root
     return total, crc_all, adl_all, n_all
 
 
