@@ -295,8 +295,8 @@ def workload_config(size_mib, world):
                         "128 KiB chunks with 32 KiB dictionary priming, one zlib stream",
             "level": 1, "chunk": 131072, "bytes_per_gpu": size_mib << 20, "total_bytes": (size_mib << 20) * world,
             "l2": "inputs (1 GiB per GPU) exceed the 126 MB L2; no flush needed",
-            "parallelism": (f"one {world * size_mib} MiB corpus, {world * PIECES_PER_RANK} pieces dealt round robin over {world} GPUs, "
-                            "assembled on rank 0") if world > 1 else "single GPU"}
+            "parallelism": (f"one {world * size_mib} MiB corpus cut into rounds of {world} pieces dealt round robin over {world} GPUs "
+                            "(2 equal rounds below 4 GPUs; shares of 1/2, 3/8, 1/8 from 4 GPUs on), assembled on rank 0") if world > 1 else "single GPU"}
 
 
 # ------------------------------------------------------------------------------------- our arm
@@ -415,7 +415,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="zb200", choices=["zb200", "reference"])
     ap.add_argument("--size-mib", type=int, default=1024)
-    ap.add_argument("--pieces", type=int, default=PIECES_PER_RANK, help="rounds per rank of the multi-GPU run")
+    ap.add_argument("--pieces", default="", help="rounds per rank of the multi-GPU run: a count, or fractions of a rank's share "
+                    "such as 0.5,0.375,0.125 (default: 2 equal rounds below 4 GPUs, 0.5,0.375,0.125 from 4 GPUs on)")
     ap.add_argument("--no-extra", action="store_true", help="skip level 6 / inflate / checksum / zip side measurements")
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
@@ -442,8 +443,14 @@ def main():
     n = args.size_mib << 20                                  # bytes per GPU
     total = n * world                                        # bytes of the one corpus
     warm = max(3, args.warmup)
-    P = max(1, args.pieces) if world > 1 else 1
-    ranges = zdist.piece_ranges(total, world, P)[rank]
+    if world == 1:
+        rounds = 1
+    elif args.pieces:
+        rounds = tuple(float(x) for x in args.pieces.split(",")) if "," in args.pieces else max(1, int(args.pieces))
+    else:                                                    # the last round's transfer to rank 0 is the exposed one: keep it small where it is large
+        rounds = PIECES_PER_RANK if world < 4 else (0.5, 0.375, 0.125)
+    ranges = zdist.piece_ranges(total, world, rounds)[rank]
+    P = len(ranges)
     log(f"[rank {rank}] generating {args.size_mib} MiB of the {total >> 20} MiB mixed corpus ({len(ranges)} piece(s))")
 
     # ---- this rank's pieces: pinned host copy [PRE | piece] and the same on the device ----

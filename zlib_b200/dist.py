@@ -156,15 +156,27 @@ def deflate_sharded(lib, data, halo, level: int = 6, wrap: int = zb.WRAP_ZLIB, g
 # ---------------------------------------------------------------------------------------------
 # One stream from all ranks with the gather hidden behind the compression (bench.py --gpus N)
 # ---------------------------------------------------------------------------------------------
-def piece_ranges(total: int, world: int, pieces_per_rank: int, chunk: int = CHUNK) -> List[List[Tuple[int, int]]]:
-    """The input cut into world * pieces_per_rank pieces dealt round robin: global piece g = j * world + r is round j of
-    rank r.  Returns, per rank, its [begin, end) list in round order.  Pieces are chunk aligned (the last may be short)."""
-    npieces = world * pieces_per_rank
+def piece_ranges(total: int, world: int, pieces_per_rank, chunk: int = CHUNK) -> List[List[Tuple[int, int]]]:
+    """The input cut into rounds of `world` equal pieces dealt round robin: global piece g = j * world + r is round j of
+    rank r.  pieces_per_rank is the number of (equal) rounds, or a tuple of fractions of a rank's share per round -- the
+    LAST round's output is the only transfer that is not hidden behind compression, so it pays to make it the small one,
+    e.g. (0.5, 0.375, 0.125).  Returns, per rank, its [begin, end) list in round order.  Pieces are chunk aligned (the
+    last ones may be short or empty)."""
+    fr = [1.0 / pieces_per_rank] * pieces_per_rank if isinstance(pieces_per_rank, int) else list(pieces_per_rank)
     nchunks = (total + chunk - 1) // chunk
-    per = (nchunks + npieces - 1) // npieces * chunk
+    per_rank = (nchunks + world - 1) // world                      # chunks of a rank's share
+    sizes, used = [], 0
+    for k, f in enumerate(fr):
+        c = per_rank - used if k == len(fr) - 1 else min(per_rank - used, max(1, round(per_rank * f)))
+        sizes.append(c)
+        used += c
     out: List[List[Tuple[int, int]]] = [[] for _ in range(world)]
-    for g in range(npieces):
-        out[g % world].append((min(total, g * per), min(total, (g + 1) * per)))
+    start = 0
+    for c in sizes:
+        for r in range(world):
+            a = (start + r * c) * chunk
+            out[r].append((min(total, a), min(total, a + c * chunk)))
+        start += world * c
     return out
 
 
