@@ -74,6 +74,20 @@ def test_ratio_gate_vs_reference(gpu_lib, oracle, kind):
         assert rc == 0 and out == data.tobytes()
 
 
+def test_ratio_gate_at_config_one_shape(gpu_lib, ref):
+    """Gate (d) at BASELINE config 1's shape: 64 MiB of synthetic text, levels 1 and 6, against the unmodified reference
+    build compressing the WHOLE buffer as one stream; and the reference decodes what we wrote (gate (a))."""
+    n = 64 << 20
+    text = gpu_lib.synth(n, kind=0, seed=7)
+    for level in (1, 6):
+        rc, z = gpu_lib.compress2(text, level)
+        assert rc == 0
+        want = len(ref.compress2(text, level))
+        assert len(z) <= 1.02 * want, (level, len(z), want, len(z) / want)
+        rc, out = ref.uncompress(z, n)
+        assert rc == 0 and out == text.tobytes()
+
+
 def test_huffman_length_limit(gpu_lib, oracle):
     """Fibonacci-weighted symbols push the optimal code past 15 bits and the code-length code past 7:
     the overflow repair of trees.c:527-545 must still give complete codes."""

@@ -118,6 +118,27 @@ class Ref:
         rc = self.dll.uncompress(out, C.byref(ol), self._p(comp), len(comp))
         return rc, (out.raw[:ol.value] if rc == 0 else b"")
 
+    def deflate_stream(self, data, level=6, wbits=15, strategy=0):
+        """deflateInit2 + deflate(Z_FINISH) + deflateEnd of the reference itself (for strategies and window sizes)."""
+        from zlib_b200.binding import z_stream, ZLIB_VERSION
+        d = self.dll
+        d.deflateInit2_.restype = C.c_int
+        d.deflateInit2_.argtypes = [C.POINTER(z_stream), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        d.deflate.restype, d.deflate.argtypes = C.c_int, [C.POINTER(z_stream), C.c_int]
+        d.deflateEnd.restype, d.deflateEnd.argtypes = C.c_int, [C.POINTER(z_stream)]
+        strm = z_stream()
+        assert d.deflateInit2_(C.byref(strm), level, 8, wbits, 8, strategy, ZLIB_VERSION, C.sizeof(z_stream)) == 0
+        n = len(data)
+        cap = n + (n >> 3) + 1024
+        src = C.create_string_buffer(bytes(data), n + 1)
+        out = C.create_string_buffer(cap)
+        strm.next_in, strm.avail_in = C.addressof(src), n
+        strm.next_out, strm.avail_out = C.addressof(out), cap
+        assert d.deflate(C.byref(strm), 4) == 1
+        z = out.raw[:strm.total_out]
+        assert d.deflateEnd(C.byref(strm)) == 0
+        return z
+
 
 def corpus(kind, n, seed=0):
     """Small deterministic test inputs (pure Python, independent of the product's generator)."""

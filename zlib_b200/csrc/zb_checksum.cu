@@ -138,6 +138,7 @@ constexpr size_t kMainSmem = 65536 + kTabImage + kRingHigh * 16384;   // 64 KiB 
 
 struct FoldArgs {                                               // per-launch constants of the combine, computed on the host
     uint32_t pw_stride[10];                                     // x^(8 * S * 2^k), S = bytes one CTA covers
+    uint32_t pw_warp[5];                                        // x^(8 * W * 2^k), W = bytes one warp covers
     uint32_t pw_last;                                           // x^(8 * D): from the end of the last full CTA to the end of the last CTA
     uint32_t pw_tail;                                           // x^(8 * (len - aligned end)): over the ragged tail
     uint32_t pw_head;                                           // x^(8 * (len - head)): from the end of the head bytes to the end
@@ -408,15 +409,29 @@ k_checksum_main(const uint8_t* __restrict__ base, uint64_t n_units, uint32_t ite
         uint32_t reg = 0, a = 0, b = 0;
         if (p.end) {
             const uint64_t suffix = cta_end - p.end;
-            reg = suffix ? gf2_mul(p.reg, pow8(suffix)) : p.reg;
             a = p.a;
             b = (p.b + (uint32_t)((suffix % kAdlerBase) * p.a % kAdlerBase)) % kAdlerBase;
         }
+        if (blockIdx.x + 1 < gridDim.x) {
+            // every warp of this CTA ran the full iters_per_warp: warp w ends (31 - w) * W bytes in front of the CTA's end, so the
+            // register at the CTA's end is a polynomial in Y = x^(8 W) -- five levels of one multiply with the host's Y^(2^k)
+            uint32_t u = __shfl_sync(0xffffffffu, p.reg, 31 - lane);      // u_q = warp 31 - q
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
+            for (int k = 0; k < 5; k++) {
+                const uint32_t hi = __shfl_down_sync(0xffffffffu, u, 1u << k);
+                if ((lane & ((2 << k) - 1)) == 0) u ^= gf2_mul(hi, fa.pw_warp[k]);
+            }
+            reg = u;                                            // lane 0 holds it
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        } else {                                                // the last CTA: ragged, one modular power per warp
+            if (p.end) { const uint64_t suffix = cta_end - p.end; reg = suffix ? gf2_mul(p.reg, pow8(suffix)) : p.reg; }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                reg ^= __shfl_xor_sync(0xffffffffu, reg, o);
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
         }
         if (lane == 0) {
             parts[blockIdx.x] = Partial{reg, a % kAdlerBase, b % kAdlerBase, 0, cta_end};
@@ -687,6 +702,7 @@ int checksum_launch(Ctx* c, const uint8_t* d_buf, size_t len, uint32_t* d_out2, 
     const uint64_t S = (uint64_t)kMainWarps * iters * kStride;
     fa.cta_bytes = S;
     for (int k = 0; k < 10; k++) fa.pw_stride[k] = host_pow8(S << k);
+    for (int k = 0; k < 5; k++) fa.pw_warp[k] = host_pow8(((uint64_t)iters * kStride) << k);
     const uint64_t aligned = n_units * kStride;
     fa.pw_last = host_pow8(aligned - (uint64_t)(blocks - 1) * S);
     fa.pw_tail = host_pow8(len - tail_begin);
