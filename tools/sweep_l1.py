@@ -28,12 +28,15 @@ for name, kind, n, seed in (("mixed1g", 1, 1 << 30, 1), ("text64m", 0, 64 << 20,
     del d, o
 print(json.dumps(out))
 ''' % ROOT
-configs = [{}, {"ZB200_WALK_PERSIST": "0"}]
-for chain in (1, 2, 3):
-    configs.append({"ZB200_L1_CHAIN": str(chain)})
-for nice in (6, 16, 32):
-    configs.append({"ZB200_L1_NICE": str(nice)})
-configs.append({"ZB200_L1_CHAIN": "2", "ZB200_L1_NICE": "16"})
+configs = [{}]
+if len(sys.argv) > 1 and sys.argv[1] == "link":
+    configs += [{"ZB200_LINK_SEG_CHUNKS": "1"}, {"ZB200_LINK_SEG_CHUNKS": "4"}]
+else:
+    configs += [{"ZB200_WALK_PERSIST": "0"}]
+    for chain in (1, 3, 4):
+        configs.append({"ZB200_L1_CHAIN": str(chain)})
+    for nice in (6, 16, 32):
+        configs.append({"ZB200_L1_NICE": str(nice)})
 for cfg in configs:
     env = dict(os.environ); env.update(cfg)
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=600)

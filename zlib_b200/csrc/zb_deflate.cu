@@ -112,7 +112,7 @@ __device__ __noinline__ uint2 ring_turn(uint32_t a0, uint32_t a1, uint32_t a2, u
 
 template <bool kExact>
 __global__ void __launch_bounds__(kLinkWarps * 32)
-k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict__ dist16, const ChunkDesc* __restrict__ cd)
+k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict__ dist16, const ChunkDesc* __restrict__ cd, uint32_t seg_bytes)
 {
     extern __shared__ uint16_t s_head[];                       // 2^15 entries: low 16 bits of the last position
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,8 +127,8 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
         seg_beg = d.beg; seg_end = (uint64_t)d.beg + d.len; origin = d.job_beg; lim = d.job_end;
         prime_beg = seg_beg - origin > kWindow ? seg_beg - kWindow : origin;
     } else {
-        seg_beg = (uint64_t)blockIdx.x * kChunk;
-        seg_end = min(total, seg_beg + kChunk);
+        seg_beg = (uint64_t)blockIdx.x * seg_bytes;             // stream mode: a CTA links seg_bytes (a few chunks: the 32 KiB of priming
+        seg_end = min(total, seg_beg + seg_bytes);              // in front of a segment is redundant work)
         prime_beg = seg_beg > kWindow ? seg_beg - kWindow : 0;
         origin = 0; lim = total;
     }
@@ -1482,11 +1482,12 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
         d_hist = c->ws[7].as<uint32_t>(); d_codes = c->ws[8].as<uint32_t>(); d_hdr = c->ws[9].as<uint32_t>();
         d_ntok = c->ws[10].as<uint32_t>();
         uint32_t* d_next = walk_persistent() ? d_ntok + nblocks : nullptr;   // the walk kernel's block counter
-        const unsigned nseg = (unsigned)((total + kChunk - 1) / kChunk);
+        static const uint32_t link_seg = kChunk * (uint32_t)std::max(1, env_int("ZB200_LINK_SEG_CHUNKS", 2));
+        const unsigned nseg = (unsigned)((total + link_seg - 1) / link_seg);
         if (cfg.chain != 0 && P.strategy != 3) {                // Z_RLE needs no chains
-            // levels 1-3 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
-            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
-            else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr);
+            // levels 1-6 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
+            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr, link_seg);
+            else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr, link_seg);
         }
         const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
         const unsigned wgrid = walk_grid(nblocks, lazy_shape);
@@ -1546,8 +1547,8 @@ static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uin
         d_ntok = c->ws[10].as<uint32_t>();
         uint32_t* d_next = walk_persistent() ? d_ntok + nblocks : nullptr;   // the walk kernel's block counter
         if (cfg.chain != 0 && P.strategy != 3) {
-            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
-            else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd);
+            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd, kChunk);
+            else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd, kChunk);
         }
         const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
         const unsigned wgrid = walk_grid(nblocks, lazy_shape);

@@ -264,11 +264,8 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
     # and the exchange and the transfers run on a side stream, so nothing of them queues behind the next piece's kernels.
     pipelined = hasattr(lib, "deflate_shard_begin") and dev.type == "cuda"
     side = _side_stream(dev) if pipelined else None
-    # odd rounds run on a second compute stream, so that the tail of one piece (its last slabs, checksum, framing) and the
-    # head of the next overlap the way the slabs inside a piece do
-    alt = _side_stream(dev, 1) if pipelined and hasattr(stream, "wait_stream") else None
-    if alt is not None:
-        alt.wait_stream(stream)                                    # the inputs are ready where the caller's stream is now
+    # (running odd rounds on a second compute stream was tried: 14.75 -> 14.64 ms device resident at N = 2, but the host-buffer
+    # run lost 4 ms -- the two pieces' H2D copies then share the link and the first piece's D2H starts later)
     import contextlib
 
     def on_side():
@@ -278,8 +275,7 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
         src_ptr, n, dict_ptr, dict_len = pieces[j]
         last = last_round_is_last and j == rounds - 1 and rank == world - 1
         flags = zb.ZB200_DEFLATE_NO_HEADER | zb.ZB200_DEFLATE_NO_TRAILER | (0 if last else zb.ZB200_DEFLATE_NOT_LAST)
-        st = alt if (alt is not None and (j & 1)) else stream
-        return (src_ptr, n, dict_ptr if dict_len else None, dict_len, outs[j].data_ptr(), outs[j].numel(), level, zb.WRAP_RAW, flags, st)
+        return (src_ptr, n, dict_ptr if dict_len else None, dict_len, outs[j].data_ptr(), outs[j].numel(), level, zb.WRAP_RAW, flags, stream)
 
     jobs = {}
     if pipelined and rounds:
@@ -350,8 +346,6 @@ def deflate_rounds(lib, pieces, level: int = 1, wrap: int = zb.WRAP_ZLIB, group=
                     final[:len(header)] = torch.tensor(list(header), dtype=torch.uint8, device=dev)
                 if trailer:
                     final[pos:total] = torch.tensor(list(trailer), dtype=torch.uint8, device=dev)
-    if alt is not None:
-        stream.wait_stream(alt)
     if side is not None:
         torch.cuda.current_stream().wait_stream(side)              # the caller's stream sees the assembled stream
     if host_final is not None or peer_final is not None:
