@@ -1050,8 +1050,8 @@ def zip_config5(args, lib, zb, zdist, synth, dev, world, rank, have_ref, barrier
             rec[1:len(mine) + 1, 4] = m[:, 3] & 0xFFFFFFFF
         allrec = torch.empty(world * (width + 1) * 5, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allrec, rec.to(dev).view(-1))
-        allrec = allrec.view(world, width + 1, 5).cpu()
-        seg_len = [int(allrec[r, 0, 0]) for r in range(world)]
+        allrec = allrec.view(world, width + 1, 5).cpu().tolist()         # plain lists: 10 000 members are walked below
+        seg_len = [int(allrec[r][0][0]) for r in range(world)]
         base = sum(seg_len[:rank])
         out["mine"] = (base, ol.value)
         lib._check(lib.dll.zb200_copy_async(shm_ptr + base, d_seg.data_ptr(), ol.value, None), "zb200_copy_async")
@@ -1061,7 +1061,7 @@ def zip_config5(args, lib, zb, zdist, synth, dev, world, rank, have_ref, barrier
             order, glob, b0 = [], [], 0
             for r in range(world):
                 for k in range(len(shares[r])):
-                    i, lo, cl, rl, crc = (int(v) for v in allrec[r, k + 1])
+                    i, lo, cl, rl, crc = allrec[r][k + 1]
                     order.append(names[i].decode())
                     glob.append((b0 + lo, cl, rl, crc))
                 b0 += seg_len[r]

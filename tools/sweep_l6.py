@@ -24,7 +24,7 @@ for name, kind, n, seed in (("mixed256m", 1, 256 << 20, 1), ("text64m", 0, 64 <<
     del d, o
 print(json.dumps(out))
 ''' % ROOT
-for cfg in ({}, {"ZB200_L6_CHAIN": "96"}, {"ZB200_L6_CHAIN": "64"}, {"ZB200_L6_CHAIN": "32"}):
+for cfg in ({}, {"ZB200_LAZY_GLOBAL_MAX": "64"}, {"ZB200_L6_CHAIN": "24"}, {"ZB200_L6_CHAIN": "24", "ZB200_LAZY_GLOBAL_MAX": "64"}, {"ZB200_L6_CHAIN": "16"}):
     env = dict(os.environ); env.update(cfg)
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=600)
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:]

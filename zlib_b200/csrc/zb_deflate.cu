@@ -1440,6 +1440,8 @@ static int walk_flat_lazy(int chain) { static const int force = env_int("ZB200_L
 // exact intra-step links (MATCH.ANY, 8.4 ms per GiB) for the levels that search long chains; levels 1..6 take the relaxed
 // links (3.1 ms per GiB, ~0.1 % larger output)
 static bool link_exact(int level, int strategy) { static const int force = env_int("ZB200_LINK_EXACT", -1); return force >= 0 ? force != 0 : (level >= 7 || (level >= 4 && strategy == 4)); }
+// lazy levels whose chain budget is at most this run in the greedy shape (links from L2, 3 CTAs per SM); development knob
+static int lazy_global_max() { static const int v = env_int("ZB200_LAZY_GLOBAL_MAX", 0); return v; }
 static bool walk_persistent() { static const bool on = env_int("ZB200_WALK_PERSIST", 1) != 0; return on; }
 static unsigned walk_grid(uint64_t nblocks, bool lazy_shape)
 {
@@ -1489,7 +1491,7 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
             if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr, link_seg);
             else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr, link_seg);
         }
-        const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
+        const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3 && (int)cfg.chain > lazy_global_max();
         const unsigned wgrid = walk_grid(nblocks, lazy_shape);
         if (d_next) ZB_CUDA(cudaMemsetAsync(d_next, 0, 4, s));
         if (lazy_shape)
@@ -1550,7 +1552,7 @@ static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uin
             if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd, kChunk);
             else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd, kChunk);
         }
-        const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3;
+        const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3 && (int)cfg.chain > lazy_global_max();
         const unsigned wgrid = walk_grid(nblocks, lazy_shape);
         if (d_next) ZB_CUDA(cudaMemsetAsync(d_next, 0, 4, s));
         if (lazy_shape)

@@ -499,8 +499,8 @@ def zip_sharded(lib, names: Sequence[str], datas: Sequence[bytes], level: int = 
     rec = rec.to(dev).view(-1)
     allrec = torch.empty(world * (width + 1) * 5, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(allrec, rec, group=group)
-    allrec = allrec.view(world, width + 1, 5).cpu()
-    seg_len = [int(allrec[r, 0, 0]) for r in range(world)]
+    allrec = allrec.view(world, width + 1, 5).cpu().tolist()
+    seg_len = [int(allrec[r][0][0]) for r in range(world)]
     seg_t = torch.frombuffer(bytearray(seg), dtype=torch.uint8).to(dev) if seg else torch.empty(0, dtype=torch.uint8, device=dev)
     if rank != root:
         if len(seg):
@@ -517,7 +517,7 @@ def zip_sharded(lib, names: Sequence[str], datas: Sequence[bytes], level: int = 
         else:
             parts.append(b"")
         for k in range(len(shares[r])):
-            i, lo, cl, rl, crc = (int(v) for v in allrec[r, k + 1])
+            i, lo, cl, rl, crc = allrec[r][k + 1]
             order.append(names[i])
             glob.append((base + lo, cl, rl, crc))
         base += seg_len[r]
