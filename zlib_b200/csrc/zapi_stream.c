@@ -696,8 +696,16 @@ ZAPI int inflateSync(z_streamp strm)                            /* inflate.c:126
     /* bytes the stream already holds are searched first, then the caller's */
     {
         size_t pn = zb200i_inflate_pending_input(s->inf);
-        if (pn) syncsearch(&have, zb200i_inflate_pending_bytes(s->inf), (unsigned)pn);
-        if (have == 4) have = 0;      /* a marker wholly inside held bytes cannot be re-positioned; keep searching */
+        if (pn) {
+            unsigned at = syncsearch(&have, zb200i_inflate_pending_bytes(s->inf), (unsigned)pn);
+            if (have == 4) {                                    /* the marker lies inside held bytes: decoding resumes right behind it */
+                in = strm->total_in; out = strm->total_out;
+                if (zb200i_inflate_resync_keep(s->inf, at) != 0) return Z_STREAM_ERROR;
+                strm->total_in = in; strm->total_out = out;
+                s->inf_bad = 0; s->inf_done = 0;
+                return Z_OK;
+            }
+        }
     }
     used = syncsearch(&have, strm->next_in, strm->avail_in);
     strm->avail_in -= used; strm->next_in += used; strm->total_in += used;

@@ -40,6 +40,8 @@ int  zb200i_inflate_run(zb200i_inflater *h, const uint8_t *in, size_t in_len, ui
 int  zb200i_inflate_set_dict(zb200i_inflater *h, const uint8_t *dict, size_t n);
 /* Drops buffered input and restarts block decoding (after inflateSync found a marker). */
 int  zb200i_inflate_resync(zb200i_inflater *h);
+/* The same when the marker ends `drop` bytes into the input the stream already holds: those bytes go, the rest stays. */
+int  zb200i_inflate_resync_keep(zb200i_inflater *h, size_t drop);
 /* inflatePrime: bits (<= 16) of value go ahead of the next input byte; only with no input pending. */
 int  zb200i_inflate_prime(zb200i_inflater *h, int bits, int value);
 int  zb200i_inflate_mode(const zb200i_inflater *h);         /* InfMode of the device state */

@@ -1722,6 +1722,16 @@ extern "C" int zb200i_inflate_set_dict(zb200i_inflater* h, const uint8_t* dict, 
     return 0;
 }
 
+extern "C" int zb200i_inflate_resync_keep(zb200i_inflater* h, size_t drop)
+{
+    // as below, but the marker was found INSIDE bytes the stream already holds: what follows it stays queued
+    std::vector<uint8_t> rest;
+    if (drop < h->carry.size()) rest.assign(h->carry.begin() + drop, h->carry.end());
+    const int rc = zb200i_inflate_resync(h);
+    if (rc == 0) h->carry.swap(rest);
+    return rc;
+}
+
 extern "C" int zb200i_inflate_resync(zb200i_inflater* h)
 {
     // inflate.c:1294-1301: keep totals, restart at a block boundary with an empty bit buffer
