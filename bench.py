@@ -403,7 +403,7 @@ def traffic_of(kernel):
     sha = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16]
     if t.get("_source_sha16") != sha:
         return None, "stale: zb_deflate.cu changed since the ncu capture in profiles/traffic.json"
-    names = {re.sub(r"<.*>|[()]|zb::", "", k).strip(): v for k, v in t.items() if not k.startswith("_")}
+    names = {re.sub(r"<.*>|[()]|zb::|^void ", "", k).strip(): v for k, v in t.items() if not k.startswith("_")}
     return names.get(kernel), "ncu --set full capture of this source (profiles/traffic.json)"
 
 
