@@ -282,3 +282,44 @@ def test_large_pageable_source_goes_through_the_staging_threads(gpu_lib):
     assert out.raw[:ol.value] == z
     rc, back = gpu_lib.uncompress(z, n)
     assert rc == zb.Z_OK and back == data.tobytes()
+
+
+def test_shard_in_two_halves_pipelines_pieces(gpu_lib, oracle):
+    """zb200_deflate_shard_begin / _end: piece j + 1 is enqueued before piece j is read back (what the multi-GPU rounds
+    do); the pieces, each primed with the 32 KiB in front of it, concatenate into one raw stream the oracle decodes."""
+    import ctypes as C
+    import numpy as np
+    n = (9 << 20) + 4321
+    data = gpu_lib.synth(n, kind=1, seed=33)
+    cuts = [0, 3 << 20, (3 << 20) + 131072, 7 << 20, n]               # chunk-aligned piece boundaries
+    cap = gpu_lib.compress_bound(4 << 20) + 64
+    outs = [np.zeros(cap, dtype=np.uint8) for _ in range(4)]
+    base = data.ctypes.data
+    jobs, res = {}, []
+
+    def begin(j):
+        a, b = cuts[j], cuts[j + 1]
+        dl = min(a, 32768)
+        flags = zb.ZB200_DEFLATE_NO_HEADER | zb.ZB200_DEFLATE_NO_TRAILER | (0 if j == 3 else zb.ZB200_DEFLATE_NOT_LAST)
+        return gpu_lib.deflate_shard_begin(base + a, b - a, (base + a - dl) if dl else None, dl, outs[j], cap, 6, zb.WRAP_RAW, flags)
+    jobs[0] = begin(0)
+    for j in range(4):
+        if j + 1 < 4:
+            jobs[j + 1] = begin(j + 1)
+        res.append(gpu_lib.deflate_shard_end(jobs.pop(j)))
+    raw = b"".join(bytes(outs[j][:res[j][0]]) for j in range(4))
+    rc, out, used = oracle.inflate(raw, n, 0)
+    assert rc == 0 and out == data.tobytes() and used == len(raw)
+    crc = 0
+    for j in range(4):
+        crc = gpu_lib.crc32_combine(crc, res[j][1], cuts[j + 1] - cuts[j])
+    assert crc == oracle.crc32(data)
+    # device buffers, both halves on a caller's stream
+    import torch
+    d = torch.from_numpy(data).cuda()
+    o = torch.empty(cap * 3, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    job = gpu_lib.deflate_shard_begin(d.data_ptr(), n, None, 0, o.data_ptr(), o.numel(), 1, zb.WRAP_ZLIB, 0, s)
+    clen, c32, a32 = gpu_lib.deflate_shard_end(job)
+    rc, out, _ = oracle.inflate(bytes(o[:clen].cpu().numpy()), n)
+    assert rc == 0 and out == data.tobytes() and c32 == oracle.crc32(data) and a32 == oracle.adler32(data)
