@@ -1162,7 +1162,8 @@ __global__ void k_frame_jobs(uint8_t* __restrict__ out, const JobDesc* __restric
 // K3: bit packing
 // ------------------------------------------------------------------------------------------
 constexpr int kPackThreads = 256;
-constexpr int kStageWords = (kPackThreads * 96 + 64) / 32 + 4;  // two symbols of <= 48 bits per thread and round
+constexpr int kPackRun = 8;                                     // consecutive symbols of a block that one thread encodes per round
+constexpr int kStageWords = (kPackThreads * kPackRun * 48 + 64) / 32 + 4;   // kPackRun symbols of <= 48 bits per thread and round
 
 struct Packer {
     uint32_t* stage;                                            // two shared staging windows, used alternately; bit 0 of the
@@ -1183,15 +1184,11 @@ struct Packer {
         if (sh) { const uint32_t hi = (uint32_t)(value >> (64 - sh)); if (hi) atomicOr(&st[wi + 2], hi); }
     }
 
-    // Every thread contributes two symbols (value, nbits <= 48 each); bits are appended in thread order, a thread's
-    // first symbol before its second.  Two barriers per round: the window written in this round is drained after
-    // the second one, and the other window (drained one round ago) is cleared for the next round meanwhile.
-    __device__ void round(uint64_t v0, uint32_t n0, uint64_t v1 = 0, uint32_t n1 = 0)
+    // Where this thread's `nbits` start in the current window (bits are appended in thread order) and how many bits the
+    // CTA adds in this round.  One barrier.
+    __device__ __forceinline__ uint32_t place(uint32_t nbits, uint32_t& total)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        uint32_t* cur = stage + par * kStageWords;
-        uint32_t* oth = stage + (par ^ 1u) * kStageWords;
-        const uint32_t nbits = n0 + n1;
         uint32_t x = nbits;
 #pragma unroll
         for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(kFullMask, x, k); if (lane >= k) x += y; }
@@ -1202,21 +1199,81 @@ struct Packer {
         uint32_t ws = warp_sums[lane & 7];
 #pragma unroll
         for (int k = 1; k < 8; k <<= 1) { const uint32_t y = __shfl_up_sync(kFullMask, ws, k, 8); if ((lane & 7) >= k) ws += y; }
-        const uint32_t total = __shfl_sync(kFullMask, ws, 7);
+        total = __shfl_sync(kFullMask, ws, 7);
         const uint32_t upto = __shfl_sync(kFullMask, ws, warp ? warp - 1 : 0);
-        const uint32_t before = warp ? upto : 0u;
-        const uint32_t off = carry_bits + before + x - nbits;
-        if (n0) put(cur, off, v0);
-        if (n1) put(cur, off + n0, v1);
+        return carry_bits + (warp ? upto : 0u) + x - nbits;
+    }
+
+    // Second barrier of a round: the window written in this round goes out -- bytes up to the output's next 4-byte
+    // boundary, whole words (read across two window words), the last bytes -- and the other window (drained one round
+    // ago) is cleared for the next round meanwhile.
+    __device__ __forceinline__ void finish(uint32_t total)
+    {
+        uint32_t* cur = stage + par * kStageWords;
+        uint32_t* oth = stage + (par ^ 1u) * kStageWords;
         __syncthreads();
         const uint32_t tbits = carry_bits + total, nbytes = tbits >> 3;
         const uint8_t* sb = reinterpret_cast<const uint8_t*>(cur);
-        for (uint32_t i = threadIdx.x; i < nbytes; i += kPackThreads) dst[bytepos + i] = sb[i];
+        uint8_t* d = dst + bytepos;
+        const uint32_t head = min(nbytes, (0u - (uint32_t)reinterpret_cast<uintptr_t>(d)) & 3u);
+        if (threadIdx.x < head) d[threadIdx.x] = sb[threadIdx.x];
+        const uint32_t nw = (nbytes - head) >> 2;
+        for (uint32_t i = threadIdx.x; i < nw; i += kPackThreads) {
+            const uint32_t bo = head + 4 * i;
+            *reinterpret_cast<uint32_t*>(d + bo) = __funnelshift_r(cur[bo >> 2], cur[(bo >> 2) + 1], (bo & 3u) * 8);
+        }
+        const uint32_t done = head + 4 * nw;
+        if (threadIdx.x < nbytes - done) d[done + threadIdx.x] = sb[done + threadIdx.x];
         const uint32_t tail = (tbits & 7) ? sb[nbytes] : 0u;
         for (uint32_t i = threadIdx.x; i < prev_words; i += kPackThreads) oth[i] = i == 0 ? tail : 0u;   // word 0 carries the pending bits over
-        prev_words = min((tbits + 31) / 32 + 1, (uint32_t)kStageWords);
+        prev_words = min((tbits + 31) / 32 + 2, (uint32_t)kStageWords);
         bytepos += nbytes; carry_bits = tbits & 7;
         par ^= 1;
+    }
+
+    // Every thread contributes two symbols (value, nbits <= 48 each); bits are appended in thread order, a thread's
+    // first symbol before its second.  Used for headers, stored blocks and chunk ends.
+    __device__ void round(uint64_t v0, uint32_t n0, uint64_t v1 = 0, uint32_t n1 = 0)
+    {
+        uint32_t* cur = stage + par * kStageWords;
+        uint32_t total;
+        const uint32_t off = place(n0 + n1, total);
+        if (n0) put(cur, off, v0);
+        if (n1) put(cur, off + n0, v1);
+        finish(total);
+    }
+
+    // Every thread contributes kPackRun consecutive symbols (value <= 48 bits, length in the top byte of the word).  The
+    // thread strings them together in a 64-bit accumulator and hands out whole words: the first word it touches and the
+    // last are shared with its neighbours (shared-memory atomic OR), the words between are its own (plain stores).
+    __device__ void round_run(const uint64_t (&sym)[kPackRun])
+    {
+        uint32_t* cur = stage + par * kStageWords;
+        uint32_t nbits = 0;
+#pragma unroll
+        for (int k = 0; k < kPackRun; k++) nbits += (uint32_t)(sym[k] >> 56);
+        uint32_t total;
+        const uint32_t off = place(nbits, total);
+        uint32_t wi = off >> 5, fill = off & 31;
+        uint64_t acc = 0;
+        bool shared_word = true;
+        auto push = [&](uint32_t val, uint32_t nb) {            // nb <= 24, fill < 32 on entry and on exit
+            acc |= (uint64_t)val << fill;
+            fill += nb;
+            if (fill >= 32) {
+                if (shared_word) { atomicOr(&cur[wi], (uint32_t)acc); shared_word = false; }
+                else cur[wi] = (uint32_t)acc;
+                wi++; acc >>= 32; fill -= 32;
+            }
+        };
+#pragma unroll
+        for (int k = 0; k < kPackRun; k++) {
+            const uint32_t nb = (uint32_t)(sym[k] >> 56);
+            push((uint32_t)sym[k] & 0xffffffu, min(nb, 24u));
+            if (nb > 24) push((uint32_t)(sym[k] >> 24) & 0xffffffu, nb - 24);
+        }
+        if ((uint32_t)acc) atomicOr(&cur[wi], (uint32_t)acc);
+        finish(total);
     }
 };
 
@@ -1231,6 +1288,7 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
     __shared__ uint32_t s_stage[2][kStageWords];
     __shared__ uint32_t s_sums[kPackThreads / 32];
     __shared__ uint32_t s_codes[kHistSize];
+    __shared__ uint32_t s_len[256];                             // match length - 3 -> code and extra bits | their count << 24
     const uint64_t c = blockIdx.x;
     const uint64_t nchunks = gridDim.x;
     const ChunkMeta cm = chunks[c];
@@ -1300,6 +1358,13 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
         }
         ends_stored = false;
         for (int i = threadIdx.x; i < (int)kHistSize; i += kPackThreads) s_codes[i] = blk_codes[b * kHistSize + i];
+        __syncthreads();
+        {   // the length part of a match in one lookup (published by the barriers of the header round)
+            static_assert(kPackThreads == 256, "one thread per match length");
+            const uint32_t l = threadIdx.x, lc = len_code(l), le = len_extra_bits(lc);
+            const uint32_t e = s_codes[257 + lc];
+            s_len[l] = (e & 0xffffu) | ((l & ((1u << le) - 1u)) << (e >> 16)) | (((e >> 16) + le) << 24);
+        }
         {   // block header: 3 bits, then the serialised trees of a dynamic block
             const uint32_t hw = bm.type == 2 ? (bm.hdr_bits + 31) / 32 : 0;
             const uint32_t* hdr = blk_hdr + b * kHdrWords;
@@ -1313,37 +1378,36 @@ k_huff_pack(const uint8_t* __restrict__ src, uint64_t n, const uint32_t* __restr
         }
         const uint32_t* t = tok + b * kBlockBytes;
         const uint32_t cnt = blk_ntok[b];
-        auto encode = [&](uint32_t i, uint32_t tk, uint64_t& v, uint32_t& nb) {   // symbol i of the block: token, or end-of-block
-            v = 0; nb = 0;
+        auto encode = [&](uint32_t i, uint32_t tk) -> uint64_t {   // symbol i of the block: token, or end-of-block; bits | count << 56
             if (i < cnt) {
                 const uint32_t dist = tk >> 16;
                 if (dist == 0) {
                     const uint32_t e = s_codes[tk & 0xff];
-                    v = e & 0xffffu; nb = e >> 16;
-                } else {
-                    // length part (<= 20 bits) and distance part (<= 28 bits) are composed in 32 bits each, then joined once
-                    const uint32_t l = tk & 0xff, lc = len_code(l), le = len_extra_bits(lc);
-                    const uint32_t e = s_codes[257 + lc];
-                    const uint32_t lpart = (e & 0xffffu) | ((l & ((1u << le) - 1u)) << (e >> 16)), lbits = (e >> 16) + le;
-                    const uint32_t d = dist - 1, dc = dist_code(d), de = dist_extra_bits(dc);
-                    const uint32_t f = s_codes[288 + dc];
-                    const uint32_t dpart = (f & 0xffffu) | ((d & ((1u << de) - 1u)) << (f >> 16)), dbits = (f >> 16) + de;
-                    v = (uint64_t)lpart | ((uint64_t)dpart << lbits); nb = lbits + dbits;
+                    return (uint64_t)(e & 0xffffu) | ((uint64_t)(e >> 16) << 56);
                 }
-            } else if (i == cnt) {
-                const uint32_t e = s_codes[256];                // end of block
-                v = e & 0xffffu; nb = e >> 16;
+                // length part (<= 20 bits) from its table, distance part (<= 28 bits) composed in 32 bits, then joined once
+                const uint32_t le = s_len[tk & 0xff], lbits = le >> 24;
+                const uint32_t d = dist - 1, dc = dist_code(d), de = dist_extra_bits(dc);
+                const uint32_t f = s_codes[288 + dc];
+                const uint32_t dpart = (f & 0xffffu) | ((d & ((1u << de) - 1u)) << (f >> 16)), dbits = (f >> 16) + de;
+                return (uint64_t)(le & 0xffffffu) | ((uint64_t)dpart << lbits) | ((uint64_t)(lbits + dbits) << 56);
             }
+            if (i == cnt) {
+                const uint32_t e = s_codes[256];                // end of block
+                return (uint64_t)(e & 0xffffu) | ((uint64_t)(e >> 16) << 56);
+            }
+            return 0;
         };
-        for (uint32_t i0 = 0; i0 <= cnt; i0 += 2 * kPackThreads) {
-            const uint32_t i = i0 + 2 * threadIdx.x;
-            uint2 tk = make_uint2(0, 0);
-            if (i + 1 < cnt) tk = *reinterpret_cast<const uint2*>(t + i);   // the block's token array is 8-byte aligned
-            else if (i < cnt) tk.x = t[i];
-            uint64_t v0, v1; uint32_t n0, n1;
-            encode(i, tk.x, v0, n0);
-            encode(i + 1, tk.y, v1, n1);
-            pk.round(v0, n0, v1, n1);
+        static_assert(kPackRun == 8, "a thread's run is loaded as two 16-byte groups");
+        for (uint32_t i0 = 0; i0 <= cnt; i0 += kPackRun * kPackThreads) {
+            const uint32_t i = i0 + kPackRun * threadIdx.x;
+            uint4 ta = make_uint4(0, 0, 0, 0), tb = ta;         // the block's token array holds kBlockBytes slots: a group that starts below cnt lies inside it
+            if (i < cnt) ta = *reinterpret_cast<const uint4*>(t + i);
+            if (i + 4 < cnt) tb = *reinterpret_cast<const uint4*>(t + i + 4);
+            uint64_t sym[kPackRun];
+            sym[0] = encode(i, ta.x); sym[1] = encode(i + 1, ta.y); sym[2] = encode(i + 2, ta.z); sym[3] = encode(i + 3, ta.w);
+            sym[4] = encode(i + 4, tb.x); sym[5] = encode(i + 5, tb.y); sym[6] = encode(i + 6, tb.z); sym[7] = encode(i + 7, tb.w);
+            pk.round_run(sym);
         }
     }
     // end of chunk: partial flush -> empty static block, bits left as they fall; final -> pad; otherwise empty stored
