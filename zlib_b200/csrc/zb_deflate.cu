@@ -1510,7 +1510,8 @@ static bool walk_persistent() { static const bool on = env_int("ZB200_WALK_PERSI
 static unsigned walk_grid(uint64_t nblocks, bool lazy_shape)
 {
     if (!walk_persistent()) return (unsigned)nblocks;
-    const uint64_t slots = (uint64_t)device_sms() * (lazy_shape ? 1 : 3);
+    static const int per_sm = std::min(3, std::max(1, env_int("ZB200_WALK_CTAS_PER_SM", 3)));   // greedy shape: three fit; fewer leave room for the other slab's kernels
+    const uint64_t slots = (uint64_t)device_sms() * (lazy_shape ? 1 : per_sm);
     return (unsigned)std::min<uint64_t>(nblocks, slots);
 }
 static uint64_t walk_slots(uint64_t nblocks) { return walk_persistent() ? std::min<uint64_t>(nblocks, (uint64_t)device_sms() * 3) : nblocks; }
