@@ -51,6 +51,25 @@ def test_all_levels(gpu_lib, oracle):
     assert rc == 0 and len(z) == sizes[6]
 
 
+def test_level_ladder_against_the_reference(gpu_lib, ref):
+    """Every level: no larger than the reference's output at the SAME level (+2 %, gate (d)), sizes do not grow with the
+    level (0.1 % slack: the budgets are knees of a sweep, not a proof), and the reference decodes each stream."""
+    for kind, seed in ((0, 21), (1, 22)):
+        data = gpu_lib.synth(16 << 20, kind=kind, seed=seed)
+        raw = data.tobytes()
+        prev = None
+        for level in range(1, 10):
+            rc, z = gpu_lib.compress2(data, level)
+            assert rc == 0
+            want = len(ref.compress2(raw, level))
+            assert len(z) <= 1.02 * want, (kind, level, len(z), want)
+            if prev is not None:
+                assert len(z) <= 1.001 * prev, (kind, level, len(z), prev)
+            prev = len(z)
+            rc, out = ref.uncompress(z, len(raw))
+            assert rc == 0 and out == raw
+
+
 def test_reference_decodes_gpu_output(gpu_lib, oracle, ref):
     rng = random.Random(3)
     for t in range(20):

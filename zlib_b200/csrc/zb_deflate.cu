@@ -42,19 +42,21 @@
 
 namespace zb {
 
-// configuration_table (deflate.c:137-149) -- with ONE change: level 1 searches two candidates, not four.  The reference's
-// fast levels enter a position into the hash chains only where a token starts (and inside matches of at most
-// max_insert_length = 4 bytes, deflate.c:1510), so four steps down its sparse chain look a long way back; here every
-// position is linked (k_lz_link), so two steps already see as much, and every further step is one more dependent trip
-// to L2.  Measured on the config shapes (level 1, reference = the whole buffer as one stream): 1 GiB mixed 0.989 x the
-// reference's size at 13.8 ms instead of 0.980 x at 15.4 ms; 64 MiB text 0.997 x instead of 0.969 x (gate: <= 1.02 x).
-// Level 6 likewise stops after 32 candidates instead of 128 (good / lazy / nice as in the reference): 256 MiB mixed
-// 18.3 -> 10.5 ms with the output 0.55 % larger (0.975 x the reference's), 64 MiB text 5.6 -> 3.7 ms at 1.0046 x the
-// reference's size (profiles/r2_sweeps.md).  Levels 7..9 keep the reference's budgets.
+// configuration_table (deflate.c:137-149): good / lazy / nice as in the reference, and the same two parsers (greedy for
+// levels 1..3, lazy for 4..9), but NOT its chain budgets, because the chains are not the reference's: k_lz_link enters
+// every position (the reference's fast levels only enter token starts) and hashes FOUR bytes where the reference's
+// UPDATE_HASH covers MIN_MATCH = 3.  A chain over three bytes is mostly other strings that share three bytes: at level 1
+// two steps down such a chain found less than ONE step down a four-byte chain finds (256 MiB mixed: 134.8 MB at 3.40 ms
+// against 127.2 MB at 3.32 ms; the reference's level 1 writes 136.3 MB, its level 9 129.1 MB), and at level 6 eight
+// candidates of a four-byte chain beat 32 of a three-byte one (124.5 MB at 5.76 ms against 126.6 MB at 9.19 ms; reference
+// level 6: 129.5 MB).  What four bytes give up are the matches of exactly three bytes (found only where hashes collide);
+// the tables of profiles/r2_sweeps.md show what that costs: nothing, on these corpora.  The budgets below are the knees of
+// those sweeps -- every level writes less than the reference's level 9 on both corpora, sizes fall and times rise with
+// the level.  Z_FIXED and windowBits < 15 use the same chains.
 static const LevelCfg h_levels[10] = {
-    {0, 0, 0, 0, 0},      {4, 4, 8, 2, 1},       {4, 5, 16, 8, 1},     {4, 6, 32, 32, 1},
-    {4, 4, 16, 16, 2},    {8, 16, 32, 32, 2},    {8, 16, 128, 32, 2},  {8, 32, 128, 256, 2},
-    {32, 128, 258, 1024, 2}, {32, 258, 258, 4096, 2}};
+    {0, 0, 0, 0, 0},      {4, 4, 8, 1, 1},       {4, 5, 16, 2, 1},     {4, 6, 32, 3, 1},
+    {4, 4, 16, 4, 2},     {8, 16, 32, 5, 2},     {8, 16, 128, 8, 2},   {8, 32, 128, 16, 2},
+    {32, 128, 258, 48, 2}, {32, 258, 258, 192, 2}};
 
 constexpr uint32_t kFullMask = 0xffffffffu;
 constexpr int kHashBits = 15;
@@ -62,7 +64,7 @@ constexpr int kHashBits = 15;
 // ------------------------------------------------------------------------------------------
 // K1a: hash-chain links
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t hash3(uint32_t v) { return ((v & 0xffffffu) * 0x9E3779B1u) >> (32 - kHashBits); }
+__device__ __forceinline__ uint32_t hash3(uint32_t v, uint32_t mask) { return ((v & mask) * 0x9E3779B1u) >> (32 - kHashBits); }   // mask: three bytes (deflate.c UPDATE_HASH covers MIN_MATCH bytes), or four
 
 // Ring version: kLinkWarps warps share one segment and one head[] table.  Warp w owns tiles
 // w, w+W, w+2W, ... (a tile = 128 consecutive positions).  Everything that does not touch head[]
@@ -112,7 +114,7 @@ __device__ __noinline__ uint2 ring_turn(uint32_t a0, uint32_t a1, uint32_t a2, u
 
 template <bool kExact>
 __global__ void __launch_bounds__(kLinkWarps * 32)
-k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict__ dist16, const ChunkDesc* __restrict__ cd, uint32_t seg_bytes)
+k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict__ dist16, const ChunkDesc* __restrict__ cd, uint32_t seg_bytes, uint32_t hash_mask)
 {
     extern __shared__ uint16_t s_head[];                       // 2^15 entries: low 16 bits of the last position
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,7 +143,8 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
     const uint32_t nwords = (uint32_t)min((uint64_t)0x7fffffffu, ((mis + total + 3) >> 2) - tile_beg * 32);
     uint16_t* dout = dist16 + q0 - mis;                         // dout[q - q0] = link of position q - mis (never dereferenced below q_seg)
     const int q_lo = (int)(prime_beg + mis - q0);               // first position to insert
-    const int q_hi = (int)(min(seg_end, lim >= origin + 2 ? lim - 2 : origin) + mis) - (int)q0;   // one past the last hashable position
+    const uint32_t hbytes = hash_mask == 0xffffffffu ? 4u : 3u; // a position is entered only if all the bytes of its hash are the stream's own
+    const int q_hi = (int)(min(seg_end, lim >= origin + hbytes - 1 ? lim - (hbytes - 1) : origin) + mis) - (int)q0;   // one past the last hashable position
     const int q_seg = (int)(seg_beg + mis - q0), q_end = (int)(seg_end + mis - q0);   // positions whose link is stored
     const int p_cap = (int)min((uint64_t)0x40000000u, q0 - mis + 128 - origin) - 128;   // stream position of q0, saturated (only "dd > p" uses it)
     const uint32_t ntiles = (uint32_t)(tile_end - tile_beg);
@@ -167,7 +170,7 @@ k_lz_link(const uint8_t* __restrict__ buf, uint64_t total, uint16_t* __restrict_
             if (j == 31) wb = ext;
             const uint32_t v = __funnelshift_r(wa, wb, (li & 3) * 8);
             const bool valid = li >= lo && li < hi;
-            h[k] = valid ? hash3(v) : (0x10000u + lane);
+            h[k] = valid ? hash3(v, hash_mask) : (0x10000u + lane);
             if (kExact) {
                 const uint32_t grp = __match_any_sync(kFullMask, h[k]);
                 const uint32_t lower = grp & lt;
@@ -1505,6 +1508,11 @@ static int walk_flat_lazy(int chain) { static const int force = env_int("ZB200_L
 // links (3.1 ms per GiB, ~0.1 % larger output)
 static bool link_exact(int level, int strategy) { static const int force = env_int("ZB200_LINK_EXACT", -1); return force >= 0 ? force != 0 : (level >= 7 || (level >= 4 && strategy == 4)); }
 // lazy levels whose chain budget is at most this run in the greedy shape (links from L2, 3 CTAs per SM); development knob
+static uint32_t link_hash_mask(int level)                       // four hashed bytes from this level on (development: 10 = the reference's three everywhere)
+{
+    static const int from = env_int("ZB200_HASH4_FROM", 1);
+    return level >= from ? 0xffffffffu : 0xffffffu;
+}
 static int lazy_global_max() { static const int v = env_int("ZB200_LAZY_GLOBAL_MAX", 0); return v; }
 static bool walk_persistent() { static const bool on = env_int("ZB200_WALK_PERSIST", 1) != 0; return on; }
 static unsigned walk_grid(uint64_t nblocks, bool lazy_shape)
@@ -1553,8 +1561,8 @@ static int deflate_slab_launch(Ctx* c, const uint8_t* d_buf, uint64_t dict, uint
         const unsigned nseg = (unsigned)((total + link_seg - 1) / link_seg);
         if (cfg.chain != 0 && P.strategy != 3) {                // Z_RLE needs no chains
             // levels 1-6 trade the exact intra-step links for speed, like the reference's fast levels trade ratio
-            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr, link_seg);
-            else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr, link_seg);
+            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr, link_seg, link_hash_mask(P.level));
+            else ZB_LAUNCH(k_lz_link<false>, nseg, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_buf, total, d_dist, (const ChunkDesc*)nullptr, link_seg, link_hash_mask(P.level));
         }
         const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3 && (int)cfg.chain > lazy_global_max();
         const unsigned wgrid = walk_grid(nblocks, lazy_shape);
@@ -1614,8 +1622,8 @@ static int deflate_jobs_launch(Ctx* c, const uint8_t* d_base, uint64_t span, uin
         d_ntok = c->ws[10].as<uint32_t>();
         uint32_t* d_next = walk_persistent() ? d_ntok + nblocks : nullptr;   // the walk kernel's block counter
         if (cfg.chain != 0 && P.strategy != 3) {
-            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd, kChunk);
-            else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd, kChunk);
+            if (link_exact(P.level, P.strategy)) ZB_LAUNCH(k_lz_link<true>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd, kChunk, link_hash_mask(P.level));
+            else ZB_LAUNCH(k_lz_link<false>, nchunks, kLinkWarps * 32, (1 << kHashBits) * 2, s, d_base, span, d_dist, d_cd, kChunk, link_hash_mask(P.level));
         }
         const bool lazy_shape = cfg.kind == 2 && cfg.chain != 0 && P.strategy != 3 && (int)cfg.chain > lazy_global_max();
         const unsigned wgrid = walk_grid(nblocks, lazy_shape);
@@ -1720,10 +1728,14 @@ static int deflate_params(DeflateParams& P, int level, int wrap, int flags)
         if (nice1 > 0) P.cfg.nice = (uint16_t)nice1;
     }
     P.strategy = (flags >> 8) & 7;                              // Z_FILTERED 1, Z_HUFFMAN_ONLY 2, Z_RLE 3, Z_FIXED 4
+    {
+        static const int chain = env_int("ZB200_CHAIN", 0), nice = env_int("ZB200_NICE", 0);   // development: whichever level runs
+        if (chain > 0) P.cfg.chain = (uint16_t)chain;
+        if (nice > 0) P.cfg.nice = (uint16_t)nice;
+    }
     if (level == 6) {
         static const int chain6 = env_int("ZB200_L6_CHAIN", 0);
         if (chain6 > 0) P.cfg.chain = (uint16_t)chain6;
-        else if (P.strategy == 4) P.cfg.chain = 128;            // Z_FIXED keeps the reference's budget: a fixed code pays 5+ bits for every extra token
     }
     const int wbits = (flags >> 12) & 15;                       // 0 = 15; deflate.c:270-279, h/deflate.h:276
     P.max_dist = (wbits >= 9 && wbits < 15) ? (1u << wbits) - 262u : kWindow;
