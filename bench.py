@@ -42,7 +42,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "deflate_level1_GBps_uncompressed"
 UNIT = "GB/s"
-PIECES_PER_RANK = 2                    # rounds of the multi-GPU run (512 MiB pieces at 1 GiB per GPU; measured 2 / 4 / 8: 15.2 / 15.9 / 16.2 ms at N = 2)
+ROUND_SHARES = (0.5, 0.375, 0.125)    # rounds of the multi-GPU run as shares of a rank's input: only the LAST round's transfer into rank 0 is exposed
+                                      # (N = 2, same box: 13.39 ms / e2e 74.6 GB/s; 0.75,0.25: 13.34 / 74.0; 0.625,0.375: 13.25 / 72.7; one round: 13.47 / 65.8)
 WINDOW = 32768
 PRE = 65536                            # bytes generated in front of a piece (the corpus generator works in 64 KiB pages)
 
@@ -416,7 +417,7 @@ def main():
     ap.add_argument("--impl", default="zb200", choices=["zb200", "reference"])
     ap.add_argument("--size-mib", type=int, default=1024)
     ap.add_argument("--pieces", default="", help="rounds per rank of the multi-GPU run: a count, or fractions of a rank's share "
-                    "such as 0.5,0.375,0.125 (default: 2 equal rounds below 4 GPUs, 0.5,0.375,0.125 from 4 GPUs on)")
+                    "such as 0.5,0.375,0.125 (default: 0.5,0.375,0.125)")
     ap.add_argument("--no-extra", action="store_true", help="skip level 6 / inflate / checksum / zip side measurements")
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
@@ -448,7 +449,7 @@ def main():
     elif args.pieces:
         rounds = tuple(float(x) for x in args.pieces.split(",")) if "," in args.pieces else max(1, int(args.pieces))
     else:                                                    # the last round's transfer to rank 0 is the exposed one: keep it small where it is large
-        rounds = PIECES_PER_RANK if world < 4 else (0.5, 0.375, 0.125)
+        rounds = ROUND_SHARES
     ranges = zdist.piece_ranges(total, world, rounds)[rank]
     P = len(ranges)
     log(f"[rank {rank}] generating {args.size_mib} MiB of the {total >> 20} MiB mixed corpus ({len(ranges)} piece(s))")
