@@ -26,7 +26,7 @@ for name, kind, n, seed in (("mixed256m", 1, 256 << 20, 1), ("text64m", 0, 64 <<
     del d, o
 print(json.dumps(out))
 ''' % ROOT
-arg = sys.argv[1]
+arg = sys.argv[1] if len(sys.argv) > 1 else json.dumps([[l, {}] for l in range(1, 10)])   # a JSON list, @file, or every level at its defaults
 for level, cfg in json.load(open(arg[1:])) if arg.startswith("@") else json.loads(arg):
     env = dict(os.environ); env.update({k: str(v) for k, v in cfg.items()})
     r = subprocess.run([sys.executable, "-c", CHILD, str(level)], env=env, capture_output=True, text=True, timeout=600)
