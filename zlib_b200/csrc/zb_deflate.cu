@@ -1513,7 +1513,10 @@ static uint32_t link_hash_mask(int level)                       // four hashed b
     static const int from = env_int("ZB200_HASH4_FROM", 1);
     return level >= from ? 0xffffffffu : 0xffffffu;
 }
-static int lazy_global_max() { static const int v = env_int("ZB200_LAZY_GLOBAL_MAX", 0); return v; }
+// Lazy levels whose chain budget is at most this run in the greedy shape (links from L2, 64-byte sub-units, 3 CTAs per SM): with
+// the short budgets of the four-byte chains the few link loads per search no longer pay for staging the links in shared memory
+// (levels 4..7: 5 to 12 % faster and 0.1 % smaller, profiles/r2_sweeps.md).  Longer chains (levels 8, 9) keep the shared-memory links.
+static int lazy_global_max() { static const int v = env_int("ZB200_LAZY_GLOBAL_MAX", 16); return v; }
 static bool walk_persistent() { static const bool on = env_int("ZB200_WALK_PERSIST", 1) != 0; return on; }
 static unsigned walk_grid(uint64_t nblocks, bool lazy_shape)
 {
